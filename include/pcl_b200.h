@@ -1,0 +1,141 @@
+/*
+ * pcl_b200.h — C ABI of the B200-native point-cloud operator library (libpcl_b200.so).
+ *
+ * This is the drop-in boundary for the set-abstraction / EdgeConv hot path of
+ * Jittor/PointCloudLib.  The reference has no C ABI of its own: its operator interface is
+ * Jittor's  jt.code(shapes, dtypes, inputs, cuda_src=...)  (misc/ops.py:278, :376-381, :656-662),
+ * i.e. "raw device pointers + shapes in, raw device pointers out, launched on a stream".  Every
+ * entry point below is exactly that, as a plain C function, and cites the reference code it
+ * replaces.  The host side (pointcloudlib_b200/misc/ops.py, a mirror of the reference's
+ * misc/ops.py module API) binds these with ctypes; INTEGRATION.md shows the stub a reference
+ * maintainer would add.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer owned by the caller (contiguous, row-major, fp32 /
+ *     int32) unless the name ends in _host; the library never allocates, frees or
+ *     synchronises (contrast misc/ops.py:238-251: cudaMallocManaged + cudaDeviceSynchronize
+ *     + cudaFree per call);
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it and the call returns;
+ *   - return value: 0 = PCL_OK; < 0 = argument error (nothing launched); > 0 = cudaError_t.
+ *     pcl_last_error() returns a thread-local message for the last non-zero return;
+ *   - re-entrant; no global mutable state except idempotent cudaFuncSetAttribute calls.
+ */
+#ifndef PCL_B200_H
+#define PCL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCL_OK 0
+#define PCL_ERR_INVALID_ARG (-1)
+#define PCL_ERR_UNSUPPORTED (-2)
+#define PCL_ERR_WORKSPACE (-3)
+
+const char *pcl_last_error(void);
+/* library version (major*10000 + minor*100 + patch) and the SM arch it was compiled for (100) */
+int pcl_version(void);
+int pcl_compiled_arch(void);
+
+/* ---- a1 / a2: FurthestPointSampler (misc/ops.py:110-111, :114-286) -------------------------
+ * xyz (B,N,3) -> idx (B,M) int32, idx[:,0] = 0; points with |p|^2 <= 1e-3 are never selected
+ * (ops.py:162-163).  `ref_block_size` is the reference's threads-per-block, optimal_block(B)
+ * (ops.py:110-111): it is part of the result because the reference's shared-memory tree
+ * reduce (ops.py:116-122,176-229) breaks ties between equal maxima by thread id (winner =
+ * smallest bit-reversed (k mod ref_block_size), then lowest k).  Power of two in [1, 512]. */
+int pcl_optimal_block(int batch_size);
+int pcl_fps(const float *xyz, int B, int N, int M, int ref_block_size, int32_t *idx,
+            void *stream);
+/* new_xyz (B,M,3) = xyz[b, idx[b,m], :]   (the reindex at ops.py:280-284) */
+int pcl_gather_xyz(const float *xyz, const int32_t *idx, int B, int N, int M, float *out,
+                   void *stream);
+
+/* ---- a13: PointConv farthest_point_sample (misc/pointconv_utils.py:74-116) -----------------
+ * start (B) int32 = first index per cloud (the reference draws np.random.randint, :88);
+ * dist = (dx*dx + dy*dy) + dz*dz without contraction; argmax = first maximum; no origin skip. */
+int pcl_fps_pointconv(const float *xyz, int B, int N, int npoint, const int32_t *start,
+                      int32_t *idx, void *stream);
+
+/* ---- a3: BallQueryGrouper (misc/ops.py:289-407) ---------------------------------------------
+ * pcl_ball_query: kernel at ops.py:291-330.  idx (B,S,nsample), cnt (B,S) = min(hits,nsample).
+ * First nsample indices with d2 < radius*radius in index order, padded with the first hit; a
+ * row with no hit is all zeros with cnt 0 (uninitialised memory in the reference). */
+int pcl_ball_query(const float *new_xyz, const float *xyz, int B, int N, int S, float radius,
+                   int nsample, int32_t *idx, int32_t *cnt, void *stream);
+/* pcl_group: the two reindex gathers + centre subtraction + concat at ops.py:383-405.
+ * out (B,S,ns,(use_xyz?3:0)+C), xyz channels first; feat may be NULL (C = 0). */
+int pcl_group(const float *new_xyz, const float *xyz, const float *feat, const int32_t *idx,
+              int B, int N, int S, int ns, int C, int use_xyz, float *out, void *stream);
+/* pcl_ball_query_group: both of the above in ONE kernel (idx stays in shared memory between the
+ * query and the gather); idx/cnt are still written (autograd needs idx).  This is the
+ * "ballquery+group" kernel of BASELINE.json's metric. */
+int pcl_ball_query_group(const float *new_xyz, const float *xyz, const float *feat, int B, int N,
+                         int S, float radius, int nsample, int C, int use_xyz, int32_t *idx,
+                         int32_t *cnt, float *out, void *stream);
+/* backward of pcl_group w.r.t. feat: dfeat[b, idx[b,s,l], c] += dout[b,s,l,off+c] (dfeat must be
+ * zeroed by the caller); off = use_xyz?3:0. */
+int pcl_group_backward(const float *dout, const int32_t *idx, int B, int N, int S, int ns, int C,
+                       int use_xyz, float *dfeat, void *stream);
+
+/* ---- a11: index_points (misc/ops.py:12-27, :706-723; pointconv_utils.py:55-72) --------------
+ * out[b,s,:] = points[b, idx[b,s], :]; idx flattened to (B,S).  Backward = scatter-add. */
+int pcl_index_points(const float *points, const int32_t *idx, int B, int N, int S, int C,
+                     float *out, void *stream);
+int pcl_index_points_backward(const float *dout, const int32_t *idx, int B, int N, int S, int C,
+                              float *dpoints, void *stream);
+
+/* ---- a6: KNN (misc/ops.py:422-663) -----------------------------------------------------------
+ * x_r (B,C,Nr) reference set, x_q (B,C,Nq) queries, channels-first; idx (B,k,Nq) int32, k-major,
+ * indices into x_r, ascending by (distance, index).  Distances are the sequential fma chain
+ * over c of ops.py:488-491; never written to memory (the reference round-trips (B,Nr,Nq)).
+ * 1 <= k <= min(Nr, 256). */
+int pcl_knn(const float *x_r, const float *x_q, int B, int C, int Nr, int Nq, int k,
+            int32_t *idx, void *stream);
+
+/* ---- a9: square_distance (misc/ops.py:30-51) — matmul form, materialised (B,N,M) ------------- */
+int pcl_square_distance(const float *src, const float *dst, int B, int N, int M, int C,
+                        float *out, void *stream);
+
+/* ---- a10: knn_point (misc/ops.py:726-737, pointconv_utils.py:120-131) -----------------------
+ * xyz (B,N,C), new_xyz (B,S,C) channels-last; idx (B,S,nsample) ascending by (matmul-form
+ * distance, index); dist_out optional (may be NULL).  1 <= nsample <= min(N,256), C <= 16. */
+int pcl_knn_point(int nsample, const float *xyz, const float *new_xyz, int B, int N, int S, int C,
+                  int32_t *idx, float *dist_out, void *stream);
+
+/* ---- a12: three_nn / three_interpolate inlined at misc/ops.py:86-93 ------------------------
+ * xyz1 (B,N,3) targets, xyz2 (B,S,3) sources, S >= 3.  idx (B,N,3), dist (B,N,3) (may be NULL),
+ * weight (B,N,3) = (1/(d+1e-8)) / sum. */
+int pcl_three_nn(const float *xyz1, const float *xyz2, int B, int N, int S, int32_t *idx,
+                 float *dist, float *weight, void *stream);
+/* out (B,N,D) = sum_j points2[b, idx[b,n,j], :] * weight[b,n,j] */
+int pcl_three_interpolate(const float *points2, const int32_t *idx, const float *weight, int B,
+                          int N, int S, int D, float *out, void *stream);
+/* dpoints2 (B,S,D) += weight * dout (dpoints2 zeroed by the caller) */
+int pcl_three_interpolate_backward(const float *dout, const int32_t *idx, const float *weight,
+                                   int B, int N, int S, int D, float *dpoints2, void *stream);
+
+/* ---- a7: get_graph_feature (networks/cls/dgcnn.py:29-50) -------------------------------------
+ * x (B,C,N) channels-first, idx (B,k,N) k-major (the KNN output, un-permuted);
+ * out (B,2C,N,k): out[b,c,n,j] = x[b,c,idx[b,j,n]] - x[b,c,n]; out[b,C+c,n,j] = x[b,c,n]. */
+int pcl_graph_feature(const float *x, const int32_t *idx, int B, int C, int N, int k, float *out,
+                      void *stream);
+/* dx (B,C,N) (zeroed by the caller) += scatter of dout through both halves */
+int pcl_graph_feature_backward(const float *dout, const int32_t *idx, int B, int C, int N, int k,
+                               float *dx, void *stream);
+
+/* ---- a15: compute_density (misc/pointconv_utils.py:174-184) -------------------------------- */
+int pcl_compute_density(const float *xyz, int B, int N, float bandwidth, float *out, void *stream);
+
+/* ---- DP / optimizer plumbing on the flat parameter bucket (train_cls.py:72 optimizer.step) --
+ * SGD with momentum + weight decay over a flat fp32 bucket: g += wd*p; m = mu*m + g; p -= lr*m;
+ * grad_scale multiplies g first (1/world_size after the NCCL all-reduce). */
+int pcl_sgd_momentum(float *param, const float *grad, float *momentum_buf, size_t n, float lr,
+                     float mu, float weight_decay, float grad_scale, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCL_B200_H */

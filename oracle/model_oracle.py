@@ -1,0 +1,158 @@
+"""Literal torch-CPU restatement of the reference's module graphs (TEST INFRASTRUCTURE ONLY).
+
+Each function follows the reference's op sequence line by line — materialised gathers, the two
+transposes, 1x1 Conv -> BatchNorm(train) -> ReLU on (B,C,S,ns), max over dim 2 — with the index
+ops taken from the C oracle (oracle/pcl_oracle.c).  Parameters are read from a CPU copy of the
+product model (same state-dict structure as the reference's), so the product's fused / re-ordered
+arithmetic is checked against the reference's own order of operations.
+
+PARITY UNPINNED for the dense layers: Conv/BatchNorm numerics live in Jittor (un-vendored, no
+version pinned); BatchNorm(train) is taken as biased batch statistics, eps 1e-5.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+import oracle
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def index_points_t(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """misc/ops.py:12-27 with torch fancy indexing (differentiable)."""
+    B = points.shape[0]
+    view_shape = [B] + [1] * (idx.dim() - 1)
+    batch_indices = torch.arange(B).view(view_shape).expand_as(idx)
+    return points[batch_indices, idx.long(), :]
+
+
+def furthest_point_sampler(x: torch.Tensor, n_samples: int) -> torch.Tensor:
+    """misc/ops.py:257-286."""
+    idx = _t(oracle.fps(x.detach().numpy(), n_samples))
+    return index_points_t(x, idx)
+
+
+def ball_query_grouper(new_xyz, pointset, feature, radius, n_samples, use_xyz):
+    """misc/ops.py:345-407."""
+    idx, _ = oracle.ball_query(new_xyz.detach().numpy(), pointset.detach().numpy(),
+                               float(str(radius)), n_samples)
+    idx = _t(idx)
+    new_pointset = index_points_t(pointset, idx)                      # (B,S,ns,3)
+    new_feature = index_points_t(feature, idx) if feature is not None else None
+    if use_xyz:
+        local_xyz = new_pointset - new_xyz.unsqueeze(dim=2)
+        new_feature = torch.cat([local_xyz, new_feature], dim=-1) if new_feature is not None else local_xyz
+    return new_feature
+
+
+def group_all(new_xyz, pointset, feature):
+    """misc/ops.py:415-419."""
+    return torch.cat([pointset, feature], dim=-1).unsqueeze(dim=1)
+
+
+def pointnet_sa(module, xyz, feature, seg: bool = False):
+    """networks/cls/pointnet2.py:33-62 (seg=True: networks/seg/pointnet2_partseg.py:42-72)."""
+    if module.n_points is not None:
+        new_xyz = furthest_point_sampler(xyz, module.n_points)
+    else:
+        new_xyz = torch.zeros((xyz.shape[0], 1, 3)) if seg else None
+    outs = []
+    for i, grouper in enumerate(module.groupers):
+        if module.n_points is not None:
+            nf = ball_query_grouper(new_xyz, xyz, feature, grouper.radius, grouper.n_samples,
+                                    grouper.use_xyz)
+        else:
+            nf = group_all(new_xyz, xyz, feature)
+        nf = nf.permute(0, 3, 1, 2)            # [B, C, n_points, n_samples]
+        nf = module.mlps[i](nf)                # Conv2d 1x1 -> BatchNorm2d -> ReLU (torch CPU)
+        nf = nf.permute(0, 2, 3, 1)            # [B, n_points, n_samples, C]
+        nf = nf.max(dim=2).values              # jittor argmax(dim=2)[1] == max values
+        outs.append(nf)
+    return new_xyz, torch.cat(outs, dim=-1)
+
+
+def pointnet2_cls(model, xyz, feature):
+    """networks/cls/pointnet2.py:149-158."""
+    for module in model.pointnet_modules:
+        xyz, feature = pointnet_sa(module, xyz, feature)
+    return model.fc_layer(feature.squeeze(dim=1))
+
+
+def feature_propagation(fp, xyz1, xyz2, points1, points2):
+    """misc/ops.py:66-107."""
+    B, N, _ = xyz1.shape
+    S = xyz2.shape[1]
+    if S == 1:
+        interpolated = points2.repeat(1, N, 1)
+    else:
+        idx, dist, _w = oracle.three_nn(xyz1.detach().numpy(), xyz2.detach().numpy())
+        idx, dists = _t(idx), _t(dist)
+        dist_recip = 1.0 / (dists + 1e-8)
+        norm = torch.sum(dist_recip, dim=2, keepdim=True)
+        weight = dist_recip / norm
+        interpolated = torch.sum(index_points_t(points2, idx) * weight.view(B, N, 3, 1), dim=2)
+    new_points = torch.cat([points1, interpolated], dim=-1) if points1 is not None else interpolated
+    new_points = new_points.permute(0, 2, 1)
+    for i, conv in enumerate(fp.mlp_convs):
+        new_points = fp.relu(fp.mlp_bns[i](conv(new_points)))
+    return new_points.permute(0, 2, 1)
+
+
+def pointnet2_partseg(model, xyz, feature, cls_label):
+    """networks/seg/pointnet2_partseg.py:158-176."""
+    B, N, _ = xyz.shape
+    l1_xyz, l1_f = pointnet_sa(model.pointnet_modules[0], xyz, feature, seg=True)
+    l2_xyz, l2_f = pointnet_sa(model.pointnet_modules[1], l1_xyz, l1_f, seg=True)
+    l3_xyz, l3_f = pointnet_sa(model.pointnet_modules[2], l2_xyz, l2_f, seg=True)
+    l2_f = feature_propagation(model.fp3, l2_xyz, l3_xyz, l2_f, l3_f)
+    l1_f = feature_propagation(model.fp2, l1_xyz, l2_xyz, l1_f, l2_f)
+    onehot = cls_label.view(B, 16, 1).repeat(1, 1, N).permute(0, 2, 1)
+    f = feature_propagation(model.fp1, xyz, l1_xyz, torch.cat([onehot, xyz, feature], 2), l1_f)
+    return model.fc_layer(f.permute(0, 2, 1))
+
+
+def get_graph_feature(x, k):
+    """networks/cls/dgcnn.py:29-50 with idx from the KNN oracle."""
+    B, C, N = x.shape
+    idx = _t(oracle.knn(x.detach().numpy(), x.detach().numpy(), k)).permute(0, 2, 1).long()
+    idx = (idx + torch.arange(B).view(-1, 1, 1) * N).reshape(-1)
+    xt = x.transpose(2, 1)
+    feature = xt.reshape(B * N, -1)[idx, :].reshape(B, N, k, C)
+    xr = xt.reshape(B, N, 1, C).repeat(1, 1, k, 1)
+    return torch.cat((feature - xr, xr), dim=3).permute(0, 3, 1, 2)
+
+
+def dgcnn(model, x):
+    """networks/cls/dgcnn.py:95-122."""
+    import torch.nn.functional as TF
+    B = x.shape[0]
+    feats = []
+    h = x
+    for conv in (model.conv1, model.conv2, model.conv3, model.conv4):
+        h = conv(get_graph_feature(h, model.k)).max(dim=-1).values
+        feats.append(h)
+    h = model.conv5(torch.cat(feats, dim=1))
+    x1 = h.max(dim=2).values.reshape(B, -1)
+    x2 = h.mean(dim=2).reshape(B, -1)
+    h = torch.cat((x1, x2), 1)
+    h = model.dp1(TF.leaky_relu(model.bn6(model.linear1(h)), 0.2))
+    h = model.dp2(TF.leaky_relu(model.bn7(model.linear2(h)), 0.2))
+    return model.linear3(h)
+
+
+def soft_cross_entropy_loss(output, target, smoothing=True):
+    """train_cls.py:31-51 (label smoothing eps = 0.2)."""
+    target = target.view(-1)
+    if smoothing:
+        eps = 0.2
+        n_class = output.shape[1]
+        one_hot = torch.zeros_like(output)
+        for i in range(output.shape[0]):
+            one_hot[i, int(target[i])] = 1
+        one_hot = one_hot * (1 - eps) + (1 - one_hot) * eps / (n_class - 1)
+        log_prb = torch.log(torch.softmax(output, dim=1))
+        return -(one_hot * log_prb).sum(dim=1).mean()
+    return torch.nn.functional.cross_entropy(output, target)

@@ -1,0 +1,110 @@
+"""ctypes binding of libpcl_b200.so (the C ABI declared in include/pcl_b200.h).
+
+The product path has NO fallback: if the shared library is missing or a tensor is not on a CUDA
+device, calls raise.  Nothing here imports ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpcl_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "pcl_b200.h")
+
+_lib = None
+
+c_int, c_float, c_void_p, c_size_t = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+P = c_void_p
+
+# name -> argtypes (all return int except pcl_last_error)
+_SIGNATURES = {
+    "pcl_version": [],
+    "pcl_compiled_arch": [],
+    "pcl_optimal_block": [c_int],
+    "pcl_fps": [P, c_int, c_int, c_int, c_int, P, P],
+    "pcl_gather_xyz": [P, P, c_int, c_int, c_int, P, P],
+    "pcl_fps_pointconv": [P, c_int, c_int, c_int, P, P, P],
+    "pcl_ball_query": [P, P, c_int, c_int, c_int, c_float, c_int, P, P, P],
+    "pcl_group": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P],
+    "pcl_ball_query_group": [P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, c_int, P, P, P, P],
+    "pcl_group_backward": [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P],
+    "pcl_index_points": [P, P, c_int, c_int, c_int, c_int, P, P],
+    "pcl_index_points_backward": [P, P, c_int, c_int, c_int, c_int, P, P],
+    "pcl_knn": [P, P, c_int, c_int, c_int, c_int, c_int, P, P],
+    "pcl_square_distance": [P, P, c_int, c_int, c_int, c_int, P, P],
+    "pcl_knn_point": [c_int, P, P, c_int, c_int, c_int, c_int, P, P, P],
+    "pcl_three_nn": [P, P, c_int, c_int, c_int, P, P, P, P],
+    "pcl_three_interpolate": [P, P, P, c_int, c_int, c_int, c_int, P, P],
+    "pcl_three_interpolate_backward": [P, P, P, c_int, c_int, c_int, c_int, P, P],
+    "pcl_graph_feature": [P, P, c_int, c_int, c_int, c_int, P, P],
+    "pcl_graph_feature_backward": [P, P, c_int, c_int, c_int, c_int, P, P],
+    "pcl_compute_density": [P, c_int, c_int, c_float, P, P],
+    "pcl_sgd_momentum": [P, P, P, c_size_t, c_float, c_float, c_float, c_float, P],
+}
+
+
+def declared_symbols(header: str = HEADER_PATH):
+    """Every function name include/pcl_b200.h declares."""
+    src = open(header).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pcl_[a-z0-9_]+)\s*\(", src)))
+
+
+def lib() -> ctypes.CDLL:
+    """Load libpcl_b200.so; raises if it has not been built (python -m pointcloudlib_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the CUDA extension is not built "
+                "(run `python -m pointcloudlib_b200.build`); there is no CPU fallback")
+        l = ctypes.CDLL(LIB_PATH)
+        l.pcl_last_error.restype = ctypes.c_char_p
+        l.pcl_last_error.argtypes = []
+        for name, argtypes in _SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = c_int
+            fn.argtypes = argtypes
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().pcl_last_error().decode(errors="replace")
+        kind = "invalid argument" if rc == -1 else "unsupported" if rc == -2 else f"cuda error {rc}" if rc > 0 else f"error {rc}"
+        raise RuntimeError(f"libpcl_b200 {what}: {kind}: {msg}")
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("libpcl_b200 operators need CUDA tensors: there is no CPU fallback "
+                           f"(got a tensor on {t.device})")
+    if not t.is_contiguous():
+        raise RuntimeError("libpcl_b200 operators need contiguous tensors")
+    return t.data_ptr()
+
+
+def stream(t=None):
+    dev = t.device if t is not None else None
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def f32(t):
+    """contiguous fp32 view/copy of a CUDA tensor."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def i32(t):
+    if t.dtype != torch.int32:
+        t = t.to(torch.int32)
+    return t.contiguous()

@@ -1,0 +1,55 @@
+"""Per-group shared-MLP + max-reduce stage of a set-abstraction / EdgeConv layer.
+
+Reference: PointNetModuleBase.execute, networks/cls/pointnet2.py:52-57 —
+``transpose(0,3,1,2) -> [Conv 1x1 -> BatchNorm(train) -> ReLU]* -> transpose(0,2,3,1) ->
+argmax(dim=2)[1]`` (Jittor's argmax returns (index, value): [1] is the MAX VALUE over n_samples).
+
+The 1x1 convolution on (B,C,S,ns) is a row-wise linear map on the (B*S*ns, C) channels-last
+matrix, so the two transposes of the reference disappear.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as TF
+from torch import nn
+
+
+def _triples(seq: nn.Sequential):
+    """Split [Conv, (BN), Act]* into (conv, bn|None, act) triples."""
+    mods = list(seq)
+    out, i = [], 0
+    while i < len(mods):
+        conv = mods[i]
+        i += 1
+        bn = None
+        if i < len(mods) and isinstance(mods[i], (nn.BatchNorm1d, nn.BatchNorm2d)):
+            bn = mods[i]
+            i += 1
+        act = None
+        if i < len(mods) and isinstance(mods[i], (nn.ReLU, nn.LeakyReLU)):
+            act = mods[i]
+            i += 1
+        out.append((conv, bn, act))
+    return out
+
+
+def shared_mlp_rows(h: torch.Tensor, seq: nn.Sequential) -> torch.Tensor:
+    """Apply [Conv1x1 -> BN -> act]* to channels-last rows h (P, Cin) -> (P, Cout)."""
+    for conv, bn, act in _triples(seq):
+        w = conv.weight.reshape(conv.weight.shape[0], -1)
+        h = TF.linear(h, w, conv.bias)
+        if bn is not None:
+            h = TF.batch_norm(h, bn.running_mean, bn.running_var, bn.weight, bn.bias,
+                              bn.training, bn.momentum, bn.eps)
+        if isinstance(act, nn.LeakyReLU):
+            h = TF.leaky_relu(h, act.negative_slope)
+        elif act is not None:
+            h = TF.relu(h)
+    return h
+
+
+def mlp_max(grouped: torch.Tensor, seq: nn.Sequential) -> torch.Tensor:
+    """grouped (B,S,ns,Cin) -> (B,S,Cout): shared MLP then max over the ns neighbours."""
+    B, S, ns, Cin = grouped.shape
+    h = shared_mlp_rows(grouped.reshape(B * S * ns, Cin), seq)
+    return h.view(B, S, ns, -1).max(dim=2).values

@@ -156,3 +156,95 @@ def soft_cross_entropy_loss(output, target, smoothing=True):
         log_prb = torch.log(torch.softmax(output, dim=1))
         return -(one_hot * log_prb).sum(dim=1).mean()
     return torch.nn.functional.cross_entropy(output, target)
+
+
+# ---------------------------------------------------------------------------------------------
+# PointConv (misc/pointconv_utils.py, networks/cls/pointconv.py)
+# ---------------------------------------------------------------------------------------------
+def square_distance_t(src, dst):
+    """misc/pointconv_utils.py:34-53 (differentiable torch form)."""
+    B, N, _ = src.shape
+    M = dst.shape[1]
+    dist = -2 * torch.matmul(src, dst.permute(0, 2, 1))
+    dist = dist + torch.sum(src ** 2, -1).view(B, N, 1)
+    dist = dist + torch.sum(dst ** 2, -1).view(B, 1, M)
+    return dist
+
+
+def pointconv_sample_and_group(npoint, nsample, xyz, points, density_scale):
+    """misc/pointconv_utils.py:133-170; the FPS start index comes from numpy's global RNG (:88)."""
+    B, N, C = xyz.shape
+    start = np.random.randint(0, N, B, dtype="l").astype(np.int32)
+    fps_idx = _t(oracle.fps_pointconv(xyz.detach().numpy(), npoint, start))
+    new_xyz = index_points_t(xyz, fps_idx)
+    idx = _t(oracle.knn_point(nsample, xyz.detach().numpy(), new_xyz.detach().numpy()))
+    grouped_xyz = index_points_t(xyz, idx)
+    grouped_xyz_norm = grouped_xyz - new_xyz.view(B, npoint, 1, C)
+    new_points = torch.cat([grouped_xyz_norm, index_points_t(points, idx)], dim=-1) \
+        if points is not None else grouped_xyz_norm
+    grouped_density = index_points_t(density_scale, idx)
+    return new_xyz, new_points, grouped_xyz_norm, idx, grouped_density
+
+
+def pointconv_sa(mod, xyz, points):
+    """misc/pointconv_utils.py:361-400 (PointConvDensitySetAbstraction.execute)."""
+    B, _, N = xyz.shape
+    xyz = xyz.permute(0, 2, 1)
+    if points is not None:
+        points = points.permute(0, 2, 1)
+    sq = square_distance_t(xyz, xyz)                                        # :179
+    xyz_density = (torch.exp(-sq / (2.0 * mod.bandwidth * mod.bandwidth)) / (2.5 * mod.bandwidth)).mean(dim=-1)
+    density_scale = mod.densitynet(xyz_density)
+    if mod.group_all:
+        new_xyz = torch.zeros((B, 1, 3), dtype=xyz.dtype)
+        grouped_xyz_norm = xyz.view(B, 1, N, 3)
+        new_points = torch.cat([grouped_xyz_norm, points.view(B, 1, N, -1)], dim=-1) \
+            if points is not None else grouped_xyz_norm
+        grouped_density = density_scale.reshape(B, N, 1).view(B, 1, N, 1)
+    else:
+        new_xyz, new_points, grouped_xyz_norm, _, grouped_density = pointconv_sample_and_group(
+            mod.npoint, mod.nsample, xyz, points, density_scale.reshape(B, N, 1))
+    new_points = new_points.permute(0, 3, 2, 1)
+    for i in range(len(mod.mlp_convs)):
+        new_points = mod.relu(mod.mlp_bns[i](mod.mlp_convs[i](new_points)))
+    weights = mod.weightnet(grouped_xyz_norm.permute(0, 3, 2, 1))
+    new_points = new_points * grouped_density.permute(0, 3, 2, 1)
+    new_points = torch.matmul(new_points.permute(0, 3, 1, 2),
+                              weights.permute(0, 3, 2, 1)).reshape(B, mod.npoint, -1)
+    new_points = mod.linear(new_points)
+    new_points = mod.relu(mod.bn_linear(new_points.permute(0, 2, 1)))
+    return new_xyz.permute(0, 2, 1), new_points
+
+
+def pointconv_cls(model, xyz):
+    """networks/cls/pointconv.py:23-34."""
+    xyz = xyz.permute(0, 2, 1)
+    B = xyz.shape[0]
+    l1_xyz, l1_points = pointconv_sa(model.sa1, xyz, None)
+    l2_xyz, l2_points = pointconv_sa(model.sa2, l1_xyz, l1_points)
+    l3_xyz, l3_points = pointconv_sa(model.sa3, l2_xyz, l2_points)
+    x = l3_points.reshape(B, 1024)
+    x = model.drop1(model.relu(model.bn1(model.fc1(x))))
+    x = model.drop2(model.relu(model.bn2(model.fc2(x))))
+    return model.fc3(x)
+
+
+def dgcnn_partseg(model, x, l):
+    """networks/seg/dgcnn_partseg.py:84-128."""
+    B, _, N = x.shape
+    h = get_graph_feature(x, model.k)
+    h = model.conv2(model.conv1(h))
+    x1 = h.max(dim=-1).values
+    h = get_graph_feature(x1, model.k)
+    h = model.conv4(model.conv3(h))
+    x2 = h.max(dim=-1).values
+    h = get_graph_feature(x2, model.k)
+    h = model.conv5(h)
+    x3 = h.max(dim=-1).values
+    h = model.conv6(torch.cat((x1, x2, x3), dim=1)).max(dim=-1, keepdim=True).values
+    ll = model.conv7(l.view(B, -1, 1))
+    h = torch.cat((h, ll), dim=1).repeat(1, 1, N)
+    h = torch.cat((h, x1, x2, x3), dim=1)
+    h = model.dp1(model.conv8(h))
+    h = model.dp2(model.conv9(h))
+    return model.conv11(model.conv10(h))

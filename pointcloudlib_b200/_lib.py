@@ -73,7 +73,55 @@ def lib() -> ctypes.CDLL:
     return _lib
 
 
+LAUNCHES = 0          # C-ABI calls that enqueued a kernel (bench.py reads the delta)
+_timer = None         # active KernelTimer or None
+
+
+class KernelTimer:
+    """Records a CUDA-event pair around selected C-ABI calls (on the launching stream)."""
+
+    def __init__(self, only=None):
+        self.only = set(only) if only else None
+        self.records = []  # (name, key, ev_start, ev_end)
+
+    def __enter__(self):
+        global _timer
+        _timer = self
+        return self
+
+    def __exit__(self, *exc):
+        global _timer
+        _timer = None
+
+    def summary(self):
+        """{(name, key): (n_launches, mean_ms, total_ms)} — call after a synchronize."""
+        out = {}
+        for name, key, e0, e1 in self.records:
+            ms = e0.elapsed_time(e1)
+            n, tot = out.get((name, key), (0, 0.0))
+            out[(name, key)] = (n + 1, tot + ms)
+        return {k: (n, tot / n, tot) for k, (n, tot) in out.items()}
+
+
+def call(name: str, *args, key=None) -> None:
+    """Invoke a C-ABI entry point, raise on a non-zero return, time it if a KernelTimer is active."""
+    fn = getattr(lib(), name)
+    t = _timer
+    if t is not None and (t.only is None or name in t.only):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        t.records.append((name, key, e0, e1))
+    else:
+        rc = fn(*args)
+    check(rc, name)
+
+
 def check(rc: int, what: str = "") -> None:
+    global LAUNCHES
+    LAUNCHES += 1
     if rc != 0:
         msg = lib().pcl_last_error().decode(errors="replace")
         kind = "invalid argument" if rc == -1 else "unsupported" if rc == -2 else f"cuda error {rc}" if rc > 0 else f"error {rc}"

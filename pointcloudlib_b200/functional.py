@@ -124,9 +124,9 @@ class _BallQueryGroupFn(torch.autograd.Function, _GroupBackwardMixin):
         idx = torch.empty((B, S, nsample), dtype=torch.int32, device=xyz.device)
         cnt = torch.empty((B, S), dtype=torch.int32, device=xyz.device)
         out = torch.empty((B, S, nsample, W), dtype=torch.float32, device=xyz.device)
-        check(lib().pcl_ball_query_group(ptr(new_xyz), ptr(xyz), ptr(feat), B, N, S, float(radius),
-                                         int(nsample), C, int(use_xyz), ptr(idx), ptr(cnt),
-                                         ptr(out), stream(xyz)), "pcl_ball_query_group")
+        _lib.call("pcl_ball_query_group", ptr(new_xyz), ptr(xyz), ptr(feat), B, N, S, float(radius),
+                  int(nsample), C, int(use_xyz), ptr(idx), ptr(cnt), ptr(out), stream(xyz),
+                  key=(B, N, S, int(nsample), C, int(use_xyz)))
         ctx.save_for_backward(idx)
         ctx.dims = (B, N, S, nsample, C, use_xyz)
         ctx.needs_feat_grad = feat is not None and feat.requires_grad

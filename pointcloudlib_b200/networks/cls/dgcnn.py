@@ -1,0 +1,89 @@
+"""DGCNN classification — host-side mirror of networks/cls/dgcnn.py (k=20, 4 EdgeConv blocks).
+
+``execute(x (B,3,N)) -> logits (B,n_classes)``.  get_graph_feature (:29-50) is one gather kernel
+(pcl_graph_feature) fed by the on-chip KNN (pcl_knn); nothing of size (B,N,N) is materialised.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as TF
+from torch import nn
+
+from ... import functional as F
+from ...misc.ops import KNN, Module, topk  # noqa: F401  (topk re-exported like dgcnn.py:11-26)
+
+
+def get_graph_feature(x, knn=None, k=None, idx=None):
+    """networks/cls/dgcnn.py:29-50: x (B,C,N) -> (B,2C,N,k) = [x_j - x_i ; x_i].
+    `idx`, if given, is (B,N,k) as in the reference; otherwise knn(x,x) -> (B,k,N)."""
+    batch_size = x.shape[0]
+    num_points = x.shape[2]
+    x = x.reshape(batch_size, -1, num_points)
+    if idx is None:
+        idx_kmajor = knn(x, x)                       # (B, k, N), the KNN module's own layout
+    else:
+        idx_kmajor = idx.permute(0, 2, 1).contiguous()
+    return F.graph_feature(x, idx_kmajor)
+
+
+def knn(x, k):
+    """networks/cls/dgcnn.py:52-57 (unused by the model)."""
+    from ...misc.ops import knn as _knn
+    return _knn(x, k)
+
+
+class DGCNN(Module):
+    """networks/cls/dgcnn.py:61-122."""
+
+    def __init__(self, n_classes=40):
+        super().__init__()
+        self.k = 20
+        self.knn = KNN(self.k)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.bn2 = nn.BatchNorm2d(64)
+        self.bn3 = nn.BatchNorm2d(128)
+        self.bn4 = nn.BatchNorm2d(256)
+        self.bn5 = nn.BatchNorm1d(1024)
+        self.conv1 = nn.Sequential(nn.Conv2d(6, 64, kernel_size=1, bias=False), self.bn1,
+                                   nn.LeakyReLU(negative_slope=0.2))
+        self.conv2 = nn.Sequential(nn.Conv2d(64 * 2, 64, kernel_size=1, bias=False), self.bn2,
+                                   nn.LeakyReLU(negative_slope=0.2))
+        self.conv3 = nn.Sequential(nn.Conv2d(64 * 2, 128, kernel_size=1, bias=False), self.bn3,
+                                   nn.LeakyReLU(negative_slope=0.2))
+        self.conv4 = nn.Sequential(nn.Conv2d(128 * 2, 256, kernel_size=1, bias=False), self.bn4,
+                                   nn.LeakyReLU(negative_slope=0.2))
+        self.conv5 = nn.Sequential(nn.Conv1d(512, 1024, kernel_size=1, bias=False), self.bn5,
+                                   nn.LeakyReLU(negative_slope=0.2))
+        self.linear1 = nn.Linear(1024 * 2, 512, bias=False)
+        self.bn6 = nn.BatchNorm1d(512)
+        self.dp1 = nn.Dropout(p=0.5)
+        self.linear2 = nn.Linear(512, 256)
+        self.bn7 = nn.BatchNorm1d(256)
+        self.dp2 = nn.Dropout(p=0.5)
+        self.linear3 = nn.Linear(256, n_classes)
+
+    def execute(self, x):
+        batch_size = x.shape[0]
+        x = get_graph_feature(x, knn=self.knn, k=self.k)
+        x = self.conv1(x)
+        x1 = x.max(dim=-1, keepdim=False).values
+        x = get_graph_feature(x1, knn=self.knn, k=self.k)
+        x = self.conv2(x)
+        x2 = x.max(dim=-1, keepdim=False).values
+        x = get_graph_feature(x2, knn=self.knn, k=self.k)
+        x = self.conv3(x)
+        x3 = x.max(dim=-1, keepdim=False).values
+        x = get_graph_feature(x3, knn=self.knn, k=self.k)
+        x = self.conv4(x)
+        x4 = x.max(dim=-1, keepdim=False).values
+        x = torch.cat((x1, x2, x3, x4), dim=1)
+        x = self.conv5(x)
+        x1 = x.max(dim=2).values.reshape(batch_size, -1)
+        x2 = x.mean(dim=2).reshape(batch_size, -1)
+        x = torch.cat((x1, x2), 1)
+        x = TF.leaky_relu(self.bn6(self.linear1(x)), 0.2)
+        x = self.dp1(x)
+        x = TF.leaky_relu(self.bn7(self.linear2(x)), 0.2)
+        x = self.dp2(x)
+        x = self.linear3(x)
+        return x

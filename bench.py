@@ -174,6 +174,36 @@ def bq_group_bytes(key):
     return 4 * (B * N * (3 + C) + 3 * B * S + B * S * ns + B * S * ns * W)
 
 
+def algorithmic_cost(name, key):
+    """(ALGORITHMIC bytes, flops) of one launch of an own kernel.  Bytes count
+    each HBM-resident operand once (tensors of a few MB that stay in L2 — weights, U/V, per-channel
+    vectors — are left out); flops = 2*P*K*N for the GEMM-shaped kernels."""
+    if name == "pcl_ball_query_group":
+        return bq_group_bytes(key), 0
+    if name == "pcl_rowgemm":
+        tag, pro, epi, P, K, N = key
+        by = {"sa_l2": 4 * (P * N + P),                    # write y2, read src
+              "sa_l3": 4 * P * K,                          # read y2 (max/min outputs are G*N*16 B)
+              "sa_b3": 4 * (P * N + P * N),                # read y2, write dyhat2
+              "sa_b2": 4 * (2 * P * K + P * N + P),        # read dyhat2 + y2, write dyhat1, read src
+              }.get(tag, 4 * P * (K + N))
+        return by, 2 * P * K * N
+    if name == "pcl_wgrad":
+        tag, P, M, N = key
+        by = {"sa_gram": 4 * P * M, "sa_dw2": 4 * (2 * P * M + P)}.get(tag, 4 * P * (M + N))
+        return by, 2 * P * M * N
+    if name == "pcl_sel_outer":
+        tag, G, C3, C2 = key
+        return 4 * G * C3 * (C2 + 2), 2 * G * C3 * C2
+    if name == "pcl_gather_bn_backward":
+        tag, P, C1 = key
+        return 4 * (P * C1 + P), 0
+    if name == "pcl_gather_stats":
+        tag, P, C1 = key
+        return 4 * P, 0
+    return 0, 0
+
+
 def run_product_arm(args):
     import torch
     import torch.distributed as dist
@@ -233,7 +263,9 @@ def run_product_arm(args):
         sampler.start()
     launches0 = _lib.LAUNCHES
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with _lib.KernelTimer(only=["pcl_ball_query_group"]) as kt:
+    timed = ["pcl_rowgemm", "pcl_wgrad", "pcl_sel_outer", "pcl_gather_stats", "pcl_gather_bn_backward",
+             "pcl_ball_query", "pcl_ball_query_group", "pcl_fps", "pcl_group_backward"]
+    with _lib.KernelTimer(only=timed) as kt:
         sync_all()
         ev0.record()
         for i in range(args.steps):
@@ -273,20 +305,29 @@ def run_product_arm(args):
 
     # ---- roofline of the ball-query+group kernel (HBM-bound) ---------------------------------
     peak, peak_src = peaks()
-    per_cfg = []
+    step_us = 1e3 * ms_total / args.steps
+    kernels = []
     for (name, key), (n, mean_ms, tot_ms) in sorted(kernel_stats.items(), key=lambda kv: -kv[1][2]):
-        by = bq_group_bytes(key)
-        per_cfg.append({"B,N,S,ns,C,use_xyz": list(key), "launches": n, "mean_us": 1e3 * mean_ms,
-                        "algorithmic_MB": by / 1e6, "GBps": by / (mean_ms * 1e-3) / 1e9,
-                        "frac": by / (mean_ms * 1e-3) / 1e9 / peak})
-    top = per_cfg[0]
-    roofline = {"kernel": "ball_query_group_kernel (pcl_ball_query_group)", "bound": "hbm",
-                "achieved": top["GBps"], "peak": peak, "unit": "GB/s", "frac": top["frac"],
-                "traffic": None, "peak_source": peak_src, "config": top["B,N,S,ns,C,use_xyz"],
-                "algorithmic_bytes_per_launch": int(top["algorithmic_MB"] * 1e6),
-                "mean_launch_us": top["mean_us"],
-                "share_of_step": sum(c["mean_us"] for c in per_cfg) / (1e3 * ms_total / args.steps),
-                "all_configs": per_cfg}
+        by, fl = algorithmic_cost(name, key)
+        k = {"call": name, "key": [str(x) for x in key] if key else None,
+             "launches_per_step": n / args.steps, "mean_us": 1e3 * mean_ms,
+             "share_of_step": 1e3 * tot_ms / args.steps / step_us}
+        if by:
+            k.update({"algorithmic_MB": by / 1e6, "GBps": by / (mean_ms * 1e-3) / 1e9,
+                      "hbm_frac": by / (mean_ms * 1e-3) / 1e9 / peak})
+        if fl:
+            k["TFLOPs"] = fl / (mean_ms * 1e-3) / 1e12
+        kernels.append(k)
+    top = next((k for k in kernels if "GBps" in k), kernels[0])
+    roofline = {"kernel": f"{top['call']} {top['key']}", "bound": "hbm",
+                "achieved": top.get("GBps"), "peak": peak, "unit": "GB/s", "frac": top.get("hbm_frac"),
+                "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(top.get("algorithmic_MB", 0) * 1e6),
+                "mean_launch_us": top["mean_us"], "share_of_step": top["share_of_step"],
+                "own_kernels_share_of_step": sum(k["share_of_step"] for k in kernels),
+                "note": "dominant own kernel by total time inside the timed region; CUDA events on the "
+                        "launch stream; 3xTF32 mma.sync row-GEMM with fused prologue/epilogue",
+                "kernels": kernels[:24]}
 
     # ---- CPU baseline (bounded sample, rank 0, N=1 only) ----------------------------------------
     cpu_baseline = None

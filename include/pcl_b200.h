@@ -129,6 +129,84 @@ int pcl_graph_feature_backward(const float *dout, const int32_t *idx, int B, int
 /* ---- a15: compute_density (misc/pointconv_utils.py:174-184) -------------------------------- */
 int pcl_compute_density(const float *xyz, int B, int N, float bandwidth, float *out, void *stream);
 
+/* ---- a5 / a8: per-group shared MLP (1x1 conv -> BatchNorm(train) -> ReLU)* -> max, fused -----
+ * Reference: PointNetModuleBase.execute, networks/cls/pointnet2.py:52-57 (dup
+ * networks/seg/pointnet2_partseg.py:61-67), EdgeConv blocks networks/cls/dgcnn.py:72-111.
+ * See DESIGN.md "fused set abstraction" for the algebra.  All activations are channels-last
+ * row matrices (P rows = B*S*ns positions).
+ *
+ * pcl_rowgemm: OUT (P,N) = epilogue( prologue(rows) (P,K) . W^T ), TF32 tensor-core MMA with a
+ * 3xTF32 split (fp32-equivalent) when x3 != 0.  W is (N, ldw) row-major, zero padded,
+ * ldw % 32 == 0, N % 16 == 0 and (N <= 128 or N % 128 == 0 or N % 64 == 0).
+ *   prologue (how a row of the A operand is produced, never materialised):
+ *     PCL_PRO_PLAIN2       [x0 (P,c0) | x1 (P,c1)]                       (layer-1 projection)
+ *     PCL_PRO_BN_ACT       act(scale*x0 + shift), x0 (P,K)               (layer l >= 3 input)
+ *     PCL_PRO_GATHER_BN_ACT act(scale*(U[src[p]] + vsign*V[p/ns]) + shift) (layer-2 input: the
+ *                          grouped tensor of misc/ops.py:383-405 after layer 1, built on the fly)
+ *     PCL_PRO_BN_BWD       bscale*(x0 - m1 - (x1-mean)*rstd*m2)          (BatchNorm backward)
+ *     PCL_PRO_G3_A2        [one-hot routed max-gradient (G,C3) | act(scale*x0+shift)]
+ *   epilogue:
+ *     PCL_EPI_STORE        out = acc
+ *     PCL_EPI_STORE_STATS  out = acc; stats += (sum, sum of squares) per column (fp64)
+ *     PCL_EPI_MAXMIN_STATS stats as above; per group of ns rows: max, min and their row offsets
+ *                          -> gmax,gmin,amax,amin (P/ns, N); nothing of size (P,N) is written
+ *     PCL_EPI_BWD_Y        v = (acc+ebias)*act'(escale*ey+eshift); out = v;
+ *                          stats += (sum v, sum v*(ey-emean)*erstd)
+ *     PCL_EPI_BWD_GATHER   same with ey := U[src[p]] + vsign*V[p/ns]
+ */
+typedef struct PclRowGemm {
+    const float *W, *x0, *x1, *U, *V, *scale, *shift, *mean, *rstd, *bscale, *m1, *m2, *g3s;
+    const int32_t *src, *selpos;
+    float *out, *gmax, *gmin;
+    int32_t *amax, *amin;
+    double *stats;
+    const float *ebias, *ey, *escale, *eshift, *emean, *erstd;
+    long long P;
+    int K, N, ldw, ns, C3, c0, c1, reserved;
+    float vsign, slope, eslope, reserved_f;
+} PclRowGemm;
+enum { PCL_PRO_PLAIN2 = 0, PCL_PRO_BN_ACT = 1, PCL_PRO_GATHER_BN_ACT = 2, PCL_PRO_BN_BWD = 3,
+       PCL_PRO_G3_A2 = 4, PCL_PRO_BN_ACT_ONES = 5 /* pcl_wgrad only: [act(bn(x0)) | 1] */ };
+enum { PCL_EPI_STORE = 0, PCL_EPI_STORE_STATS = 1, PCL_EPI_MAXMIN_STATS = 2, PCL_EPI_BWD_Y = 3,
+       PCL_EPI_BWD_GATHER = 4 };
+int pcl_rowgemm(const PclRowGemm *args, int prologue, int epilogue, int x3, void *stream);
+
+/* pcl_wgrad: OUT (M,N) += sum over rows p of L(p)[m] * R(p)[n]  (weight gradients, Gram
+ * matrices).  L and R rows are produced by the same prologue functors as pcl_rowgemm (args_l /
+ * args_r use the prologue fields only; K there = the row width).  OUT is fp32, accumulated with
+ * atomics, must be zeroed by the caller; ldo = its row stride. */
+int pcl_wgrad(const PclRowGemm *args_l, int prologue_l, const PclRowGemm *args_r, int prologue_r,
+              long long P, int M, int N, float *out, int ldo, int x3, void *stream);
+
+/* per-channel sum / sum of squares of y1 = U[src[p]] + vsign*V[p/ns] over all P rows (fp64) */
+int pcl_gather_stats(const float *U, const float *V, const int32_t *src, long long P, int ns,
+                     int C, float vsign, double *stats, void *stream);
+/* stats (2,C) fp64 -> BatchNorm(train) scale/shift/mean/rstd (+ running-stat update, may be NULL) */
+int pcl_bn_param(const double *stats, long long P, const float *gamma, const float *beta, float eps,
+                 float momentum, float *running_mean, float *running_var, float *scale,
+                 float *shift, float *mean, float *rstd, int C, void *stream);
+/* out (G,C) = act(scale*sel + shift), sel = scale >= 0 ? gmax : gmin  (max commutes with the
+ * monotone per-channel map; act slope 0 = ReLU); also ysel (G,C) = sel and selpos (G,C). */
+int pcl_maxpool_finalize(const float *gmax, const float *gmin, const int32_t *amax,
+                         const int32_t *amin, const float *scale, const float *shift, float slope,
+                         long long G, int C, float *out, float *ysel, int32_t *selpos,
+                         void *stream);
+/* backward of the finalize + BatchNorm sums of the last layer: g3s (G,C) = scale*dout*act'(out);
+ * sums (2,C) fp64 += (sum g3, sum g3*xhat_sel), g3 = dout*act'. */
+int pcl_maxpool_backward(const float *dout, const float *out, const float *ysel,
+                         const float *scale, const float *mean, const float *rstd, float slope,
+                         long long G, int C, float *g3s, double *sums, void *stream);
+/* T (C3,C2) += sum_g g3s[g,c3] * act(scale2*y2[g*ns+selpos[g,c3], :] + shift2)   (sparse dW3 term) */
+int pcl_sel_outer(const float *g3s, const int32_t *selpos, const float *y2, const float *scale2,
+                  const float *shift2, float slope, long long G, int ns, int C3, int C2, float *T,
+                  void *stream);
+/* layer-1 backward scatter: dz1 = bscale*(dyh - m1 - xhat*m2) with y1 gathered again;
+ * dU[src[p],:] += dz1 (atomics); dV[p/ns,:] = vsign * sum over the group of dz1. */
+int pcl_gather_bn_backward(const float *dyh, const float *U, const float *V, const int32_t *src,
+                           const float *mean, const float *rstd, const float *bscale,
+                           const float *m1, const float *m2, long long P, int ns, int C,
+                           float vsign, float *dU, float *dV, void *stream);
+
 /* ---- DP / optimizer plumbing on the flat parameter bucket (train_cls.py:72 optimizer.step) --
  * SGD with momentum + weight decay over a flat fp32 bucket: g += wd*p; m = mu*m + g; p -= lr*m;
  * grad_scale multiplies g first (1/world_size after the NCCL all-reduce). */

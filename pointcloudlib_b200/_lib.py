@@ -47,6 +47,12 @@ _SIGNATURES = {
 }
 
 
+# entry points bound in pointcloudlib_b200/fused.py (struct-taking signatures)
+FUSED_SYMBOLS = ("pcl_rowgemm", "pcl_wgrad", "pcl_gather_stats", "pcl_bn_param",
+                 "pcl_maxpool_finalize", "pcl_maxpool_backward", "pcl_sel_outer",
+                 "pcl_gather_bn_backward")
+
+
 def declared_symbols(header: str = HEADER_PATH):
     """Every function name include/pcl_b200.h declares."""
     src = open(header).read()
@@ -69,8 +75,42 @@ def lib() -> ctypes.CDLL:
             fn = getattr(l, name)
             fn.restype = c_int
             fn.argtypes = argtypes
-        _lib = l
+        _lib = _TimedLib(l)
     return _lib
+
+
+class _TimedLib:
+    """Proxy over the CDLL: when a KernelTimer is active every pcl_* call is bracketed by a CUDA
+    event pair on the current stream (key = the call's integer arguments)."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        self._cache = {}
+
+    def __getattr__(self, name):
+        fn = getattr(self._cdll, name)
+        if not name.startswith("pcl_") or name in ("pcl_last_error", "pcl_version",
+                                                    "pcl_compiled_arch", "pcl_optimal_block"):
+            return fn
+        w = self._cache.get(name)
+        if w is None:
+            def w(*args, _fn=fn, _name=name):
+                t = _timer
+                if t is None or _in_call or (t.only is not None and _name not in t.only):
+                    return _fn(*args)
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                rc = _fn(*args)
+                e1.record()
+                t.records.append((_name, tuple(a for a in args if isinstance(a, int) and abs(a) < (1 << 31)),
+                                  e0, e1))
+                return rc
+            self._cache[name] = w
+        return w
+
+
+_in_call = False  # set while call() itself is timing (avoids double records)
 
 
 LAUNCHES = 0          # C-ABI calls that enqueued a kernel (bench.py reads the delta)
@@ -105,14 +145,19 @@ class KernelTimer:
 
 def call(name: str, *args, key=None) -> None:
     """Invoke a C-ABI entry point, raise on a non-zero return, time it if a KernelTimer is active."""
+    global _in_call
     fn = getattr(lib(), name)
     t = _timer
     if t is not None and (t.only is None or name in t.only):
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        rc = fn(*args)
-        e1.record()
+        _in_call = True
+        try:
+            e0.record()
+            rc = fn(*args)
+            e1.record()
+        finally:
+            _in_call = False
         t.records.append((name, key, e0, e1))
     else:
         rc = fn(*args)

@@ -1,0 +1,294 @@
+"""Fused set-abstraction MLP stage: host orchestration of the row-GEMM kernels (csrc/mlp_fused.cu).
+
+Reference stage: PointNetModuleBase.execute, networks/cls/pointnet2.py:51-57 — grouper ->
+transpose -> [Conv1x1 -> BatchNorm(train) -> ReLU] x3 -> transpose -> max over n_samples.
+
+Forward (per radius branch), with P = B*S*ns rows, G = B*S groups:
+    U = [xyz|feat] . W1^T  (B*N rows), V = new_xyz . W1[:, :3]^T (G rows)    layer 1 BEFORE the gather
+    y1[p] = U[src[p]] - V[p // ns]            (never stored; stats by one gather pass)
+    y2 = relu(bn1(y1)) . W2^T                 (stored, P x C2; BN2 stats in the GEMM epilogue)
+    y3 = relu(bn2(y2)) . W3^T                 (never stored: epilogue keeps per-group max / min + stats)
+    out = relu(bn3(max or min by sign of the BN scale))        (max commutes with a monotone map)
+Backward: the last layer is handled analytically (BatchNorm backward through a linear layer is a
+C2 x C2 linear map of a2 plus a sparse routed term), so y3 is never recomputed:
+    da2 = G3s.W3 - a2.Q + const,  dW3 = T - s3 c1/P (x) S2 - t (.) (W3.M2 - mu3 (x) S2)
+with M2 = a2^T a2, S2 = colsum(a2) (one Gram pass), T = sparse routed outer product.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import lib, ptr, stream
+
+PRO_PLAIN2, PRO_BN_ACT, PRO_GATHER_BN_ACT, PRO_BN_BWD, PRO_G3_A2, PRO_BN_ACT_ONES = range(6)
+EPI_STORE, EPI_STORE_STATS, EPI_MAXMIN_STATS, EPI_BWD_Y, EPI_BWD_GATHER = range(5)
+
+_PTR_FIELDS = ("W", "x0", "x1", "U", "V", "scale", "shift", "mean", "rstd", "bscale", "m1", "m2",
+               "g3s", "src", "selpos", "out", "gmax", "gmin", "amax", "amin", "stats", "ebias",
+               "ey", "escale", "eshift", "emean", "erstd")
+_INT_FIELDS = ("K", "N", "ldw", "ns", "C3", "c0", "c1", "reserved")
+_FLT_FIELDS = ("vsign", "slope", "eslope", "reserved_f")
+
+
+class PclRowGemm(ctypes.Structure):
+    """Mirror of `struct PclRowGemm` in include/pcl_b200.h."""
+    _fields_ = ([(n, ctypes.c_void_p) for n in _PTR_FIELDS] + [("P", ctypes.c_longlong)]
+                + [(n, ctypes.c_int) for n in _INT_FIELDS] + [(n, ctypes.c_float) for n in _FLT_FIELDS])
+
+
+# x3 = True: 3xTF32 split MMA (fp32-equivalent accuracy).  False: single-pass TF32.
+X3 = True
+
+_bound = False
+
+
+def _bind():
+    global _bound
+    if _bound:
+        return
+    l = lib()._cdll  # the raw CDLL: argtypes must be set on the ctypes function objects
+    P, I, L, Fl = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+    RG = ctypes.POINTER(PclRowGemm)
+    sigs = {
+        "pcl_rowgemm": [RG, I, I, I, P],
+        "pcl_wgrad": [RG, I, RG, I, L, I, I, P, I, I, P],
+        "pcl_gather_stats": [P, P, P, L, I, I, Fl, P, P],
+        "pcl_bn_param": [P, L, P, P, Fl, Fl, P, P, P, P, P, P, I, P],
+        "pcl_maxpool_finalize": [P, P, P, P, P, P, Fl, L, I, P, P, P, P],
+        "pcl_maxpool_backward": [P, P, P, P, P, P, Fl, L, I, P, P, P],
+        "pcl_sel_outer": [P, P, P, P, P, Fl, L, I, I, I, P, P],
+        "pcl_gather_bn_backward": [P, P, P, P, P, P, P, P, P, L, I, I, Fl, P, P, P],
+    }
+    for name, argtypes in sigs.items():
+        fn = getattr(l, name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = argtypes
+    _bound = True
+
+
+SIGNATURE_NAMES = ("pcl_rowgemm", "pcl_wgrad", "pcl_gather_stats", "pcl_bn_param",
+                   "pcl_maxpool_finalize", "pcl_maxpool_backward", "pcl_sel_outer",
+                   "pcl_gather_bn_backward")
+
+
+def _args(**kw):
+    """Build a PclRowGemm from tensors / scalars; returns (struct, keepalive list)."""
+    a = PclRowGemm()
+    keep = []
+    for k, v in kw.items():
+        if k in _PTR_FIELDS:
+            if v is not None:
+                keep.append(v)
+                setattr(a, k, ptr(v))
+        else:
+            setattr(a, k, v)
+    return a, keep
+
+
+def pack_weight(w: torch.Tensor) -> torch.Tensor:
+    """(N, K) -> (N, ceil32(K)) zero-padded, contiguous fp32."""
+    N, K = w.shape
+    ld = (K + 31) // 32 * 32
+    if ld == K:
+        return w.contiguous().float()
+    out = torch.zeros((N, ld), dtype=torch.float32, device=w.device)
+    out[:, :K] = w
+    return out
+
+
+def rowgemm(pro: int, epi: int, name: str, **kw):
+    _bind()
+    a, keep = _args(**kw)
+    _lib.call("pcl_rowgemm", ctypes.byref(a), pro, epi, int(X3), stream(), key=(name, pro, epi, a.P, a.K, a.N))
+    return keep
+
+
+def wgrad(pro_l, kw_l, pro_r, kw_r, P, M, N, out, name="wgrad"):
+    _bind()
+    al, k1 = _args(**kw_l)
+    ar, k2 = _args(**kw_r)
+    _lib.call("pcl_wgrad", ctypes.byref(al), pro_l, ctypes.byref(ar), pro_r, P, M, N, ptr(out),
+              out.stride(0), int(X3), stream(), key=(name, P, M, N))
+
+
+def bn_param(stats, P, bn, C):
+    """stats (2,C) fp64 -> scale, shift, mean, rstd (fp32); updates bn.running_* in training mode."""
+    _bind()
+    dev = stats.device
+    scale, shift, mean, rstd = (torch.empty(C, dtype=torch.float32, device=dev) for _ in range(4))
+    track = bn.track_running_stats and bn.running_mean is not None
+    momentum = bn.momentum if bn.momentum is not None else 0.1
+    _lib.call("pcl_bn_param", ptr(stats), P, ptr(bn.weight.detach()), ptr(bn.bias.detach()),
+              float(bn.eps), float(momentum), ptr(bn.running_mean) if track else None,
+              ptr(bn.running_var) if track else None, ptr(scale), ptr(shift), ptr(mean), ptr(rstd),
+              C, stream())
+    if track and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return scale, shift, mean, rstd
+
+
+def supported(ns: int, chans, n_layers: int) -> bool:
+    """Can this branch take the fused path?  3 layers, ns | 128, channel widths the tiles cover."""
+    if n_layers != 3 or 128 % ns != 0 or ns < 1:
+        return False
+    c1, c2, c3 = chans
+    ok_n = lambda n: n % 32 == 0 and (n <= 128 or n % 64 == 0)
+    return ok_n(c1) and ok_n(c2) and ok_n(c3) and c1 <= 256 and c2 <= 256
+
+
+class FusedSAFn(torch.autograd.Function):
+    """out (B,S,C3) = max_l relu(bn3(conv3(relu(bn2(conv2(relu(bn1(conv1(grouped)))))))))."""
+
+    @staticmethod
+    def forward(ctx, xyz, new_xyz, feat, idx, W1, W2, W3, g1, b1, g2, b2, g3, b3, bns, slope):
+        _bind()
+        dev = xyz.device
+        B, N, _ = xyz.shape
+        S, ns = idx.shape[1], idx.shape[2]
+        G, P = B * S, B * S * ns
+        C = feat.shape[2] if feat is not None else 0
+        C1, C2, C3 = W1.shape[0], W2.shape[0], W3.shape[0]
+        W1m, W2m, W3m = W1.reshape(C1, -1), W2.reshape(C2, -1), W3.reshape(C3, -1)
+        xyz_r = xyz.reshape(B * N, 3).contiguous()
+        feat_r = feat.reshape(B * N, C).contiguous() if feat is not None else None
+        nxyz_r = new_xyz.reshape(G, 3).contiguous()
+        src = (idx + (torch.arange(B, device=dev, dtype=torch.int32) * N).view(B, 1, 1)).reshape(-1).contiguous()
+        f32 = dict(dtype=torch.float32, device=dev)
+
+        # ---- layer 1 on the source points and on the centres (before the gather) ------------
+        U = torch.empty((B * N, C1), **f32)
+        W1p = pack_weight(W1m)
+        rowgemm(PRO_PLAIN2, EPI_STORE, "sa_proj_u", W=W1p, x0=xyz_r, x1=feat_r, c0=3, c1=C, P=B * N,
+                K=3 + C, N=C1, ldw=W1p.shape[1], out=U)
+        V = torch.empty((G, C1), **f32)
+        W1x = pack_weight(W1m[:, :3])
+        rowgemm(PRO_PLAIN2, EPI_STORE, "sa_proj_v", W=W1x, x0=nxyz_r, c0=3, c1=0, P=G, K=3, N=C1,
+                ldw=W1x.shape[1], out=V)
+        stats1 = torch.zeros((2, C1), dtype=torch.float64, device=dev)
+        _lib.call("pcl_gather_stats", ptr(U), ptr(V), ptr(src), P, ns, C1, -1.0, ptr(stats1), stream(),
+                  key=("sa_gather_stats", P, C1))
+        sc1, sh1, mu1, rs1 = bn_param(stats1, P, bns[0], C1)
+
+        # ---- layer 2: gather + BN1 + ReLU in the prologue, BN2 statistics in the epilogue ----
+        y2 = torch.empty((P, C2), **f32)
+        stats2 = torch.zeros((2, C2), dtype=torch.float64, device=dev)
+        W2p = pack_weight(W2m)
+        rowgemm(PRO_GATHER_BN_ACT, EPI_STORE_STATS, "sa_l2", W=W2p, U=U, V=V, src=src, ns=ns, vsign=-1.0,
+                scale=sc1, shift=sh1, slope=slope, P=P, K=C1, N=C2, ldw=W2p.shape[1], out=y2, stats=stats2)
+        sc2, sh2, mu2, rs2 = bn_param(stats2, P, bns[1], C2)
+
+        # ---- layer 3: BN2 + ReLU prologue; per-group max/min + BN3 statistics epilogue -------
+        gmax, gmin = torch.empty((G, C3), **f32), torch.empty((G, C3), **f32)
+        amax = torch.empty((G, C3), dtype=torch.int32, device=dev)
+        amin = torch.empty((G, C3), dtype=torch.int32, device=dev)
+        stats3 = torch.zeros((2, C3), dtype=torch.float64, device=dev)
+        W3p = pack_weight(W3m)
+        rowgemm(PRO_BN_ACT, EPI_MAXMIN_STATS, "sa_l3", W=W3p, x0=y2, scale=sc2, shift=sh2, slope=slope,
+                ns=ns, P=P, K=C2, N=C3, ldw=W3p.shape[1], gmax=gmax, gmin=gmin, amax=amax, amin=amin,
+                stats=stats3)
+        sc3, sh3, mu3, rs3 = bn_param(stats3, P, bns[2], C3)
+        out = torch.empty((G, C3), **f32)
+        ysel = torch.empty((G, C3), **f32)
+        selpos = torch.empty((G, C3), dtype=torch.int32, device=dev)
+        _lib.call("pcl_maxpool_finalize", ptr(gmax), ptr(gmin), ptr(amax), ptr(amin), ptr(sc3), ptr(sh3),
+                  float(slope), G, C3, ptr(out), ptr(ysel), ptr(selpos), stream())
+
+        ctx.save_for_backward(xyz_r, feat_r if feat_r is not None else xyz_r, nxyz_r, src, U, V, y2,
+                              W1m, W2m, W3m, sc1, sh1, mu1, rs1, sc2, sh2, mu2, rs2, sc3, mu3, rs3,
+                              out, ysel, selpos)
+        ctx.dims = (B, N, S, ns, C, C1, C2, C3, slope, feat is not None)
+        ctx.w_shapes = (W1.shape, W2.shape, W3.shape)
+        return out.view(B, S, C3)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (xyz_r, feat_r, nxyz_r, src, U, V, y2, W1m, W2m, W3m, sc1, sh1, mu1, rs1, sc2, sh2, mu2, rs2,
+         sc3, mu3, rs3, out, ysel, selpos) = ctx.saved_tensors
+        B, N, S, ns, C, C1, C2, C3, slope, has_feat = ctx.dims
+        dev = dout.device
+        G, P = B * S, B * S * ns
+        f32 = dict(dtype=torch.float32, device=dev)
+        f64 = dict(dtype=torch.float64, device=dev)
+        dout = dout.reshape(G, C3).contiguous().float()
+
+        # ---- max-pool + BN3 sums (routed gradient is sparse: one row per (group, channel)) ----
+        g3s = torch.empty((G, C3), **f32)
+        sums3 = torch.zeros((2, C3), **f64)
+        _lib.call("pcl_maxpool_backward", ptr(dout), ptr(out), ptr(ysel), ptr(sc3), ptr(mu3), ptr(rs3),
+                  float(slope), G, C3, ptr(g3s), ptr(sums3), stream())
+        c1, c2 = sums3[0], sums3[1]                      # = dbeta3, dgamma3
+        W3d = W3m.double()
+        s3 = sc3.double()
+        t = s3 * c2 * rs3.double() / P                    # (C3)
+        Q = W3d.t() @ (t.view(-1, 1) * W3d)               # (C2, C2)
+        const = ((t * mu3.double()) - (s3 * c1 / P)) @ W3d  # q0 - r0, (C2)
+        Wb = pack_weight(torch.cat([W3d.t(), -Q.t()], dim=1).float())      # (C2, C3 + C2)
+
+        # ---- da2 -> dyhat2 (grad at the BN2 output masked by ReLU'), BN2 sums -----------------
+        dyh2 = torch.empty((P, C2), **f32)
+        sums2 = torch.zeros((2, C2), **f64)
+        constf = const.float().contiguous()
+        rowgemm(PRO_G3_A2, EPI_BWD_Y, "sa_b3", W=Wb, g3s=g3s, selpos=selpos, C3=C3, ns=ns, x0=y2,
+                scale=sc2, shift=sh2, slope=slope, P=P, K=C3 + C2, N=C2, ldw=Wb.shape[1], out=dyh2,
+                stats=sums2, ebias=constf, ey=y2, escale=sc2, eshift=sh2, emean=mu2, erstd=rs2,
+                eslope=slope)
+
+        # ---- dW3 from the Gram matrix of a2 and the sparse routed term -------------------------
+        gram = torch.zeros((C2, C2 + 4), **f32)            # [:, :C2] = a2^T a2, [:, C2] = colsum(a2)
+        a2kw = dict(x0=y2, scale=sc2, shift=sh2, slope=slope, K=C2)
+        wgrad(PRO_BN_ACT, a2kw, PRO_BN_ACT_ONES, a2kw, P, C2, C2 + 1, gram, name="sa_gram")
+        T = torch.zeros((C3, C2), **f32)
+        _lib.call("pcl_sel_outer", ptr(g3s), ptr(selpos), ptr(y2), ptr(sc2), ptr(sh2), float(slope), G,
+                  ns, C3, C2, ptr(T), stream(), key=("sa_sel_outer", G, C3, C2))
+        M2, S2 = gram[:, :C2].double(), gram[:, C2].double()
+        dW3 = (T.double() - (s3 * c1 / P).view(-1, 1) * S2.view(1, -1)
+               - t.view(-1, 1) * (W3d @ M2 - mu3.double().view(-1, 1) * S2.view(1, -1))).float()
+
+        # ---- layer 2 backward -----------------------------------------------------------------
+        m1_2 = (sums2[0] / P).float().contiguous()
+        m2_2 = (sums2[1] / P).float().contiguous()
+        dz2kw = dict(x0=dyh2, x1=y2, mean=mu2, rstd=rs2, bscale=sc2, m1=m1_2, m2=m2_2, K=C2)
+        a1kw = dict(U=U, V=V, src=src, ns=ns, vsign=-1.0, scale=sc1, shift=sh1, slope=slope, K=C1)
+        dW2 = torch.zeros((C2, C1), **f32)
+        wgrad(PRO_BN_BWD, dz2kw, PRO_GATHER_BN_ACT, a1kw, P, C2, C1, dW2, name="sa_dw2")
+        dyh1 = torch.empty((P, C1), **f32)
+        sums1 = torch.zeros((2, C1), **f64)
+        W2t = pack_weight(W2m.t().contiguous())             # (C1, C2): da1 = dz2 . W2
+        rowgemm(PRO_BN_BWD, EPI_BWD_GATHER, "sa_b2", W=W2t, P=P, N=C1, ldw=W2t.shape[1], out=dyh1,
+                stats=sums1, U=U, V=V, src=src, ns=ns, vsign=-1.0, escale=sc1, eshift=sh1, emean=mu1,
+                erstd=rs1, eslope=slope, **dz2kw)
+
+        # ---- layer 1 backward: BN1 backward + scatter onto the source points / centres ---------
+        m1_1 = (sums1[0] / P).float().contiguous()
+        m2_1 = (sums1[1] / P).float().contiguous()
+        dU = torch.zeros((B * N, C1), **f32)
+        dV = torch.empty((G, C1), **f32)
+        _lib.call("pcl_gather_bn_backward", ptr(dyh1), ptr(U), ptr(V), ptr(src), ptr(mu1), ptr(rs1),
+                  ptr(sc1), ptr(m1_1), ptr(m2_1), P, ns, C1, -1.0, ptr(dU), ptr(dV), stream(),
+                  key=("sa_b1_scatter", P, C1))
+        # plain dense GEMMs over the N source points (small): dW1 = dU^T [xyz|feat] + dV^T [cen|0]
+        dW1 = torch.empty((C1, 3 + C), **f32)
+        dW1[:, :3] = dU.t() @ xyz_r + dV.t() @ nxyz_r
+        dfeat = None
+        if has_feat:
+            dW1[:, 3:] = dU.t() @ feat_r
+            if ctx.needs_input_grad[2]:
+                dfeat = (dU @ W1m[:, 3:]).view(B, N, C)
+
+        s1, s2, s3s = ctx.w_shapes
+        return (None, None, dfeat, None, dW1.view(s1), dW2.view(s2), dW3.view(s3s),
+                sums1[1].float(), sums1[0].float(), sums2[1].float(), sums2[0].float(),
+                c2.float(), c1.float(), None, None)
+
+
+def fused_sa_branch(xyz, new_xyz, feat, idx, seq, slope: float = 0.0):
+    """Apply one radius branch's shared MLP + max to the neighbourhoods given by idx (B,S,ns)."""
+    convs = [m for m in seq if isinstance(m, (torch.nn.Conv2d, torch.nn.Conv1d))]
+    bns = [m for m in seq if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm1d))]
+    assert len(convs) == 3 and len(bns) == 3 and all(c.bias is None for c in convs)
+    return FusedSAFn.apply(xyz, new_xyz, feat, idx, convs[0].weight, convs[1].weight, convs[2].weight,
+                           bns[0].weight, bns[0].bias, bns[1].weight, bns[1].bias, bns[2].weight,
+                           bns[2].bias, bns, float(slope))

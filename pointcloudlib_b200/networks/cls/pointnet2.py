@@ -13,7 +13,7 @@ import torch
 from torch import nn
 
 from ...misc.ops import BallQueryGrouper, FurthestPointSampler, GroupAll, Module
-from ...sa import mlp_max
+from ...sa import sa_branch
 
 
 class PointNetModuleBase(Module):
@@ -50,9 +50,8 @@ class PointNetModuleBase(Module):
 
         new_feature_list = []
         for i, grouper in enumerate(self.groupers):
-            new_feature = grouper(new_xyz, xyz, feature)  # (B, n_points, n_samples, C)
-            # transpose -> mlps -> transpose -> argmax(dim=2)[1]  (pointnet2.py:53-57)
-            new_feature_list.append(mlp_max(new_feature, self.mlps[i]))
+            # grouper -> transpose -> mlps -> transpose -> argmax(dim=2)[1]  (pointnet2.py:51-57)
+            new_feature_list.append(sa_branch(grouper, self.mlps[i], new_xyz, xyz, feature))
         new_feature = torch.cat(new_feature_list, dim=-1)
         return new_xyz, new_feature
 

@@ -9,6 +9,8 @@ matrix, so the two transposes of the reference disappear.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn.functional as TF
 from torch import nn
@@ -46,6 +48,30 @@ def shared_mlp_rows(h: torch.Tensor, seq: nn.Sequential) -> torch.Tensor:
         elif act is not None:
             h = TF.relu(h)
     return h
+
+
+FUSED = os.environ.get("PCL_FUSED", "1") != "0"
+
+
+def sa_branch(grouper, seq: nn.Sequential, new_xyz, xyz, feature) -> torch.Tensor:
+    """One (grouper, shared MLP) branch of a set-abstraction module -> (B, S, Cout).
+
+    Ball-query branches whose shape the row-GEMM tiles cover take the fused path
+    (pointcloudlib_b200.fused: the grouped tensor and the last layer's output are never
+    materialised); anything else goes grouper -> mlp_max, the reference's own sequence."""
+    from . import functional as F
+    from . import fused
+    from .misc.ops import BallQueryGrouper
+
+    if FUSED and isinstance(grouper, BallQueryGrouper) and grouper.use_xyz and xyz.is_cuda:
+        tr = _triples(seq)
+        chans = [c.weight.shape[0] for c, _, _ in tr]
+        plain = all(c.bias is None and b is not None and b.training and isinstance(a, nn.ReLU)
+                    for c, b, a in tr)
+        if plain and fused.supported(grouper.n_samples, chans, len(tr)):
+            idx, _cnt = F.ball_query(new_xyz, xyz, float(str(grouper.radius)), grouper.n_samples)
+            return fused.fused_sa_branch(xyz, new_xyz, feature, idx, seq, slope=0.0)
+    return mlp_max(grouper(new_xyz, xyz, feature), seq)
 
 
 def mlp_max(grouped: torch.Tensor, seq: nn.Sequential) -> torch.Tensor:

@@ -17,7 +17,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in declared if not hasattr(lib, s)]
     assert not missing, f"declared in pcl_b200.h but not exported: {missing}"
     # and the python binding table covers exactly the header
-    bound = set(_lib._SIGNATURES) | {"pcl_last_error"}
+    bound = set(_lib._SIGNATURES) | set(_lib.FUSED_SYMBOLS) | {"pcl_last_error"}
     assert bound == set(declared), (sorted(bound - set(declared)), sorted(set(declared) - bound))
 
 

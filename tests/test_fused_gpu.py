@@ -1,0 +1,125 @@
+"""Fused set-abstraction stage (row-GEMM kernels, csrc/mlp_fused.cu) against the reference's own op
+sequence: materialised group -> [1x1 conv -> BatchNorm(train) -> ReLU] x3 -> max over n_samples,
+evaluated in float64 on the CPU (oracle/model_oracle.py semantics) and in fp32 on the GPU through
+the unfused path.  Tolerances: forward 1e-3 of the tensor's max magnitude (north_star's bound for
+float reductions); gradients 1e-3 relative L2 for the 3xTF32 path."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+import oracle
+from pointcloudlib_b200 import functional as F
+from pointcloudlib_b200 import fused, sa
+from pointcloudlib_b200.misc.ops import BallQueryGrouper
+from pointcloudlib_b200.synthetic import modelnet_batch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _mlp(chans, cin):
+    layers, c = [], cin
+    for co in chans:
+        layers += [nn.Conv2d(c, co, 1, bias=False), nn.BatchNorm2d(co), nn.ReLU()]
+        c = co
+    seq = nn.Sequential(*layers)
+    g = torch.Generator().manual_seed(1)
+    for m in seq:
+        if isinstance(m, nn.BatchNorm2d):      # non-trivial affine, incl. negative scales (min path)
+            m.weight.data = torch.randn(m.weight.shape, generator=g)
+            m.bias.data = 0.3 * torch.randn(m.bias.shape, generator=g)
+    return seq
+
+
+def _ref64(seq, grouped):
+    """float64 CPU: transpose -> mlps -> transpose -> max(dim=2)  (pointnet2.py:53-57)."""
+    h = seq(grouped.permute(0, 3, 1, 2))
+    return h.permute(0, 2, 3, 1).max(dim=2).values
+
+
+def _rel(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("B,N,S,r,ns,C,chans", [
+    (4, 1024, 128, 0.2, 32, 3, (64, 64, 128)),
+    (4, 1024, 128, 0.1, 16, 3, (32, 32, 64)),
+    (2, 1024, 128, 0.4, 128, 3, (64, 96, 128)),
+    (4, 512, 64, 0.4, 64, 320, (128, 128, 256)),
+    (3, 300, 50, 0.3, 64, 5, (32, 64, 64)),        # ragged: P not a multiple of the 128-row tile
+])
+@pytest.mark.parametrize("x3", [True, False])
+def test_fused_sa_branch_matches_reference_sequence(B, N, S, r, ns, C, chans, x3):
+    xyz, nrm, _ = modelnet_batch(B, N, seed=N + ns)
+    g = torch.Generator().manual_seed(5)
+    feat = nrm if C == 3 else torch.randn(B, N, C, generator=g)
+    seq = _mlp(chans, 3 + C)
+    seq.train()
+    ref_seq = copy.deepcopy(seq).double()
+    grouper = BallQueryGrouper(r, ns, True)
+
+    fidx = oracle.fps(xyz.numpy(), S)
+    new_xyz = torch.from_numpy(oracle.index_points(xyz.numpy(), fidx))
+    ridx, _ = oracle.ball_query(new_xyz.numpy(), xyz.numpy(), float(str(r)), ns)
+    feat64 = feat.double().requires_grad_(True)
+    grouped = torch.from_numpy(oracle.group(new_xyz.numpy(), xyz.numpy(), feat.numpy(), ridx)).double()
+    # make the float64 graph differentiable w.r.t. the features: rebuild the feature part by gather
+    bi = torch.arange(B).view(B, 1, 1).expand(B, S, ns)
+    grouped = torch.cat([grouped[..., :3], feat64[bi, torch.from_numpy(ridx).long()]], dim=-1)
+    ref = _ref64(ref_seq, grouped)
+    gout = torch.randn(ref.shape, generator=g)
+    ref.backward(gout.double())
+
+    seq_d = copy.deepcopy(seq).to(DEV)
+    fd = feat.to(DEV).requires_grad_(True)
+    old = fused.X3
+    fused.X3 = x3
+    try:
+        assert sa.FUSED and fused.supported(ns, list(chans), 3)
+        out = sa.sa_branch(grouper, seq_d, new_xyz.to(DEV), xyz.to(DEV), fd)
+        out.backward(gout.to(DEV))
+        torch.cuda.synchronize()
+    finally:
+        fused.X3 = old
+    # single-pass TF32 (10-bit mantissa) is an opt-in experiment, not the product default: its
+    # gradients are only sanity-bounded here
+    ftol, gtol = (1e-3, 2e-3) if x3 else (1e-2, 2e-1)
+    scale = ref.abs().max().item()
+    assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= ftol * scale
+    for (n, p), (_, q) in zip(seq_d.named_parameters(), ref_seq.named_parameters()):
+        assert _rel(p.grad, q.grad) <= gtol, f"{n}: rel-L2 {_rel(p.grad, q.grad):.3e}"
+    assert _rel(fd.grad, feat64.grad) <= gtol
+    # running statistics follow nn.BatchNorm semantics (momentum 0.1, unbiased variance)
+    for m, mr in zip(seq_d, ref_seq):
+        if isinstance(m, nn.BatchNorm2d):
+            np.testing.assert_allclose(m.running_mean.cpu().numpy(), mr.running_mean.float().numpy(),
+                                       rtol=1e-3, atol=1e-4)
+            np.testing.assert_allclose(m.running_var.cpu().numpy(), mr.running_var.float().numpy(),
+                                       rtol=2e-3, atol=1e-4)
+
+
+def test_fused_equals_unfused_gpu_path():
+    """Same weights, same inputs: fused kernels vs grouper + torch layers on the GPU (fp32)."""
+    B, N, S, ns, C = 8, 2048, 256, 32, 3
+    xyz, nrm, _ = modelnet_batch(B, N, seed=1)
+    seq = _mlp((64, 64, 128), 3 + C).to(DEV).train()
+    seq2 = copy.deepcopy(seq)
+    grouper = BallQueryGrouper(0.2, ns, True)
+    xd, nd = xyz.to(DEV), nrm.to(DEV)
+    new_xyz = F.gather_xyz(xd, F.furthest_point_sample(xd, S))
+    out_f = sa.sa_branch(grouper, seq, new_xyz, xd, nd)
+    sa.FUSED = False
+    try:
+        out_u = sa.sa_branch(grouper, seq2, new_xyz, xd, nd)
+    finally:
+        sa.FUSED = True
+    g = torch.randn_like(out_f)
+    out_f.backward(g)
+    out_u.backward(g)
+    assert (out_f - out_u).abs().max().item() <= 1e-3 * out_u.abs().max().item()
+    for (n, p), (_, q) in zip(seq.named_parameters(), seq2.named_parameters()):
+        assert _rel(p.grad, q.grad) <= 2e-3, n

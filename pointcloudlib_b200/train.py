@@ -66,12 +66,18 @@ class Trainer:
         self.distributed = dist.is_initialized() if distributed is None else distributed
         self.world = dist.get_world_size() if self.distributed else 1
 
+    def reduce_gradients(self) -> float:
+        """Data-parallel exchange: ONE all-reduce (SUM) of the flat gradient bucket; returns the
+        scale (1/world) the optimizer applies.  The operators are per-cloud, so this is the only
+        collective of a step (NCCL over NVLink / NVSwitch on GPUs, gloo in the CPU tests)."""
+        if self.world > 1:
+            dist.all_reduce(self.opt.grads)
+        return 1.0 / self.world
+
     def step(self, *inputs, labels):
         self.opt.zero_grad()
         logits = self.model(*inputs)
         loss = soft_cross_entropy_loss(logits, labels)
         loss.backward()
-        if self.world > 1:
-            dist.all_reduce(self.opt.grads)  # one flat bucket over NVLink / NVSwitch
-        self.opt.step(grad_scale=1.0 / self.world)
+        self.opt.step(grad_scale=self.reduce_gradients())
         return loss.detach()

@@ -75,6 +75,7 @@ def test_trainer_step_matches_torch_sgd():
         if isinstance(m, torch.nn.Dropout):
             m.p = 0.0
     ref_model = copy.deepcopy(model).double()
+    init = [q.detach().clone() for q in ref_model.parameters()]
     model = model.to(DEV)
     xyz, nrm, lab = modelnet_batch(4, 512, seed=5)
     trainer = Trainer(model, lr=1e-3, momentum=0.9)
@@ -87,9 +88,12 @@ def test_trainer_step_matches_torch_sgd():
         ref_loss.backward()
         opt.step()
     _close(loss, ref_loss, "loss after 2 steps", rtol=5e-3)
-    for (n, p), (_, q) in zip(model.named_parameters(), ref_model.named_parameters()):
+    # compare the parameter UPDATES (lr * momentum-filtered gradients) with the gradient tolerance
+    gscale = max((q.detach() - q0).norm().item() for q, q0 in zip(ref_model.parameters(), init))
+    for (n, p), (_, q), q0 in zip(model.named_parameters(), ref_model.named_parameters(), init):
         err = (p.detach().cpu().double() - q.detach()).norm().item()
-        assert err <= 2e-3 * q.detach().norm().item() + 1e-7, f"param {n}: rel-L2 {err:.3e}"
+        upd = max((q.detach() - q0).norm().item(), 1e-3 * gscale)
+        assert err <= 2e-2 * upd, f"param {n}: update rel-L2 {err / upd:.3e}"
 
 
 def _prep(model):

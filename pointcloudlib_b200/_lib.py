@@ -164,9 +164,14 @@ def call(name: str, *args, key=None) -> None:
     check(rc, name)
 
 
+_DEBUG_SYNC = os.environ.get("PCL_DEBUG_SYNC", "0") == "1"  # debugging aid: sync after every call
+
+
 def check(rc: int, what: str = "") -> None:
     global LAUNCHES
     LAUNCHES += 1
+    if _DEBUG_SYNC:
+        torch.cuda.synchronize()
     if rc != 0:
         msg = lib().pcl_last_error().decode(errors="replace")
         kind = "invalid argument" if rc == -1 else "unsupported" if rc == -2 else f"cuda error {rc}" if rc > 0 else f"error {rc}"

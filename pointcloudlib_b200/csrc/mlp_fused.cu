@@ -20,170 +20,9 @@
 //    (a = a_hi + a_lo) which restores fp32-level accuracy.  CTA tile 128 x (16*NT), K streamed in
 //    chunks of 32 through a 2-stage shared-memory pipeline (weights by cp.async, the transformed
 //    A rows through registers), 8 warps as 4(M) x 2(N), persistent CTAs (2 per SM).
-#include "common.cuh"
+#include "mlp_functors.cuh"
 
 namespace pcl {
-
-constexpr int BM = 128;     // rows per CTA tile
-constexpr int BK = 32;      // K chunk
-constexpr int LDK = 36;     // smem row stride of a K chunk (== 4 mod 32: conflict-free fragments)
-constexpr int kThreads = 256;
-
-__device__ __forceinline__ uint32_t f2tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4],
-                                         const uint32_t (&b)[2]) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
-        "{%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-template <int N>
-__device__ __forceinline__ void split_tf32(const float (&x)[N], uint32_t (&hi)[N],
-                                           uint32_t (&lo)[N]) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        hi[i] = f2tf32(x[i]);
-        lo[i] = f2tf32(x[i] - __uint_as_float(hi[i]));
-    }
-}
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
-    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-__device__ __forceinline__ float act_f(float z, float slope) { return z > 0.f ? z : z * slope; }
-__device__ __forceinline__ float4 ld4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
-__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
-
-// ------------------------------------------------------------------------------------------
-// Prologue functors: 4 consecutive channels k..k+3 (k % 4 == 0) of operand row p (p < P).
-// ------------------------------------------------------------------------------------------
-struct ProPlain2 {
-    static __device__ __forceinline__ float4 load(const PclRowGemm &a, long long p, int k) {
-        float v[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int kk = k + j;
-            float x = 0.f;
-            if (kk < a.c0)
-                x = __ldg(a.x0 + p * a.c0 + kk);
-            else if (kk < a.c0 + a.c1)
-                x = __ldg(a.x1 + p * a.c1 + (kk - a.c0));
-            v[j] = x;
-        }
-        return make_float4(v[0], v[1], v[2], v[3]);
-    }
-};
-__device__ __forceinline__ float4 bn_act4(float4 y, const float *scale, const float *shift, int k,
-                                          float slope) {
-    const float4 s = ld4(scale + k), h = ld4(shift + k);
-    return make_float4(act_f(fmaf(s.x, y.x, h.x), slope), act_f(fmaf(s.y, y.y, h.y), slope),
-                       act_f(fmaf(s.z, y.z, h.z), slope), act_f(fmaf(s.w, y.w, h.w), slope));
-}
-struct ProBnAct {
-    static __device__ __forceinline__ float4 load(const PclRowGemm &a, long long p, int k) {
-        if (k >= a.K) return f4zero();
-        return bn_act4(ld4(a.x0 + p * a.K + k), a.scale, a.shift, k, a.slope);
-    }
-};
-__device__ __forceinline__ float4 gather_y4(const PclRowGemm &a, long long p, int k, int C) {
-    const float4 u = ld4(a.U + (long long)__ldg(a.src + p) * C + k);
-    if (a.V == nullptr) return u;
-    const float4 v = ld4(a.V + (p / a.ns) * C + k);
-    return make_float4(fmaf(a.vsign, v.x, u.x), fmaf(a.vsign, v.y, u.y), fmaf(a.vsign, v.z, u.z),
-                       fmaf(a.vsign, v.w, u.w));
-}
-// [act(bn(x0)) | 1 | 0 ...]: the extra ones column turns a Gram wgrad into (A^T.A | column sums)
-struct ProBnActOnes {
-    static __device__ __forceinline__ float4 load(const PclRowGemm &a, long long p, int k) {
-        if (k >= a.K) return make_float4(k == a.K ? 1.f : 0.f, 0.f, 0.f, 0.f);
-        return bn_act4(ld4(a.x0 + p * a.K + k), a.scale, a.shift, k, a.slope);
-    }
-};
-struct ProGatherBnAct {
-    static __device__ __forceinline__ float4 load(const PclRowGemm &a, long long p, int k) {
-        if (k >= a.K) return f4zero();
-        return bn_act4(gather_y4(a, p, k, a.K), a.scale, a.shift, k, a.slope);
-    }
-};
-struct ProBnBwd {
-    static __device__ __forceinline__ float4 load(const PclRowGemm &a, long long p, int k) {
-        if (k >= a.K) return f4zero();
-        const float4 d = ld4(a.x0 + p * a.K + k), y = ld4(a.x1 + p * a.K + k);
-        const float4 mu = ld4(a.mean + k), rs = ld4(a.rstd + k), bs = ld4(a.bscale + k);
-        const float4 m1 = ld4(a.m1 + k), m2 = ld4(a.m2 + k);
-        return make_float4(bs.x * (d.x - m1.x - (y.x - mu.x) * rs.x * m2.x),
-                           bs.y * (d.y - m1.y - (y.y - mu.y) * rs.y * m2.y),
-                           bs.z * (d.z - m1.z - (y.z - mu.z) * rs.z * m2.z),
-                           bs.w * (d.w - m1.w - (y.w - mu.w) * rs.w * m2.w));
-    }
-};
-struct ProG3A2 {
-    static __device__ __forceinline__ float4 load(const PclRowGemm &a, long long p, int k) {
-        if (k < a.C3) {
-            const long long g = p / a.ns;
-            const int r = (int)(p - g * a.ns);
-            const int4 sp = __ldg(reinterpret_cast<const int4 *>(a.selpos + g * a.C3 + k));
-            const float4 gv = ld4(a.g3s + g * a.C3 + k);
-            return make_float4(sp.x == r ? gv.x : 0.f, sp.y == r ? gv.y : 0.f,
-                               sp.z == r ? gv.z : 0.f, sp.w == r ? gv.w : 0.f);
-        }
-        const int kk = k - a.C3, C2 = a.K - a.C3;
-        if (kk >= C2) return f4zero();
-        return bn_act4(ld4(a.x0 + p * C2 + kk), a.scale, a.shift, kk, a.slope);
-    }
-};
-
-// ------------------------------------------------------------------------------------------
-// Epilogue functors.  rowpass(): v = 4 accumulator columns n..n+3 of row p; returns the value to
-// store in v and the "second statistic" term in q (sum v and sum q are accumulated per column).
-// ------------------------------------------------------------------------------------------
-struct EpiStore {
-    static constexpr bool kStore = true, kStats = false, kMaxMin = false;
-    static __device__ __forceinline__ void rowpass(const PclRowGemm &, float4 &, float4 &, long long, int) {}
-};
-struct EpiStoreStats {
-    static constexpr bool kStore = true, kStats = true, kMaxMin = false;
-    static __device__ __forceinline__ void rowpass(const PclRowGemm &, float4 &v, float4 &q, long long, int) {
-        q = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
-    }
-};
-struct EpiMaxMinStats {
-    static constexpr bool kStore = false, kStats = true, kMaxMin = true;
-    static __device__ __forceinline__ void rowpass(const PclRowGemm &, float4 &v, float4 &q, long long, int) {
-        q = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
-    }
-};
-__device__ __forceinline__ void bwd_act4(const PclRowGemm &a, float4 &v, float4 &q, float4 y, int n) {
-    const float4 b = a.ebias ? ld4(a.ebias + n) : f4zero();
-    const float4 s = ld4(a.escale + n), h = ld4(a.eshift + n), mu = ld4(a.emean + n),
-                 rs = ld4(a.erstd + n);
-    v.x = (v.x + b.x) * (fmaf(s.x, y.x, h.x) > 0.f ? 1.f : a.eslope);
-    v.y = (v.y + b.y) * (fmaf(s.y, y.y, h.y) > 0.f ? 1.f : a.eslope);
-    v.z = (v.z + b.z) * (fmaf(s.z, y.z, h.z) > 0.f ? 1.f : a.eslope);
-    v.w = (v.w + b.w) * (fmaf(s.w, y.w, h.w) > 0.f ? 1.f : a.eslope);
-    q = make_float4(v.x * (y.x - mu.x) * rs.x, v.y * (y.y - mu.y) * rs.y,
-                    v.z * (y.z - mu.z) * rs.z, v.w * (y.w - mu.w) * rs.w);
-}
-struct EpiBwdY {
-    static constexpr bool kStore = true, kStats = true, kMaxMin = false;
-    static __device__ __forceinline__ void rowpass(const PclRowGemm &a, float4 &v, float4 &q, long long p, int n) {
-        bwd_act4(a, v, q, ld4(a.ey + p * a.N + n), n);
-    }
-};
-struct EpiBwdGather {
-    static constexpr bool kStore = true, kStats = true, kMaxMin = false;
-    static __device__ __forceinline__ void rowpass(const PclRowGemm &a, float4 &v, float4 &q, long long p, int n) {
-        bwd_act4(a, v, q, gather_y4(a, p, n, a.N), n);
-    }
-};
 
 // ------------------------------------------------------------------------------------------
 // Row GEMM.  grid = persistent CTAs; dynamic smem = 2 stages x (BM + BN) x LDK floats
@@ -784,12 +623,26 @@ static int wgrad_l(const PclRowGemm &al, int pl, const PclRowGemm &ar, int pr, l
 
 }  // namespace pcl
 
+namespace pcl {
+int rowgemm_tc_dispatch(const PclRowGemm &a, int pro, int epi, cudaStream_t st);  // rowgemm_tc.cu
+int wgrad_tc_dispatch(const PclRowGemm &al, int pl, const PclRowGemm &ar, int pr, long long P, int M,
+                      int N, float *out, int ldo, cudaStream_t st);                 // wgrad_tc.cu
+static PclRowGemm with_ns_shift(PclRowGemm a) {
+    a.reserved = -1;
+    if (a.ns > 0 && (a.ns & (a.ns - 1)) == 0) {
+        int s = 0;
+        while ((1 << s) < a.ns) ++s;
+        a.reserved = s;
+    }
+    return a;
+}
+}
 using namespace pcl;
 
 extern "C" int pcl_rowgemm(const PclRowGemm *args, int prologue, int epilogue, int x3,
                            void *stream) {
     PCL_REQUIRE(args, "pcl_rowgemm: null args");
-    const PclRowGemm &a = *args;
+    const PclRowGemm a = with_ns_shift(*args);
     PCL_REQUIRE(a.P >= 0 && a.K >= 1 && a.N >= 16, "pcl_rowgemm: bad shape P=%lld K=%d N=%d", a.P,
                 a.K, a.N);
     PCL_REQUIRE(a.W && a.ldw >= a.K && a.ldw % 32 == 0, "pcl_rowgemm: W must be packed, ldw %% 32 == 0");
@@ -800,6 +653,8 @@ extern "C" int pcl_rowgemm(const PclRowGemm *args, int prologue, int epilogue, i
                     "pcl_rowgemm: max/min epilogue needs ns | 128 (ns=%d)", a.ns);
     if (a.P == 0) return PCL_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    // x3: 0 = mma.sync TF32, 1 = mma.sync 3xTF32, 2 = tcgen05 3xTF32 (W = [raw | hi | lo] stacked)
+    if (x3 == 2) return rowgemm_tc_dispatch(a, prologue, epilogue, st);
     return x3 ? dispatch_pro<true>(a, prologue, epilogue, st)
               : dispatch_pro<false>(a, prologue, epilogue, st);
 }
@@ -811,8 +666,12 @@ extern "C" int pcl_wgrad(const PclRowGemm *args_l, int prologue_l, const PclRowG
     PCL_REQUIRE(P >= 0 && M >= 1 && N >= 1 && ldo >= N, "pcl_wgrad: bad shape");
     if (P == 0) return PCL_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    return x3 ? wgrad_l<true>(*args_l, prologue_l, *args_r, prologue_r, P, M, N, out, ldo, st)
-              : wgrad_l<false>(*args_l, prologue_l, *args_r, prologue_r, P, M, N, out, ldo, st);
+    const PclRowGemm al = with_ns_shift(*args_l), ar = with_ns_shift(*args_r);
+    // x3 == 2: tcgen05 core when the output fits one 128 x 160 accumulator tile
+    if (x3 == 2 && M <= 128 && N <= 160)
+        return wgrad_tc_dispatch(al, prologue_l, ar, prologue_r, P, M, N, out, ldo, st);
+    return x3 ? wgrad_l<true>(al, prologue_l, ar, prologue_r, P, M, N, out, ldo, st)
+              : wgrad_l<false>(al, prologue_l, ar, prologue_r, P, M, N, out, ldo, st);
 }
 
 extern "C" int pcl_gather_stats(const float *U, const float *V, const int32_t *src, long long P,

@@ -1,0 +1,383 @@
+// rowgemm_tc.cu — the fused row-GEMM on Blackwell's 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// Same contract, prologue and epilogue functors as rowgemm_kernel in mlp_fused.cu (see there and
+// include/pcl_b200.h); only the MMA core differs:
+//   * the 128 x BN fp32 accumulator lives in TENSOR MEMORY (tcgen05.alloc, BN <= 128 columns), not
+//     in registers; one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8);
+//   * operands are staged by the CTA's threads directly in the UMMA canonical K-major SWIZZLE_128B
+//     layout (8-row x 128-byte atoms, 16-byte chunks XOR-swizzled by row), so the prologue
+//     (gather / BatchNorm / ReLU / BatchNorm-backward / routed one-hot) writes what the tensor core
+//     reads with no fragment loads at all;
+//   * fp32-equivalent accuracy by the 3xTF32 split done ONCE per element while staging:
+//     a = a_hi + a_lo (both exactly representable in TF32), D += a_lo.w_hi + a_hi.w_lo + a_hi.w_hi;
+//     the weights arrive pre-split from the host ([raw | hi | lo] stacked);
+//   * 2-stage smem ring released by tcgen05.commit -> mbarrier; the next chunk's global loads are
+//     issued one iteration ahead (across tile boundaries) so HBM latency overlaps MMA + epilogue;
+//   * epilogue: tcgen05.ld 32x32b (each warp its own 32-lane quarter) -> smem tile -> the same
+//     coalesced row pass / per-group column scan as the mma.sync kernel.
+#include "mlp_functors.cuh"
+
+namespace pcl {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        " selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                            uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 16 consecutive fp32 columns of this thread's TMEM lane (warp w reads lanes 32*(w%4)..+31)
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: start>>4 | LBO(unused)=1 | SBO=1024B |
+// version=1 (sm_100) | layout_type=2.  (cute/arch/mma_sm100_desc.hpp bit layout.)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// byte offset of 16-byte chunk c (0..7) of row r inside a K-major SW128 tile (tile base 1024-aligned)
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) {
+    return ((uint32_t)(r >> 3) << 10) + ((uint32_t)(r & 7) << 7) + ((uint32_t)((c ^ r) & 7) << 4);
+}
+
+// dynamic smem: 1024 (alignment slack) + max(one stage, epilogue tile).  One stage = A_hi, A_lo
+// (128 x 128 B each) + W_hi, W_lo (BN x 128 B each).  TWO CTAs per SM: while one CTA's MMAs run, the
+// other stages its next chunk / runs its epilogue (each CTA owns BN<=128 of the 512 TMEM columns).
+template <int BN, class Pro, class Epi>
+__global__ void __launch_bounds__(256, 2) rowgemm_tc_kernel(const PclRowGemm a) {
+    constexpr int BMt = 128;
+    constexpr int A_TILE = BMt * 128, W_TILE = BN * 128;  // bytes
+    constexpr int LDT = BN + 4;
+    constexpr int NW = BN / 16;  // W float4 per thread per chunk (hi and lo together)
+    constexpr uint32_t TCOLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : 128);
+    // instruction descriptor: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), K-major both, N>>3, M>>4
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                               ((uint32_t)(BMt >> 4) << 24);
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    // 1024-byte alignment by offsetting inside the shared array (keeps the address space known to
+    // the compiler: st.shared / ld.shared instead of generic accesses)
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ __align__(16) float s_ps[2][1024];  // per-tile column partial sums [stat][row-slot*BN + col]
+    __shared__ __align__(8) uint64_t s_bar[2];  // stage-free, accumulator-full
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_pmx[8][BN], s_pmn[8][BN];   // partial max / min of the column scan
+    __shared__ int s_pix[8][BN], s_pin[8][BN];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(&s_tmem)),
+                     "r"(TCOLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        mbar_init(smem_u32(&s_bar[0]), 1);
+        mbar_init(smem_u32(&s_bar[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t bar_free = smem_u32(&s_bar[0]);
+    const uint32_t bar_full = smem_u32(&s_bar[1]);
+
+    const long long n_tiles = (a.P + BMt - 1) / BMt;
+    const int n_pass = a.N / BN;
+    const int nk = a.ldw / 32;
+    const float *Whi = a.W + (long long)a.N * a.ldw;  // W = [raw | hi | lo]; lo = hi + N*ldw
+
+    uint8_t *sAhi = smem, *sAlo = sAhi + A_TILE, *sWhi = sAlo + A_TILE, *sWlo = sWhi + W_TILE;
+    const int a_row = tid >> 3, a_c = tid & 7;
+    constexpr int QN = BN / 4;
+    constexpr int RPS = 256 / QN;
+    const int e_q = tid % QN, e_r = tid / QN;
+    const bool e_active = tid < RPS * QN;
+    // column-scan map: PARTS threads per column, each scanning RPP consecutive rows
+    constexpr int PARTS = 256 / BN >= 8 ? 8 : 256 / BN;
+    constexpr int RPP = BMt / PARTS;
+    const int s_col = tid % BN, s_part = tid / BN;
+
+    uint32_t uses = 0, tiles_done = 0;
+
+    for (int pass = 0; pass < n_pass; ++pass) {
+        const int n0 = pass * BN;
+        // thread tid < 2*BN owns the fp64 accumulator of (stat = tid / BN, column = tid % BN)
+        double acc_d = 0.0;
+        __syncthreads();
+
+        long long tile = blockIdx.x;
+        int kc = 0;
+        bool have = tile < n_tiles;
+        float4 ra[4], rw[NW];
+        auto prefetch = [&](long long tl, int kcc) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const long long p = tl * BMt + a_row + 32 * i;
+                ra[i] = p < a.P ? Pro::load(a, p, kcc * 32 + a_c * 4) : f4zero();
+            }
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                // element e of [hi: BN x 8 chunks | lo: BN x 8 chunks]
+                const int e = tid + 256 * i, half = e / (BN * 8), r = e % (BN * 8);
+                const int n = r >> 3, c = r & 7;
+                rw[i] = ld4(Whi + (long long)half * a.N * a.ldw + (long long)(n0 + n) * a.ldw + kcc * 32 + c * 4);
+            }
+        };
+        if (have) prefetch(tile, 0);
+
+        while (have) {
+            if (uses > 0) mbar_wait(bar_free, (uses - 1) & 1);  // previous chunk's MMAs have read the stage
+            ++uses;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                const int e = tid + 256 * i, half = e / (BN * 8), r = e % (BN * 8);
+                *reinterpret_cast<float4 *>((half ? sWlo : sWhi) + sw128_off(r >> 3, r & 7)) = rw[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t off = sw128_off(a_row + 32 * i, a_c);
+                float x[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w};
+                uint32_t hi[4], lo[4];
+                split_tf32<4>(x, hi, lo);
+                *reinterpret_cast<uint4 *>(sAhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4 *>(sAlo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                const uint64_t dAhi = umma_desc_sw128(smem_u32(sAhi)), dAlo = umma_desc_sw128(smem_u32(sAlo));
+                const uint64_t dWhi = umma_desc_sw128(smem_u32(sWhi)), dWlo = umma_desc_sw128(smem_u32(sWlo));
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t adv = (uint64_t)(ks * 2);  // 32 bytes per K=8 step, in 16-byte units
+                    tc_mma_tf32(tmem, dAlo + adv, dWhi + adv, IDESC, (kc > 0 || ks > 0) ? 1u : 0u);
+                    tc_mma_tf32(tmem, dAhi + adv, dWlo + adv, IDESC, 1u);
+                    tc_mma_tf32(tmem, dAhi + adv, dWhi + adv, IDESC, 1u);
+                }
+                tc_commit(bar_free);
+                if (kc == nk - 1) tc_commit(bar_full);
+            }
+            int kc_n = kc + 1;
+            long long tile_n = tile;
+            if (kc_n == nk) {
+                kc_n = 0;
+                tile_n += gridDim.x;
+            }
+            const bool have_n = tile_n < n_tiles;
+            if (have_n) prefetch(tile_n, kc_n);  // global loads in flight during the MMAs (+ epilogue)
+
+            if (kc == nk - 1) {
+                // ---------------- epilogue of this tile ----------------
+                const long long p0 = tile * BMt;
+                mbar_wait(bar_full, tiles_done & 1);
+                ++tiles_done;
+                tc_fence_after();
+                float *T = reinterpret_cast<float *>(smem);  // aliases the stage (all MMAs done)
+                {
+                    const int q = warp & 3, h = warp >> 2;
+                    const int row = q * 32 + lane;
+#pragma unroll
+                    for (int cc = 0; cc < BN / 32; ++cc) {
+                        const int c0 = h * (BN / 2) + cc * 16;
+                        float v[16];
+                        tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<float4 *>(T + row * LDT + c0 + 4 * j) =
+                                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                }
+                tc_fence_before();
+                __syncthreads();
+                if (e_active) {
+                    float4 s = f4zero(), q2 = f4zero();
+                    for (int r = e_r; r < BMt; r += RPS) {
+                        const long long p = p0 + r;
+                        if (p >= a.P) break;
+                        float4 v = *reinterpret_cast<const float4 *>(T + r * LDT + e_q * 4);
+                        float4 q = f4zero();
+                        Epi::rowpass(a, v, q, p, n0 + e_q * 4);
+                        if (Epi::kStore)
+                            *reinterpret_cast<float4 *>(a.out + p * a.N + n0 + e_q * 4) = v;
+                        if (Epi::kStats) {
+                            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                            q2.x += q.x; q2.y += q.y; q2.z += q.z; q2.w += q.w;
+                        }
+                    }
+                    if (Epi::kStats) {  // fp32 partials of <= 128/RPS rows -> smem (no atomics)
+                        *reinterpret_cast<float4 *>(&s_ps[0][e_r * BN + e_q * 4]) = s;
+                        *reinterpret_cast<float4 *>(&s_ps[1][e_r * BN + e_q * 4]) = q2;
+                    }
+                }
+                if (Epi::kMaxMin) {
+                    // PARTS threads per column, each scanning RPP consecutive rows; groups of ns rows
+                    // (ns | 128) either fit inside a part (written directly) or span several parts
+                    // (partials combined through shared memory).
+                    const int ns = a.ns;
+                    const int rows = (int)min((long long)BMt, a.P - p0);
+                    const bool direct = ns <= RPP;
+                    const int sub = direct ? ns : RPP;
+                    if (s_part < PARTS) {
+                        const int rbeg = s_part * RPP;
+                        for (int r0 = rbeg; r0 < rbeg + RPP && r0 < rows; r0 += sub) {
+                            float mx = T[r0 * LDT + s_col], mn = mx;
+                            int imx = 0, imn = 0;
+#pragma unroll 4
+                            for (int l = 1; l < sub; ++l) {
+                                const float v = T[(r0 + l) * LDT + s_col];
+                                if (v > mx) { mx = v; imx = l; }
+                                if (v < mn) { mn = v; imn = l; }
+                            }
+                            if (direct) {
+                                const long long o = ((p0 + r0) / ns) * a.N + n0 + s_col;
+                                a.gmax[o] = mx; a.gmin[o] = mn; a.amax[o] = imx; a.amin[o] = imn;
+                            } else {
+                                s_pmx[s_part][s_col] = mx; s_pmn[s_part][s_col] = mn;
+                                s_pix[s_part][s_col] = imx; s_pin[s_part][s_col] = imn;
+                            }
+                        }
+                    }
+                    if (!direct) {
+                        __syncthreads();
+                        const int ppg = ns / RPP;  // parts per group
+                        if (tid < BN) {
+                            for (int g0 = 0; g0 * ns < rows; ++g0) {
+                                float mx = s_pmx[g0 * ppg][tid], mn = s_pmn[g0 * ppg][tid];
+                                int imx = s_pix[g0 * ppg][tid], imn = s_pin[g0 * ppg][tid];
+                                for (int j = 1; j < ppg; ++j) {
+                                    const int pt = g0 * ppg + j;
+                                    if (s_pmx[pt][tid] > mx) { mx = s_pmx[pt][tid]; imx = j * RPP + s_pix[pt][tid]; }
+                                    if (s_pmn[pt][tid] < mn) { mn = s_pmn[pt][tid]; imn = j * RPP + s_pin[pt][tid]; }
+                                }
+                                const long long o = ((p0 + (long long)g0 * ns) / ns) * a.N + n0 + tid;
+                                a.gmax[o] = mx; a.gmin[o] = mn; a.amax[o] = imx; a.amin[o] = imn;
+                            }
+                        }
+                    }
+                }
+                __syncthreads();  // T consumed before the next chunk overwrites the stage
+                if (Epi::kStats && tid < 2 * BN) {
+                    const float *ps = &s_ps[tid / BN][tid % BN];
+                    float t = 0.f;
+#pragma unroll
+                    for (int r = 0; r < RPS; ++r) t += ps[r * BN];
+                    acc_d += (double)t;
+                }
+            }
+            tile = tile_n;
+            kc = kc_n;
+            have = have_n;
+        }
+        __syncthreads();
+        if (Epi::kStats && tid < 2 * BN)
+            atomicAdd(a.stats + (long long)(tid / BN) * a.N + n0 + (tid % BN), acc_d);
+        __syncthreads();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TCOLS)
+                     : "memory");
+    }
+}
+
+template <int BN, class Pro, class Epi>
+static int launch_tc(const PclRowGemm &a, cudaStream_t st) {
+    const size_t stage = (size_t)2 * 128 * 128 + (size_t)2 * BN * 128;
+    const size_t tile = (size_t)128 * (BN + 4) * sizeof(float);
+    const size_t smem = 1024 + (stage > tile ? stage : tile);
+    auto kern = rowgemm_tc_kernel<BN, Pro, Epi>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("pcl_rowgemm(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    const long long n_tiles = (a.P + 127) / 128;
+    long long grid = 2LL * kNumSMs;  // two persistent CTAs per SM
+    if (grid > n_tiles) grid = n_tiles;
+    kern<<<(unsigned)grid, 256, smem, st>>>(a);
+    return check_launch("pcl_rowgemm(tcgen05)");
+}
+
+template <class Pro, class Epi>
+static int tc_dispatch_bn(const PclRowGemm &a, cudaStream_t st) {
+    const int N = a.N;
+    if (N % 128 == 0) return launch_tc<128, Pro, Epi>(a, st);
+    if (N == 96) return launch_tc<96, Pro, Epi>(a, st);
+    if (N % 64 == 0) return launch_tc<64, Pro, Epi>(a, st);
+    if (N % 32 == 0) return launch_tc<32, Pro, Epi>(a, st);
+    set_error("pcl_rowgemm: N=%d must be a multiple of 32 (or 96)", N);
+    return PCL_ERR_UNSUPPORTED;
+}
+
+// called from pcl_rowgemm (mlp_fused.cu) when x3 == 2
+int rowgemm_tc_dispatch(const PclRowGemm &a, int pro, int epi, cudaStream_t st) {
+#define PCL_COMBO(P_, E_, PRO_, EPI_) \
+    if (pro == P_ && epi == E_) return tc_dispatch_bn<PRO_, EPI_>(a, st)
+    PCL_COMBO(PCL_PRO_PLAIN2, PCL_EPI_STORE, ProPlain2, EpiStore);
+    PCL_COMBO(PCL_PRO_PLAIN2, PCL_EPI_STORE_STATS, ProPlain2, EpiStoreStats);
+    PCL_COMBO(PCL_PRO_BN_ACT, PCL_EPI_STORE_STATS, ProBnAct, EpiStoreStats);
+    PCL_COMBO(PCL_PRO_BN_ACT, PCL_EPI_MAXMIN_STATS, ProBnAct, EpiMaxMinStats);
+    PCL_COMBO(PCL_PRO_GATHER_BN_ACT, PCL_EPI_STORE_STATS, ProGatherBnAct, EpiStoreStats);
+    PCL_COMBO(PCL_PRO_GATHER_BN_ACT, PCL_EPI_MAXMIN_STATS, ProGatherBnAct, EpiMaxMinStats);
+    PCL_COMBO(PCL_PRO_BN_BWD, PCL_EPI_STORE, ProBnBwd, EpiStore);
+    PCL_COMBO(PCL_PRO_BN_BWD, PCL_EPI_BWD_Y, ProBnBwd, EpiBwdY);
+    PCL_COMBO(PCL_PRO_BN_BWD, PCL_EPI_BWD_GATHER, ProBnBwd, EpiBwdGather);
+    PCL_COMBO(PCL_PRO_G3_A2, PCL_EPI_BWD_Y, ProG3A2, EpiBwdY);
+    PCL_COMBO(PCL_PRO_G3_A2, PCL_EPI_BWD_GATHER, ProG3A2, EpiBwdGather);
+#undef PCL_COMBO
+    set_error("pcl_rowgemm: unsupported (prologue %d, epilogue %d) pair", pro, epi);
+    return PCL_ERR_UNSUPPORTED;
+}
+
+}  // namespace pcl

@@ -39,8 +39,10 @@ class PclRowGemm(ctypes.Structure):
                 + [(n, ctypes.c_int) for n in _INT_FIELDS] + [(n, ctypes.c_float) for n in _FLT_FIELDS])
 
 
-# x3 = True: 3xTF32 split MMA (fp32-equivalent accuracy).  False: single-pass TF32.
-X3 = True
+# MMA core of the row GEMMs: 2 = tcgen05.mma kind::tf32 + TMEM accumulators, 3xTF32 split (default);
+# 1 = mma.sync 3xTF32 (fallback / A-B comparison); 0 = mma.sync single-pass TF32 (experiment).
+# pcl_wgrad follows the same switch (tcgen05 when the output fits one 128 x 160 accumulator tile).
+MODE = int(__import__("os").environ.get("PCL_MMA_MODE", "2"))
 
 _bound = False
 
@@ -88,21 +90,27 @@ def _args(**kw):
     return a, keep
 
 
+def _tf32_rna(x: torch.Tensor) -> torch.Tensor:
+    """cvt.rna.tf32.f32 on the host: round the magnitude to 10 mantissa bits, ties away."""
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 def pack_weight(w: torch.Tensor) -> torch.Tensor:
-    """(N, K) -> (N, ceil32(K)) zero-padded, contiguous fp32."""
+    """(N, K) -> (3, N, ceil32(K)) zero-padded fp32: [raw | tf32 hi | tf32 lo] (w = hi + lo + O(2^-22))."""
     N, K = w.shape
     ld = (K + 31) // 32 * 32
-    if ld == K:
-        return w.contiguous().float()
-    out = torch.zeros((N, ld), dtype=torch.float32, device=w.device)
-    out[:, :K] = w
+    out = torch.zeros((3, N, ld), dtype=torch.float32, device=w.device)
+    out[0, :, :K] = w
+    out[1] = _tf32_rna(out[0])
+    out[2] = _tf32_rna(out[0] - out[1])
     return out
 
 
 def rowgemm(pro: int, epi: int, name: str, **kw):
     _bind()
     a, keep = _args(**kw)
-    _lib.call("pcl_rowgemm", ctypes.byref(a), pro, epi, int(X3), stream(), key=(name, pro, epi, a.P, a.K, a.N))
+    _lib.call("pcl_rowgemm", ctypes.byref(a), pro, epi, int(MODE), stream(), key=(name, pro, epi, a.P, a.K, a.N))
     return keep
 
 
@@ -111,7 +119,7 @@ def wgrad(pro_l, kw_l, pro_r, kw_r, P, M, N, out, name="wgrad"):
     al, k1 = _args(**kw_l)
     ar, k2 = _args(**kw_r)
     _lib.call("pcl_wgrad", ctypes.byref(al), pro_l, ctypes.byref(ar), pro_r, P, M, N, ptr(out),
-              out.stride(0), int(X3), stream(), key=(name, P, M, N))
+              out.stride(0), int(MODE), stream(), key=(name, P, M, N))
 
 
 def bn_param(stats, P, bn, C):
@@ -162,11 +170,11 @@ class FusedSAFn(torch.autograd.Function):
         U = torch.empty((B * N, C1), **f32)
         W1p = pack_weight(W1m)
         rowgemm(PRO_PLAIN2, EPI_STORE, "sa_proj_u", W=W1p, x0=xyz_r, x1=feat_r, c0=3, c1=C, P=B * N,
-                K=3 + C, N=C1, ldw=W1p.shape[1], out=U)
+                K=3 + C, N=C1, ldw=W1p.shape[-1], out=U)
         V = torch.empty((G, C1), **f32)
         W1x = pack_weight(W1m[:, :3])
         rowgemm(PRO_PLAIN2, EPI_STORE, "sa_proj_v", W=W1x, x0=nxyz_r, c0=3, c1=0, P=G, K=3, N=C1,
-                ldw=W1x.shape[1], out=V)
+                ldw=W1x.shape[-1], out=V)
         stats1 = torch.zeros((2, C1), dtype=torch.float64, device=dev)
         _lib.call("pcl_gather_stats", ptr(U), ptr(V), ptr(src), P, ns, C1, -1.0, ptr(stats1), stream(),
                   key=("sa_gather_stats", P, C1))
@@ -177,7 +185,7 @@ class FusedSAFn(torch.autograd.Function):
         stats2 = torch.zeros((2, C2), dtype=torch.float64, device=dev)
         W2p = pack_weight(W2m)
         rowgemm(PRO_GATHER_BN_ACT, EPI_STORE_STATS, "sa_l2", W=W2p, U=U, V=V, src=src, ns=ns, vsign=-1.0,
-                scale=sc1, shift=sh1, slope=slope, P=P, K=C1, N=C2, ldw=W2p.shape[1], out=y2, stats=stats2)
+                scale=sc1, shift=sh1, slope=slope, P=P, K=C1, N=C2, ldw=W2p.shape[-1], out=y2, stats=stats2)
         sc2, sh2, mu2, rs2 = bn_param(stats2, P, bns[1], C2)
 
         # ---- layer 3: BN2 + ReLU prologue; per-group max/min + BN3 statistics epilogue -------
@@ -187,7 +195,7 @@ class FusedSAFn(torch.autograd.Function):
         stats3 = torch.zeros((2, C3), dtype=torch.float64, device=dev)
         W3p = pack_weight(W3m)
         rowgemm(PRO_BN_ACT, EPI_MAXMIN_STATS, "sa_l3", W=W3p, x0=y2, scale=sc2, shift=sh2, slope=slope,
-                ns=ns, P=P, K=C2, N=C3, ldw=W3p.shape[1], gmax=gmax, gmin=gmin, amax=amax, amin=amin,
+                ns=ns, P=P, K=C2, N=C3, ldw=W3p.shape[-1], gmax=gmax, gmin=gmin, amax=amax, amin=amin,
                 stats=stats3)
         sc3, sh3, mu3, rs3 = bn_param(stats3, P, bns[2], C3)
         out = torch.empty((G, C3), **f32)
@@ -232,7 +240,7 @@ class FusedSAFn(torch.autograd.Function):
         sums2 = torch.zeros((2, C2), **f64)
         constf = const.float().contiguous()
         rowgemm(PRO_G3_A2, EPI_BWD_Y, "sa_b3", W=Wb, g3s=g3s, selpos=selpos, C3=C3, ns=ns, x0=y2,
-                scale=sc2, shift=sh2, slope=slope, P=P, K=C3 + C2, N=C2, ldw=Wb.shape[1], out=dyh2,
+                scale=sc2, shift=sh2, slope=slope, P=P, K=C3 + C2, N=C2, ldw=Wb.shape[-1], out=dyh2,
                 stats=sums2, ebias=constf, ey=y2, escale=sc2, eshift=sh2, emean=mu2, erstd=rs2,
                 eslope=slope)
 
@@ -257,7 +265,7 @@ class FusedSAFn(torch.autograd.Function):
         dyh1 = torch.empty((P, C1), **f32)
         sums1 = torch.zeros((2, C1), **f64)
         W2t = pack_weight(W2m.t().contiguous())             # (C1, C2): da1 = dz2 . W2
-        rowgemm(PRO_BN_BWD, EPI_BWD_GATHER, "sa_b2", W=W2t, P=P, N=C1, ldw=W2t.shape[1], out=dyh1,
+        rowgemm(PRO_BN_BWD, EPI_BWD_GATHER, "sa_b2", W=W2t, P=P, N=C1, ldw=W2t.shape[-1], out=dyh1,
                 stats=sums1, U=U, V=V, src=src, ns=ns, vsign=-1.0, escale=sc1, eshift=sh1, emean=mu1,
                 erstd=rs1, eslope=slope, **dz2kw)
 

@@ -33,6 +33,19 @@ __device__ __forceinline__ void split_tf32(const float (&x)[N], uint32_t (&hi)[N
         lo[i] = f2tf32(x[i] - __uint_as_float(hi[i]));
     }
 }
+// 3xTF32 split for the tcgen05 kernels, 2 full-rate instructions per element instead of two
+// quarter-rate cvt.rna: hi = x with the low 13 mantissa bits cleared (exactly a TF32 value),
+// lo = x - hi (exact in fp32); kind::tf32 reads the top 19 bits of lo, so the dropped part is
+// <= 2^-20 |x|, the same order as the neglected lo*lo product.
+template <int N>
+__device__ __forceinline__ void split_tf32_trunc(const float (&x)[N], uint32_t (&hi)[N],
+                                                 uint32_t (&lo)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        hi[i] = __float_as_uint(x[i]) & 0xFFFFE000u;
+        lo[i] = __float_as_uint(x[i] - __uint_as_float(hi[i]));
+    }
+}
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc));
@@ -132,44 +145,80 @@ struct ProG3A2 {
 // Epilogue functors.  rowpass(): v = 4 accumulator columns n..n+3 of row p; returns the value to
 // store in v and the "second statistic" term in q (sum v and sum q are accumulated per column).
 // ------------------------------------------------------------------------------------------
+struct EpiNoParams {};
 struct EpiStore {
     static constexpr bool kStore = true, kStats = false, kMaxMin = false;
-    static __device__ __forceinline__ void rowpass(const PclRowGemm &, float4 &, float4 &, long long, int) {}
+    using Params = EpiNoParams;
+    static __device__ __forceinline__ Params load_params(const PclRowGemm &, int) { return {}; }
+    static __device__ __forceinline__ void rowpass(const PclRowGemm &, const Params &, float4 &, float4 &, long long, int) {}
+    static __device__ __forceinline__ float4 fetch(const PclRowGemm &, long long, int) { return f4zero(); }
+    static __device__ __forceinline__ void apply(const PclRowGemm &, const Params &, float4 &, float4 &, float4) {}
 };
 struct EpiStoreStats {
     static constexpr bool kStore = true, kStats = true, kMaxMin = false;
-    static __device__ __forceinline__ void rowpass(const PclRowGemm &, float4 &v, float4 &q, long long, int) {
+    using Params = EpiNoParams;
+    static __device__ __forceinline__ Params load_params(const PclRowGemm &, int) { return {}; }
+    static __device__ __forceinline__ void rowpass(const PclRowGemm &, const Params &, float4 &v, float4 &q, long long, int) {
+        q = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
+    }
+    static __device__ __forceinline__ float4 fetch(const PclRowGemm &, long long, int) { return f4zero(); }
+    static __device__ __forceinline__ void apply(const PclRowGemm &, const Params &, float4 &v, float4 &q, float4) {
         q = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
     }
 };
 struct EpiMaxMinStats {
     static constexpr bool kStore = false, kStats = true, kMaxMin = true;
-    static __device__ __forceinline__ void rowpass(const PclRowGemm &, float4 &v, float4 &q, long long, int) {
+    using Params = EpiNoParams;
+    static __device__ __forceinline__ Params load_params(const PclRowGemm &, int) { return {}; }
+    static __device__ __forceinline__ void rowpass(const PclRowGemm &, const Params &, float4 &v, float4 &q, long long, int) {
+        q = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
+    }
+    static __device__ __forceinline__ float4 fetch(const PclRowGemm &, long long, int) { return f4zero(); }
+    static __device__ __forceinline__ void apply(const PclRowGemm &, const Params &, float4 &v, float4 &q, float4) {
         q = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
     }
 };
-__device__ __forceinline__ void bwd_act4(const PclRowGemm &a, float4 &v, float4 &q, float4 y, int n) {
-    const float4 b = a.ebias ? ld4(a.ebias + n) : f4zero();
-    const float4 s = ld4(a.escale + n), h = ld4(a.eshift + n), mu = ld4(a.emean + n),
-                 rs = ld4(a.erstd + n);
-    v.x = (v.x + b.x) * (fmaf(s.x, y.x, h.x) > 0.f ? 1.f : a.eslope);
-    v.y = (v.y + b.y) * (fmaf(s.y, y.y, h.y) > 0.f ? 1.f : a.eslope);
-    v.z = (v.z + b.z) * (fmaf(s.z, y.z, h.z) > 0.f ? 1.f : a.eslope);
-    v.w = (v.w + b.w) * (fmaf(s.w, y.w, h.w) > 0.f ? 1.f : a.eslope);
-    q = make_float4(v.x * (y.x - mu.x) * rs.x, v.y * (y.y - mu.y) * rs.y,
-                    v.z * (y.z - mu.z) * rs.z, v.w * (y.w - mu.w) * rs.w);
+// per-column vectors of the backward epilogues, loaded once per (pass, thread): the thread's 4
+// columns are fixed, so nothing per-channel is re-read per row
+struct EpiBwdParams {
+    float4 b, s, h, mu, rs;
+};
+__device__ __forceinline__ EpiBwdParams load_bwd_params(const PclRowGemm &a, int n) {
+    EpiBwdParams e;
+    e.b = a.ebias ? ld4(a.ebias + n) : f4zero();
+    e.s = ld4(a.escale + n);
+    e.h = ld4(a.eshift + n);
+    e.mu = ld4(a.emean + n);
+    e.rs = ld4(a.erstd + n);
+    return e;
+}
+__device__ __forceinline__ void bwd_act4(const PclRowGemm &a, const EpiBwdParams &e, float4 &v, float4 &q, float4 y) {
+    v.x = (v.x + e.b.x) * (fmaf(e.s.x, y.x, e.h.x) > 0.f ? 1.f : a.eslope);
+    v.y = (v.y + e.b.y) * (fmaf(e.s.y, y.y, e.h.y) > 0.f ? 1.f : a.eslope);
+    v.z = (v.z + e.b.z) * (fmaf(e.s.z, y.z, e.h.z) > 0.f ? 1.f : a.eslope);
+    v.w = (v.w + e.b.w) * (fmaf(e.s.w, y.w, e.h.w) > 0.f ? 1.f : a.eslope);
+    q = make_float4(v.x * (y.x - e.mu.x) * e.rs.x, v.y * (y.y - e.mu.y) * e.rs.y,
+                    v.z * (y.z - e.mu.z) * e.rs.z, v.w * (y.w - e.mu.w) * e.rs.w);
 }
 struct EpiBwdY {
     static constexpr bool kStore = true, kStats = true, kMaxMin = false;
-    static __device__ __forceinline__ void rowpass(const PclRowGemm &a, float4 &v, float4 &q, long long p, int n) {
-        bwd_act4(a, v, q, ld4(a.ey + p * a.N + n), n);
+    using Params = EpiBwdParams;
+    static __device__ __forceinline__ Params load_params(const PclRowGemm &a, int n) { return load_bwd_params(a, n); }
+    static __device__ __forceinline__ void rowpass(const PclRowGemm &a, const Params &e, float4 &v, float4 &q, long long p, int n) {
+        bwd_act4(a, e, v, q, ld4(a.ey + p * a.N + n));
     }
+    static __device__ __forceinline__ float4 fetch(const PclRowGemm &a, long long p, int n) { return ld4(a.ey + p * a.N + n); }
+    static __device__ __forceinline__ void apply(const PclRowGemm &a, const Params &e, float4 &v, float4 &q, float4 y) { bwd_act4(a, e, v, q, y); }
 };
 struct EpiBwdGather {
     static constexpr bool kStore = true, kStats = true, kMaxMin = false;
-    static __device__ __forceinline__ void rowpass(const PclRowGemm &a, float4 &v, float4 &q, long long p, int n) {
-        bwd_act4(a, v, q, gather_y4(a, p, n, a.N), n);
+    using Params = EpiBwdParams;
+    static __device__ __forceinline__ Params load_params(const PclRowGemm &a, int n) { return load_bwd_params(a, n); }
+    static __device__ __forceinline__ void rowpass(const PclRowGemm &a, const Params &e, float4 &v, float4 &q, long long p, int n) {
+        bwd_act4(a, e, v, q, gather_y4(a, p, n, a.N));
     }
+    static __device__ __forceinline__ float4 fetch(const PclRowGemm &a, long long p, int n) { return gather_y4(a, p, n, a.N); }
+    static __device__ __forceinline__ void apply(const PclRowGemm &a, const Params &e, float4 &v, float4 &q, float4 y) { bwd_act4(a, e, v, q, y); }
 };
 
 }  // namespace pcl

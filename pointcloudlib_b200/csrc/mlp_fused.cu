@@ -166,12 +166,13 @@ __global__ void __launch_bounds__(kThreads, 2) rowgemm_kernel(const PclRowGemm a
             __syncthreads();
             if (e_active) {
                 float4 s = f4zero(), q2 = f4zero();
+                const typename Epi::Params epar = Epi::load_params(a, n0 + e_q * 4);
                 for (int r = e_r; r < BM; r += RPS) {
                     const long long p = p0 + r;
                     if (p >= a.P) break;
                     float4 v = *reinterpret_cast<const float4 *>(T + r * LDT + e_q * 4);
                     float4 q = f4zero();
-                    Epi::rowpass(a, v, q, p, n0 + e_q * 4);
+                    Epi::rowpass(a, epar, v, q, p, n0 + e_q * 4);
                     if (Epi::kStore)
                         *reinterpret_cast<float4 *>(a.out + p * a.N + n0 + e_q * 4) = v;
                     if (Epi::kStats) {

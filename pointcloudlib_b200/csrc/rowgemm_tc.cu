@@ -106,8 +106,9 @@ __global__ void __launch_bounds__(256, 2) rowgemm_tc_kernel(const PclRowGemm a) 
     __shared__ __align__(16) float s_ps[2][1024];  // per-tile column partial sums [stat][row-slot*BN + col]
     __shared__ __align__(8) uint64_t s_bar[2];  // stage-free, accumulator-full
     __shared__ uint32_t s_tmem;
-    __shared__ float s_pmx[8][BN], s_pmn[8][BN];   // partial max / min of the column scan
-    __shared__ int s_pix[8][BN], s_pin[8][BN];
+    constexpr int PARTS_ = 256 / BN >= 8 ? 8 : 256 / BN;
+    __shared__ float s_pmx[PARTS_][BN], s_pmn[PARTS_][BN];   // partial max / min of the column scan
+    __shared__ int s_pix[PARTS_][BN], s_pin[PARTS_][BN];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (warp == 0) {
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(256, 2) rowgemm_tc_kernel(const PclRowGemm a) 
                 const uint32_t off = sw128_off(a_row + 32 * i, a_c);
                 float x[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w};
                 uint32_t hi[4], lo[4];
-                split_tf32<4>(x, hi, lo);
+                split_tf32_trunc<4>(x, hi, lo);
                 *reinterpret_cast<uint4 *>(sAhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<uint4 *>(sAlo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
@@ -239,19 +240,34 @@ __global__ void __launch_bounds__(256, 2) rowgemm_tc_kernel(const PclRowGemm a) 
                 }
                 tc_fence_before();
                 __syncthreads();
-                if (e_active) {
+                if (!Epi::kMaxMin && e_active) {
                     float4 s = f4zero(), q2 = f4zero();
-                    for (int r = e_r; r < BMt; r += RPS) {
-                        const long long p = p0 + r;
-                        if (p >= a.P) break;
-                        float4 v = *reinterpret_cast<const float4 *>(T + r * LDT + e_q * 4);
-                        float4 q = f4zero();
-                        Epi::rowpass(a, v, q, p, n0 + e_q * 4);
-                        if (Epi::kStore)
-                            *reinterpret_cast<float4 *>(a.out + p * a.N + n0 + e_q * 4) = v;
-                        if (Epi::kStats) {
-                            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-                            q2.x += q.x; q2.y += q.y; q2.z += q.z; q2.w += q.w;
+                    const typename Epi::Params epar = Epi::load_params(a, n0 + e_q * 4);
+                    // 4 rows per batch: the epilogue's global reads (y2 / gathered u rows) of the
+                    // whole batch are in flight before the first one is consumed
+                    for (int r = e_r; r < BMt; r += 4 * RPS) {
+                        float4 y[4];
+                        bool ok[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int rr = r + j * RPS;
+                            ok[j] = rr < BMt && p0 + rr < a.P;
+                            y[j] = ok[j] ? Epi::fetch(a, p0 + rr, n0 + e_q * 4) : f4zero();
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (!ok[j]) continue;
+                            const int rr = r + j * RPS;
+                            const long long p = p0 + rr;
+                            float4 v = *reinterpret_cast<const float4 *>(T + rr * LDT + e_q * 4);
+                            float4 q = f4zero();
+                            Epi::apply(a, epar, v, q, y[j]);
+                            if (Epi::kStore)
+                                *reinterpret_cast<float4 *>(a.out + p * a.N + n0 + e_q * 4) = v;
+                            if (Epi::kStats) {
+                                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                                q2.x += q.x; q2.y += q.y; q2.z += q.z; q2.w += q.w;
+                            }
                         }
                     }
                     if (Epi::kStats) {  // fp32 partials of <= 128/RPS rows -> smem (no atomics)
@@ -260,32 +276,69 @@ __global__ void __launch_bounds__(256, 2) rowgemm_tc_kernel(const PclRowGemm a) 
                     }
                 }
                 if (Epi::kMaxMin) {
-                    // PARTS threads per column, each scanning RPP consecutive rows; groups of ns rows
-                    // (ns | 128) either fit inside a part (written directly) or span several parts
-                    // (partials combined through shared memory).
+                    // Column scan: PARTS threads per column, each owning RPP consecutive rows.  Per
+                    // element: 1 LDS + max + min + sum + sum of squares; the arg-max / arg-min are
+                    // tracked per 8-row block and resolved inside the winning block afterwards (first
+                    // occurrence wins, like a sequential scan).  Groups of ns rows (ns | 128) either lie
+                    // inside a part (written directly) or span parts (partials combined below).
                     const int ns = a.ns;
                     const int rows = (int)min((long long)BMt, a.P - p0);
                     const bool direct = ns <= RPP;
                     const int sub = direct ? ns : RPP;
+                    float csum = 0.f, csq = 0.f;
                     if (s_part < PARTS) {
                         const int rbeg = s_part * RPP;
                         for (int r0 = rbeg; r0 < rbeg + RPP && r0 < rows; r0 += sub) {
-                            float mx = T[r0 * LDT + s_col], mn = mx;
-                            int imx = 0, imn = 0;
-#pragma unroll 4
-                            for (int l = 1; l < sub; ++l) {
-                                const float v = T[(r0 + l) * LDT + s_col];
-                                if (v > mx) { mx = v; imx = l; }
-                                if (v < mn) { mn = v; imn = l; }
+                            const float *Tc = T + r0 * LDT + s_col;
+                            float mx = -3.402823466e38f, mn = 3.402823466e38f;
+                            int bmx = 0, bmn = 0;
+                            if ((sub & 7) == 0) {
+                                for (int b = 0; b < sub; b += 8) {
+                                    float v[8];
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) v[i] = Tc[(b + i) * LDT];
+                                    const float bm = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])),
+                                                           fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+                                    const float bn = fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])),
+                                                           fminf(fminf(v[4], v[5]), fminf(v[6], v[7])));
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        csum += v[i];
+                                        csq = fmaf(v[i], v[i], csq);
+                                    }
+                                    if (bm > mx) { mx = bm; bmx = b; }
+                                    if (bn < mn) { mn = bn; bmn = b; }
+                                }
+                                int imx = bmx + 7, imn = bmn + 7;
+#pragma unroll
+                                for (int i = 6; i >= 0; --i) {
+                                    if (Tc[(bmx + i) * LDT] == mx) imx = bmx + i;
+                                    if (Tc[(bmn + i) * LDT] == mn) imn = bmn + i;
+                                }
+                                bmx = imx;
+                                bmn = imn;
+                            } else {
+                                mx = mn = Tc[0];
+                                csum += mx;
+                                csq = fmaf(mx, mx, csq);
+                                for (int l = 1; l < sub; ++l) {
+                                    const float v = Tc[l * LDT];
+                                    csum += v;
+                                    csq = fmaf(v, v, csq);
+                                    if (v > mx) { mx = v; bmx = l; }
+                                    if (v < mn) { mn = v; bmn = l; }
+                                }
                             }
                             if (direct) {
                                 const long long o = ((p0 + r0) / ns) * a.N + n0 + s_col;
-                                a.gmax[o] = mx; a.gmin[o] = mn; a.amax[o] = imx; a.amin[o] = imn;
+                                a.gmax[o] = mx; a.gmin[o] = mn; a.amax[o] = bmx; a.amin[o] = bmn;
                             } else {
                                 s_pmx[s_part][s_col] = mx; s_pmn[s_part][s_col] = mn;
-                                s_pix[s_part][s_col] = imx; s_pin[s_part][s_col] = imn;
+                                s_pix[s_part][s_col] = bmx; s_pin[s_part][s_col] = bmn;
                             }
                         }
+                        s_ps[0][s_part * BN + s_col] = csum;
+                        s_ps[1][s_part * BN + s_col] = csq;
                     }
                     if (!direct) {
                         __syncthreads();
@@ -308,9 +361,10 @@ __global__ void __launch_bounds__(256, 2) rowgemm_tc_kernel(const PclRowGemm a) 
                 __syncthreads();  // T consumed before the next chunk overwrites the stage
                 if (Epi::kStats && tid < 2 * BN) {
                     const float *ps = &s_ps[tid / BN][tid % BN];
+                    constexpr int NSLOT = Epi::kMaxMin ? PARTS : RPS;
                     float t = 0.f;
 #pragma unroll
-                    for (int r = 0; r < RPS; ++r) t += ps[r * BN];
+                    for (int r = 0; r < NSLOT; ++r) t += ps[r * BN];
                     acc_d += (double)t;
                 }
             }

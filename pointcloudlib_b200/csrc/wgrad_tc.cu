@@ -118,7 +118,7 @@ wgrad_tc_kernel(const PclRowGemm al, const PclRowGemm ar, long long P, int M, in
     auto store_split = [&](uint8_t *hi_t, uint8_t *lo_t, uint32_t off, const float4 &v) {
         float x[4] = {v.x, v.y, v.z, v.w};
         uint32_t hi[4], lo[4];
-        split_tf32<4>(x, hi, lo);
+        split_tf32_trunc<4>(x, hi, lo);
         *reinterpret_cast<uint4 *>(hi_t + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4 *>(lo_t + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     };

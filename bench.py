@@ -174,6 +174,13 @@ def bq_group_bytes(key):
     return 4 * (B * N * (3 + C) + 3 * B * S + B * S * ns + B * S * ns * W)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, from profiles/rowgemm_tc_r01_ncu_full.txt
+# (ncu --set full capture of the same kernel and shape).
+NCU_TRAFFIC = {
+    ("pcl_rowgemm", ("sa_b3", "4", "3", "2097152", "224", "96")): 822381000 + 766228992,
+}
+
+
 def algorithmic_cost(name, key):
     """(ALGORITHMIC bytes, flops) of one launch of an own kernel.  Bytes count
     each HBM-resident operand once (tensors of a few MB that stay in L2 — weights, U/V, per-channel
@@ -319,15 +326,47 @@ def run_product_arm(args):
             k["TFLOPs"] = fl / (mean_ms * 1e-3) / 1e12
         kernels.append(k)
     top = next((k for k in kernels if "GBps" in k), kernels[0])
+    traffic = NCU_TRAFFIC.get((top["call"], tuple(top["key"] or ())))
     roofline = {"kernel": f"{top['call']} {top['key']}", "bound": "hbm",
                 "achieved": top.get("GBps"), "peak": peak, "unit": "GB/s", "frac": top.get("hbm_frac"),
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(top.get("algorithmic_MB", 0) * 1e6),
                 "mean_launch_us": top["mean_us"], "share_of_step": top["share_of_step"],
                 "own_kernels_share_of_step": sum(k["share_of_step"] for k in kernels),
                 "note": "dominant own kernel by total time inside the timed region; CUDA events on the "
-                        "launch stream; 3xTF32 mma.sync row-GEMM with fused prologue/epilogue",
+                        "launch stream; tcgen05 3xTF32 row-GEMM with fused prologue/epilogue; traffic = "
+                        "dram read+write of the same kernel/shape from the committed ncu --set full "
+                        "capture (profiles/), when one exists for that key",
                 "kernels": kernels[:24]}
+
+    # ---- second half of the metric: ball-query+group (unfused BallQueryGrouper kernel) GB/s -----
+    # The training step above never materialises the grouped tensor; the reference-facing
+    # BallQueryGrouper module does, through pcl_ball_query_group.  Timed here on the config's own
+    # shapes (SA1: N=4096,S=512,C=3; SA2: N=512,S=128,C=320), CUDA events, 10 launches each,
+    # output tensors (6-700 MB) far larger than L2 for the big cases.
+    from pointcloudlib_b200 import functional as PF
+    bq = []
+    xyz0, nrm0, _ = resident[0]
+    cen1 = PF.gather_xyz(xyz0, PF.furthest_point_sample(xyz0, 512))
+    cen2 = PF.gather_xyz(cen1, PF.furthest_point_sample(cen1, 128))
+    feat2 = torch.randn(B_PER_GPU, 512, 320, device=dev)
+    for (cen, pts, feat, r, ns) in [(cen1, xyz0, nrm0, 0.1, 16), (cen1, xyz0, nrm0, 0.2, 32),
+                                    (cen1, xyz0, nrm0, 0.4, 128), (cen2, cen1, feat2, 0.2, 32),
+                                    (cen2, cen1, feat2, 0.4, 64), (cen2, cen1, feat2, 0.8, 128)]:
+        for _ in range(3):
+            PF.ball_query_group(cen, pts, feat, r, ns)
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(10):
+            PF.ball_query_group(cen, pts, feat, r, ns)
+        b1.record()
+        torch.cuda.synchronize()
+        us = 1e3 * b0.elapsed_time(b1) / 10
+        key = (B_PER_GPU, pts.shape[1], cen.shape[1], ns, feat.shape[2], 1)
+        by = bq_group_bytes(key)
+        bq.append({"B,N,S,ns,C,use_xyz": list(key), "radius": r, "mean_us": us,
+                   "algorithmic_MB": by / 1e6, "GBps": by / us / 1e3, "hbm_frac": by / us / 1e3 / peak})
+    roofline["ballquery_group"] = bq
 
     # ---- CPU baseline (bounded sample, rank 0, N=1 only) ----------------------------------------
     cpu_baseline = None

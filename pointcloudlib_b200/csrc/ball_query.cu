@@ -19,6 +19,7 @@ namespace pcl {
 
 constexpr int kBQWarps = 8;
 constexpr int kBQThreads = kBQWarps * 32;
+constexpr int kGU = 16;  // gather-writer unroll (elements per lane per iteration)
 
 struct BQArgs {
     const float *new_xyz;  // (B,S,3)
@@ -46,23 +47,33 @@ __device__ __forceinline__ void group_rows(const BQArgs &a, int b, int s, const 
     const float *pb = a.xyz + (long long)b * a.N * 3;
     int l = lane / W, c = lane % W;
     const int dl = 32 / W, dc = 32 % W;
-    for (long long e = lane; e < total; e += 32) {
-        const int k = sidx[l];
-        float v;
-        if (c < off) {
-            const float p = SMEM_XYZ ? s_xyz[c * a.N + k] : __ldg(pb + 3 * k + c);
-            const float ctr = c == 0 ? cx : (c == 1 ? cy : cz);
-            v = __fsub_rn(p, ctr);  // ops.py:401 local_xyz = grouped_xyz - new_xyz
-        } else {
-            v = __ldg(fb + (long long)k * a.C + (c - off));
+    // kGU elements per lane per iteration: all gathers are in flight before the first store
+    // (Little's law: ~6.5 MB must be in flight chip-wide to saturate HBM3e)
+    for (long long e = lane; e < total; e += 32 * kGU) {
+        float v[kGU];
+#pragma unroll
+        for (int j = 0; j < kGU; ++j) {
+            v[j] = 0.f;
+            if (e + 32 * j < total) {
+                const int k = sidx[l];
+                if (c < off) {
+                    const float p = SMEM_XYZ ? s_xyz[c * a.N + k] : __ldg(pb + 3 * k + c);
+                    const float ctr = c == 0 ? cx : (c == 1 ? cy : cz);
+                    v[j] = __fsub_rn(p, ctr);  // ops.py:401 local_xyz = grouped_xyz - new_xyz
+                } else {
+                    v[j] = __ldg(fb + (long long)k * a.C + (c - off));
+                }
+            }
+            l += dl;
+            c += dc;
+            if (c >= W) {
+                c -= W;
+                ++l;
+            }
         }
-        o[e] = v;
-        l += dl;
-        c += dc;
-        if (c >= W) {
-            c -= W;
-            ++l;
-        }
+#pragma unroll
+        for (int j = 0; j < kGU; ++j)
+            if (e + 32 * j < total) o[e + 32 * j] = v[j];
     }
 }
 
@@ -94,29 +105,39 @@ __global__ void __launch_bounds__(kBQThreads) ball_query_group_kernel(BQArgs a) 
                     cz = __ldg(a.new_xyz + bs * 3 + 2);
         if (QUERY) {
             int cnt = 0, first = 0;
-            for (int base = 0; base < a.N; base += 32) {
-                const int k = base + lane;
-                bool hit = false;
-                if (k < a.N) {
-                    float x, y, z;
-                    if (SMEM_XYZ) {
-                        x = s_xyz[k];
-                        y = s_xyz[a.N + k];
-                        z = s_xyz[2 * a.N + k];
-                    } else {
-                        x = __ldg(pb + 3 * k);
-                        y = __ldg(pb + 3 * k + 1);
-                        z = __ldg(pb + 3 * k + 2);
+            // 128 points per iteration (4 independent distance evaluations per lane) to hide the
+            // shared-memory latency; hits are still consumed in index order, 32 at a time
+            for (int base = 0; base < a.N && cnt < a.ns; base += 128) {
+                unsigned m[4];
+                bool hit[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = base + 32 * j + lane;
+                    hit[j] = false;
+                    if (k < a.N) {
+                        float x, y, z;
+                        if (SMEM_XYZ) {
+                            x = s_xyz[k];
+                            y = s_xyz[a.N + k];
+                            z = s_xyz[2 * a.N + k];
+                        } else {
+                            x = __ldg(pb + 3 * k);
+                            y = __ldg(pb + 3 * k + 1);
+                            z = __ldg(pb + 3 * k + 2);
+                        }
+                        hit[j] = sqdist3(cx, cy, cz, x, y, z) < a.r2;  // ops.py:317-320, strict <
                     }
-                    hit = sqdist3(cx, cy, cz, x, y, z) < a.r2;  // ops.py:317-320, strict <
                 }
-                const unsigned m = __ballot_sync(0xffffffffu, hit);
-                if (m) {
-                    if (cnt == 0) first = base + __ffs(m) - 1;
-                    const int pos = cnt + __popc(m & ((1u << lane) - 1u));
-                    if (hit && pos < a.ns) sidx[pos] = k;
-                    cnt += __popc(m);
-                    if (cnt >= a.ns) break;  // ops.py:313 loop condition cnt < nsample
+#pragma unroll
+                for (int j = 0; j < 4; ++j) m[j] = __ballot_sync(0xffffffffu, hit[j]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (m[j] && cnt < a.ns) {  // ops.py:313 loop condition cnt < nsample
+                        if (cnt == 0) first = base + 32 * j + __ffs(m[j]) - 1;
+                        const int pos = cnt + __popc(m[j] & ((1u << lane) - 1u));
+                        if (hit[j] && pos < a.ns) sidx[pos] = base + 32 * j + lane;
+                        cnt += __popc(m[j]);
+                    }
                 }
             }
             cnt = min(cnt, a.ns);

@@ -86,16 +86,20 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int c) {
     return ((uint32_t)(r >> 3) << 10) + ((uint32_t)(r & 7) << 7) + ((uint32_t)((c ^ r) & 7) << 4);
 }
 
-// dynamic smem: 1024 (alignment slack) + max(one stage, epilogue tile).  One stage = A_hi, A_lo
-// (128 x 128 B each) + W_hi, W_lo (BN x 128 B each).  TWO CTAs per SM: while one CTA's MMAs run, the
-// other stages its next chunk / runs its epilogue (each CTA owns BN<=128 of the 512 TMEM columns).
+// A "macro tile" is RT = 2 row tiles of 128 rows that share ONE staged weight chunk (the 3xTF32
+// weights are 40-65 % of the L2->SM traffic when re-streamed per 128 rows) and own one TMEM
+// accumulator each (columns [rt*BN, rt*BN+BN)).
+// dynamic smem: 1024 (alignment slack) + one stage = RT x (A_hi, A_lo: 128 x 128 B each) + W_hi, W_lo
+// (BN x 128 B each); the epilogue tile aliases it.  TWO CTAs per SM: while one CTA's MMAs run, the
+// other stages its next chunk / runs its epilogue (each CTA owns 2*BN <= 256 of the 512 TMEM columns).
 template <int BN, class Pro, class Epi>
 __global__ void __launch_bounds__(256, 2) rowgemm_tc_kernel(const PclRowGemm a) {
     constexpr int BMt = 128;
+    constexpr int RT = 2;
     constexpr int A_TILE = BMt * 128, W_TILE = BN * 128;  // bytes
     constexpr int LDT = BN + 4;
-    constexpr int NW = BN / 16;  // W float4 per thread per chunk (hi and lo together)
-    constexpr uint32_t TCOLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : 128);
+    constexpr int NW = BN / 16;  // W 16-byte chunks per thread per K chunk (hi and lo together)
+    constexpr uint32_t TCOLS = RT * BN <= 32 ? 32 : (RT * BN <= 64 ? 64 : (RT * BN <= 128 ? 128 : 256));
     // instruction descriptor: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), K-major both, N>>3, M>>4
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                ((uint32_t)(BMt >> 4) << 24);
@@ -130,12 +134,13 @@ __global__ void __launch_bounds__(256, 2) rowgemm_tc_kernel(const PclRowGemm a) 
     const uint32_t bar_free = smem_u32(&s_bar[0]);
     const uint32_t bar_full = smem_u32(&s_bar[1]);
 
-    const long long n_tiles = (a.P + BMt - 1) / BMt;
+    const long long n_tiles = (a.P + RT * BMt - 1) / (RT * BMt);  // macro tiles
     const int n_pass = a.N / BN;
     const int nk = a.ldw / 32;
     const float *Whi = a.W + (long long)a.N * a.ldw;  // W = [raw | hi | lo]; lo = hi + N*ldw
 
-    uint8_t *sAhi = smem, *sAlo = sAhi + A_TILE, *sWhi = sAlo + A_TILE, *sWlo = sWhi + W_TILE;
+    // stage layout: [A0_hi | A0_lo | A1_hi | A1_lo | W_hi | W_lo]
+    uint8_t *sA = smem, *sWhi = smem + RT * 2 * A_TILE, *sWlo = sWhi + W_TILE;
     const int a_row = tid >> 3, a_c = tid & 7;
     constexpr int QN = BN / 4;
     constexpr int RPS = 256 / QN;
@@ -147,6 +152,7 @@ __global__ void __launch_bounds__(256, 2) rowgemm_tc_kernel(const PclRowGemm a) 
     const int s_col = tid % BN, s_part = tid / BN;
 
     uint32_t uses = 0, tiles_done = 0;
+    const int dbg = a.c0 >> 16;  // profiling knobs (scratch/knobs.py): 1 no MMA, 2 no epilogue body, 4 no A loads, 8 no W
 
     for (int pass = 0; pass < n_pass; ++pass) {
         const int n0 = pass * BN;
@@ -157,53 +163,58 @@ __global__ void __launch_bounds__(256, 2) rowgemm_tc_kernel(const PclRowGemm a) 
         long long tile = blockIdx.x;
         int kc = 0;
         bool have = tile < n_tiles;
-        float4 ra[4], rw[NW];
+        float4 ra[4 * RT];
         auto prefetch = [&](long long tl, int kcc) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const long long p = tl * BMt + a_row + 32 * i;
-                ra[i] = p < a.P ? Pro::load(a, p, kcc * 32 + a_c * 4) : f4zero();
-            }
-#pragma unroll
-            for (int i = 0; i < NW; ++i) {
-                // element e of [hi: BN x 8 chunks | lo: BN x 8 chunks]
-                const int e = tid + 256 * i, half = e / (BN * 8), r = e % (BN * 8);
-                const int n = r >> 3, c = r & 7;
-                rw[i] = ld4(Whi + (long long)half * a.N * a.ldw + (long long)(n0 + n) * a.ldw + kcc * 32 + c * 4);
+            for (int i = 0; i < 4 * RT; ++i) {
+                const long long p = tl * (RT * BMt) + a_row + 32 * i;
+                ra[i] = (p < a.P && !(dbg & 4)) ? Pro::load(a, p, kcc * 32 + a_c * 4) : f4zero();
             }
         };
         if (have) prefetch(tile, 0);
 
         while (have) {
-            if (uses > 0) mbar_wait(bar_free, (uses - 1) & 1);  // previous chunk's MMAs have read the stage
+            if (uses > 0 && !(dbg & 1)) mbar_wait(bar_free, (uses - 1) & 1);  // previous chunk's MMAs have read the stage
             ++uses;
+            // weights: cp.async straight into the swizzled stage (L2 hits; the latency hides behind
+            // the A split/stores below) — no registers, one chunk serves both row tiles
 #pragma unroll
             for (int i = 0; i < NW; ++i) {
+                // element e of [hi: BN x 8 chunks | lo: BN x 8 chunks]
                 const int e = tid + 256 * i, half = e / (BN * 8), r = e % (BN * 8);
-                *reinterpret_cast<float4 *>((half ? sWlo : sWhi) + sw128_off(r >> 3, r & 7)) = rw[i];
+                const int n = r >> 3, c = r & 7;
+                if (!(dbg & 8)) cp_async16((half ? sWlo : sWhi) + sw128_off(n, c),
+                           Whi + (long long)half * a.N * a.ldw + (long long)(n0 + n) * a.ldw + kc * 32 + c * 4);
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t off = sw128_off(a_row + 32 * i, a_c);
+            for (int i = 0; i < 4 * RT; ++i) {
+                uint8_t *hi_t = sA + (i / 4) * 2 * A_TILE, *lo_t = hi_t + A_TILE;
+                const uint32_t off = sw128_off(a_row + 32 * (i % 4), a_c);
                 float x[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w};
                 uint32_t hi[4], lo[4];
                 split_tf32_trunc<4>(x, hi, lo);
-                *reinterpret_cast<uint4 *>(sAhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4 *>(sAlo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<uint4 *>(hi_t + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4 *>(lo_t + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
+            cp_async_wait_all();
             fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
             tc_fence_before();
             __syncthreads();
-            if (tid == 0) {
+            if (tid == 0 && !(dbg & 1)) {
                 tc_fence_after();
-                const uint64_t dAhi = umma_desc_sw128(smem_u32(sAhi)), dAlo = umma_desc_sw128(smem_u32(sAlo));
                 const uint64_t dWhi = umma_desc_sw128(smem_u32(sWhi)), dWlo = umma_desc_sw128(smem_u32(sWlo));
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t adv = (uint64_t)(ks * 2);  // 32 bytes per K=8 step, in 16-byte units
-                    tc_mma_tf32(tmem, dAlo + adv, dWhi + adv, IDESC, (kc > 0 || ks > 0) ? 1u : 0u);
-                    tc_mma_tf32(tmem, dAhi + adv, dWlo + adv, IDESC, 1u);
-                    tc_mma_tf32(tmem, dAhi + adv, dWhi + adv, IDESC, 1u);
+                for (int rt = 0; rt < RT; ++rt) {
+                    const uint64_t dAhi = umma_desc_sw128(smem_u32(sA + rt * 2 * A_TILE));
+                    const uint64_t dAlo = umma_desc_sw128(smem_u32(sA + rt * 2 * A_TILE + A_TILE));
+                    const uint32_t d = tmem + (uint32_t)(rt * BN);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t adv = (uint64_t)(ks * 2);  // 32 bytes per K=8 step, in 16-byte units
+                        tc_mma_tf32(d, dAlo + adv, dWhi + adv, IDESC, (kc > 0 || ks > 0) ? 1u : 0u);
+                        tc_mma_tf32(d, dAhi + adv, dWlo + adv, IDESC, 1u);
+                        tc_mma_tf32(d, dAhi + adv, dWhi + adv, IDESC, 1u);
+                    }
                 }
                 tc_commit(bar_free);
                 if (kc == nk - 1) tc_commit(bar_full);
@@ -218,12 +229,14 @@ __global__ void __launch_bounds__(256, 2) rowgemm_tc_kernel(const PclRowGemm a) 
             if (have_n) prefetch(tile_n, kc_n);  // global loads in flight during the MMAs (+ epilogue)
 
             if (kc == nk - 1) {
-                // ---------------- epilogue of this tile ----------------
-                const long long p0 = tile * BMt;
-                mbar_wait(bar_full, tiles_done & 1);
+                // ---------------- epilogue of this macro tile (one row tile at a time) ----------------
+                if (!(dbg & 1)) mbar_wait(bar_full, tiles_done & 1);
                 ++tiles_done;
                 tc_fence_after();
                 float *T = reinterpret_cast<float *>(smem);  // aliases the stage (all MMAs done)
+              for (int rt = 0; rt < RT; ++rt) {
+                const long long p0 = tile * (RT * BMt) + (long long)rt * BMt;
+                if (p0 >= a.P || (dbg & 2)) break;  // ragged tail: the second row tile may be empty (uniform)
                 {
                     const int q = warp & 3, h = warp >> 2;
                     const int row = q * 32 + lane;
@@ -231,7 +244,7 @@ __global__ void __launch_bounds__(256, 2) rowgemm_tc_kernel(const PclRowGemm a) 
                     for (int cc = 0; cc < BN / 32; ++cc) {
                         const int c0 = h * (BN / 2) + cc * 16;
                         float v[16];
-                        tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                        tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(rt * BN + c0), v);
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             *reinterpret_cast<float4 *>(T + row * LDT + c0 + 4 * j) =
@@ -358,7 +371,7 @@ __global__ void __launch_bounds__(256, 2) rowgemm_tc_kernel(const PclRowGemm a) 
                         }
                     }
                 }
-                __syncthreads();  // T consumed before the next chunk overwrites the stage
+                __syncthreads();  // T consumed before the next row tile / chunk overwrites it
                 if (Epi::kStats && tid < 2 * BN) {
                     const float *ps = &s_ps[tid / BN][tid % BN];
                     constexpr int NSLOT = Epi::kMaxMin ? PARTS : RPS;
@@ -367,6 +380,8 @@ __global__ void __launch_bounds__(256, 2) rowgemm_tc_kernel(const PclRowGemm a) 
                     for (int r = 0; r < NSLOT; ++r) t += ps[r * BN];
                     acc_d += (double)t;
                 }
+                if (rt + 1 < RT) __syncthreads();  // s_ps / partial-scan buffers reused by the next row tile
+              }
             }
             tile = tile_n;
             kc = kc_n;
@@ -387,7 +402,7 @@ __global__ void __launch_bounds__(256, 2) rowgemm_tc_kernel(const PclRowGemm a) 
 
 template <int BN, class Pro, class Epi>
 static int launch_tc(const PclRowGemm &a, cudaStream_t st) {
-    const size_t stage = (size_t)2 * 128 * 128 + (size_t)2 * BN * 128;
+    const size_t stage = (size_t)2 * 2 * 128 * 128 + (size_t)2 * BN * 128;  // RT = 2 row tiles
     const size_t tile = (size_t)128 * (BN + 4) * sizeof(float);
     const size_t smem = 1024 + (stage > tile ? stage : tile);
     auto kern = rowgemm_tc_kernel<BN, Pro, Epi>;
@@ -396,7 +411,7 @@ static int launch_tc(const PclRowGemm &a, cudaStream_t st) {
         set_error("pcl_rowgemm(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         return (int)e;
     }
-    const long long n_tiles = (a.P + 127) / 128;
+    const long long n_tiles = (a.P + 255) / 256;  // macro tiles of 2 x 128 rows
     long long grid = 2LL * kNumSMs;  // two persistent CTAs per SM
     if (grid > n_tiles) grid = n_tiles;
     kern<<<(unsigned)grid, 256, smem, st>>>(a);

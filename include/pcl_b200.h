@@ -207,6 +207,24 @@ int pcl_gather_bn_backward(const float *dyh, const float *U, const float *V, con
                            const float *m1, const float *m2, long long P, int ns, int C,
                            float vsign, float *dU, float *dV, void *stream);
 
+/* ---- a7 / a8: fused EdgeConv (networks/cls/dgcnn.py:29-50 + :72-83,100-111) -------------------
+ * W.[x_j - x_i ; x_i] = W1.x_j + (W2-W1).x_i  =>  y[i,j] = u[src[i,j]] + vsign*v[i] on per-point
+ * projections u, v (pcl_rowgemm PCL_PRO_PLAIN2); statistics by pcl_gather_stats; then:
+ * pcl_gather_maxmin: per group of ns rows and channel, max / min of y and their offsets
+ * (gmax,gmin,amax,amin (G,C)) — feeds pcl_maxpool_finalize; C % 4 == 0, C <= 256. */
+int pcl_gather_maxmin(const float *U, const float *V, const int32_t *src, long long G, int ns,
+                      int C, float vsign, float *gmax, float *gmin, int32_t *amax, int32_t *amin,
+                      void *stream);
+/* BatchNorm backward of y from the ROUTED output gradient (g3s (G,C) = BN scale * masked grad,
+ * selpos (G,C) from pcl_maxpool_finalize / pcl_maxpool_backward):
+ * dz = [selpos == l] g3s - bscale*(m1 + xhat*m2); dU[src] += dz (atomics, zeroed by the caller);
+ * dV[g] = vsign * sum_l dz. */
+int pcl_gather_bn_backward_routed(const float *g3s, const int32_t *selpos, const float *U,
+                                  const float *V, const int32_t *src, const float *mean,
+                                  const float *rstd, const float *bscale, const float *m1,
+                                  const float *m2, long long G, int ns, int C, float vsign,
+                                  float *dU, float *dV, void *stream);
+
 /* ---- DP / optimizer plumbing on the flat parameter bucket (train_cls.py:72 optimizer.step) --
  * SGD with momentum + weight decay over a flat fp32 bucket: g += wd*p; m = mu*m + g; p -= lr*m;
  * grad_scale multiplies g first (1/world_size after the NCCL all-reduce). */

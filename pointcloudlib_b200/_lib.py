@@ -50,7 +50,7 @@ _SIGNATURES = {
 # entry points bound in pointcloudlib_b200/fused.py (struct-taking signatures)
 FUSED_SYMBOLS = ("pcl_rowgemm", "pcl_wgrad", "pcl_gather_stats", "pcl_bn_param",
                  "pcl_maxpool_finalize", "pcl_maxpool_backward", "pcl_sel_outer",
-                 "pcl_gather_bn_backward")
+                 "pcl_gather_bn_backward", "pcl_gather_maxmin", "pcl_gather_bn_backward_routed")
 
 
 def declared_symbols(header: str = HEADER_PATH):

@@ -63,6 +63,8 @@ def _bind():
         "pcl_maxpool_backward": [P, P, P, P, P, P, Fl, L, I, P, P, P],
         "pcl_sel_outer": [P, P, P, P, P, Fl, L, I, I, I, P, P],
         "pcl_gather_bn_backward": [P, P, P, P, P, P, P, P, P, L, I, I, Fl, P, P, P],
+        "pcl_gather_maxmin": [P, P, P, L, I, I, Fl, P, P, P, P, P],
+        "pcl_gather_bn_backward_routed": [P, P, P, P, P, P, P, P, P, P, L, I, I, Fl, P, P, P],
     }
     for name, argtypes in sigs.items():
         fn = getattr(l, name)
@@ -73,7 +75,7 @@ def _bind():
 
 SIGNATURE_NAMES = ("pcl_rowgemm", "pcl_wgrad", "pcl_gather_stats", "pcl_bn_param",
                    "pcl_maxpool_finalize", "pcl_maxpool_backward", "pcl_sel_outer",
-                   "pcl_gather_bn_backward")
+                   "pcl_gather_bn_backward", "pcl_gather_maxmin", "pcl_gather_bn_backward_routed")
 
 
 def _args(**kw):
@@ -300,3 +302,97 @@ def fused_sa_branch(xyz, new_xyz, feat, idx, seq, slope: float = 0.0):
     return FusedSAFn.apply(xyz, new_xyz, feat, idx, convs[0].weight, convs[1].weight, convs[2].weight,
                            bns[0].weight, bns[0].bias, bns[1].weight, bns[1].bias, bns[2].weight,
                            bns[2].bias, bns, float(slope))
+
+
+class FusedEdgeConvFn(torch.autograd.Function):
+    """DGCNN EdgeConv block, networks/cls/dgcnn.py:29-50 + :72-83,100-111:
+    out (B,C',N) = max_j act(bn(W . [x_j - x_i ; x_i])),  j over the k neighbours idx (B,k,N).
+
+    W.[x_j - x_i ; x_i] = W1.x_j + (W2-W1).x_i: the conv runs on the N points (k times fewer
+    FLOPs), the (B,2C,N,k) graph-feature tensor and the (B,C',N,k) conv output never exist."""
+
+    @staticmethod
+    def forward(ctx, x, idx_kmajor, W, gamma, beta, bn, slope):
+        _bind()
+        dev = x.device
+        B, C, N = x.shape
+        k = idx_kmajor.shape[1]
+        Co = W.shape[0]
+        G, P = B * N, B * N * k
+        Wm = W.reshape(Co, 2 * C)
+        W1, Wd = Wm[:, :C], Wm[:, C:] - Wm[:, :C]
+        Xr = x.transpose(1, 2).reshape(G, C).contiguous()
+        src = (idx_kmajor.permute(0, 2, 1)
+               + (torch.arange(B, device=dev, dtype=torch.int32) * N).view(B, 1, 1)).reshape(-1).contiguous()
+        f32 = dict(dtype=torch.float32, device=dev)
+        U, V = torch.empty((G, Co), **f32), torch.empty((G, Co), **f32)
+        W1p, Wdp = pack_weight(W1), pack_weight(Wd)
+        rowgemm(PRO_PLAIN2, EPI_STORE, "ec_proj_u", W=W1p, x0=Xr, c0=C, c1=0, P=G, K=C, N=Co,
+                ldw=W1p.shape[-1], out=U)
+        rowgemm(PRO_PLAIN2, EPI_STORE, "ec_proj_v", W=Wdp, x0=Xr, c0=C, c1=0, P=G, K=C, N=Co,
+                ldw=Wdp.shape[-1], out=V)
+        stats = torch.zeros((2, Co), dtype=torch.float64, device=dev)
+        _lib.call("pcl_gather_stats", ptr(U), ptr(V), ptr(src), P, k, Co, 1.0, ptr(stats), stream(),
+                  key=("ec_gather_stats", P, Co))
+        sc, sh, mu, rs = bn_param(stats, P, bn, Co)
+        gmax, gmin = torch.empty((G, Co), **f32), torch.empty((G, Co), **f32)
+        amax = torch.empty((G, Co), dtype=torch.int32, device=dev)
+        amin = torch.empty((G, Co), dtype=torch.int32, device=dev)
+        _lib.call("pcl_gather_maxmin", ptr(U), ptr(V), ptr(src), G, k, Co, 1.0, ptr(gmax), ptr(gmin),
+                  ptr(amax), ptr(amin), stream(), key=("ec_gather_maxmin", P, Co))
+        out = torch.empty((G, Co), **f32)
+        ysel = torch.empty((G, Co), **f32)
+        selpos = torch.empty((G, Co), dtype=torch.int32, device=dev)
+        _lib.call("pcl_maxpool_finalize", ptr(gmax), ptr(gmin), ptr(amax), ptr(amin), ptr(sc), ptr(sh),
+                  float(slope), G, Co, ptr(out), ptr(ysel), ptr(selpos), stream())
+        ctx.save_for_backward(Xr, src, U, V, W1, Wd, sc, mu, rs, out, ysel, selpos)
+        ctx.dims = (B, C, N, k, Co, slope)
+        ctx.w_shape = W.shape
+        return out.view(B, N, Co).transpose(1, 2)
+
+    @staticmethod
+    def backward(ctx, dout):
+        Xr, src, U, V, W1, Wd, sc, mu, rs, out, ysel, selpos = ctx.saved_tensors
+        B, C, N, k, Co, slope = ctx.dims
+        dev = dout.device
+        G, P = B * N, B * N * k
+        f32 = dict(dtype=torch.float32, device=dev)
+        dout = dout.transpose(1, 2).reshape(G, Co).contiguous().float()
+        g3s = torch.empty((G, Co), **f32)
+        sums = torch.zeros((2, Co), dtype=torch.float64, device=dev)
+        _lib.call("pcl_maxpool_backward", ptr(dout), ptr(out), ptr(ysel), ptr(sc), ptr(mu), ptr(rs),
+                  float(slope), G, Co, ptr(g3s), ptr(sums), stream())
+        m1 = (sums[0] / P).float().contiguous()
+        m2 = (sums[1] / P).float().contiguous()
+        dU = torch.zeros((G, Co), **f32)
+        dV = torch.empty((G, Co), **f32)
+        _lib.call("pcl_gather_bn_backward_routed", ptr(g3s), ptr(selpos), ptr(U), ptr(V), ptr(src),
+                  ptr(mu), ptr(rs), ptr(sc), ptr(m1), ptr(m2), G, k, Co, 1.0, ptr(dU), ptr(dV), stream(),
+                  key=("ec_bwd_scatter", P, Co))
+        # plain dense GEMMs over the B*N points
+        dW1 = dU.t() @ Xr
+        dWd = dV.t() @ Xr
+        dW = torch.cat([dW1 - dWd, dWd], dim=1).view(ctx.w_shape)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = (dU @ W1 + dV @ Wd).view(B, N, C).transpose(1, 2)
+        return dx, None, dW, sums[1].float(), sums[0].float(), None, None
+
+
+def edgeconv_supported(conv_seq) -> bool:
+    mods = list(conv_seq)
+    if len(mods) != 3:
+        return False
+    conv, bn, act = mods
+    return (isinstance(conv, torch.nn.Conv2d) and conv.bias is None and conv.kernel_size == (1, 1)
+            and isinstance(bn, torch.nn.BatchNorm2d) and bn.training
+            and isinstance(act, torch.nn.LeakyReLU)
+            and conv.weight.shape[0] % 32 == 0 and conv.weight.shape[0] <= 256
+            and (conv.weight.shape[0] <= 128 or conv.weight.shape[0] % 64 == 0))
+
+
+def fused_edgeconv(x, idx_kmajor, conv_seq):
+    """x (B,C,N), idx (B,k,N) from KNN, conv_seq = Sequential(Conv2d(2C,C',1,bias=False), BN, LeakyReLU)."""
+    conv, bn, act = list(conv_seq)
+    return FusedEdgeConvFn.apply(x, idx_kmajor, conv.weight, bn.weight, bn.bias, bn,
+                                 float(act.negative_slope))

@@ -26,6 +26,20 @@ def get_graph_feature(x, knn=None, k=None, idx=None):
     return F.graph_feature(x, idx_kmajor)
 
 
+def edge_conv(x, knn, k, conv_seq):
+    """get_graph_feature -> conv block -> max over k (dgcnn.py:100-102 and the three repeats).
+    Takes the fused EdgeConv path (pointcloudlib_b200.fused.FusedEdgeConvFn) when the block has
+    the cls model's shape (one 1x1 conv, BatchNorm in training mode, LeakyReLU); otherwise the
+    reference's own sequence."""
+    from ... import fused
+    from ...sa import FUSED
+    if FUSED and x.is_cuda and fused.edgeconv_supported(conv_seq):
+        B, _, N = x.shape
+        xr = x.reshape(B, -1, N)
+        return fused.fused_edgeconv(xr, knn(xr, xr), conv_seq)
+    return conv_seq(get_graph_feature(x, knn=knn, k=k)).max(dim=-1, keepdim=False).values
+
+
 def knn(x, k):
     """networks/cls/dgcnn.py:52-57 (unused by the model)."""
     from ...misc.ops import knn as _knn
@@ -64,18 +78,11 @@ class DGCNN(Module):
 
     def execute(self, x):
         batch_size = x.shape[0]
-        x = get_graph_feature(x, knn=self.knn, k=self.k)
-        x = self.conv1(x)
-        x1 = x.max(dim=-1, keepdim=False).values
-        x = get_graph_feature(x1, knn=self.knn, k=self.k)
-        x = self.conv2(x)
-        x2 = x.max(dim=-1, keepdim=False).values
-        x = get_graph_feature(x2, knn=self.knn, k=self.k)
-        x = self.conv3(x)
-        x3 = x.max(dim=-1, keepdim=False).values
-        x = get_graph_feature(x3, knn=self.knn, k=self.k)
-        x = self.conv4(x)
-        x4 = x.max(dim=-1, keepdim=False).values
+        # four EdgeConv blocks: get_graph_feature -> convN -> max over k (dgcnn.py:100-111)
+        x1 = edge_conv(x, self.knn, self.k, self.conv1)
+        x2 = edge_conv(x1, self.knn, self.k, self.conv2)
+        x3 = edge_conv(x2, self.knn, self.k, self.conv3)
+        x4 = edge_conv(x3, self.knn, self.k, self.conv4)
         x = torch.cat((x1, x2, x3, x4), dim=1)
         x = self.conv5(x)
         x1 = x.max(dim=2).values.reshape(batch_size, -1)

@@ -126,3 +126,33 @@ def test_fused_equals_unfused_gpu_path():
     assert (out_f - out_u).abs().max().item() <= 1e-3 * out_u.abs().max().item()
     for (n, p), (_, q) in zip(seq.named_parameters(), seq2.named_parameters()):
         assert _rel(p.grad, q.grad) <= 5e-3, n
+
+
+@pytest.mark.parametrize("B,C,N,k,Co", [(4, 3, 256, 20, 64), (2, 64, 512, 20, 128), (2, 128, 300, 16, 256)])
+def test_fused_edgeconv_matches_reference_sequence(B, C, N, k, Co):
+    """networks/cls/dgcnn.py:29-50 + conv/BN/LeakyReLU/max, float64 CPU literal vs the fused kernels."""
+    from oracle import model_oracle
+    torch.manual_seed(77)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, C, N, generator=g)
+    seq = nn.Sequential(nn.Conv2d(2 * C, Co, 1, bias=False), nn.BatchNorm2d(Co), nn.LeakyReLU(0.2))
+    seq[1].weight.data = torch.randn(Co, generator=g)          # incl. negative scales (min path)
+    seq[1].bias.data = 0.3 * torch.randn(Co, generator=g)
+    seq.train()
+    ref_seq = copy.deepcopy(seq).double()
+    x64 = x.double().requires_grad_(True)
+    ref = ref_seq(model_oracle.get_graph_feature(x64, k)).max(dim=-1).values
+    gout = torch.randn(ref.shape, generator=g)
+    ref.backward(gout.double())
+
+    seq_d = copy.deepcopy(seq).to(DEV)
+    xd = x.to(DEV).requires_grad_(True)
+    idx = F.knn(xd.detach(), xd.detach(), k)
+    assert fused.edgeconv_supported(seq_d)
+    out = fused.fused_edgeconv(xd, idx, seq_d)
+    out.backward(gout.to(DEV))
+    scale = ref.abs().max().item()
+    assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= 1e-3 * scale
+    for (n, p), (_, q) in zip(seq_d.named_parameters(), ref_seq.named_parameters()):
+        assert _rel(p.grad, q.grad) <= 5e-3, f"{n}: rel-L2 {_rel(p.grad, q.grad):.3e}"
+    assert _rel(xd.grad, x64.grad) <= 5e-3

@@ -626,6 +626,8 @@ static int wgrad_l(const PclRowGemm &al, int pl, const PclRowGemm &ar, int pr, l
 
 namespace pcl {
 int rowgemm_tc_dispatch(const PclRowGemm &a, int pro, int epi, cudaStream_t st);  // rowgemm_tc.cu
+bool rowgemm_ws_supported(const PclRowGemm &a, int pro, int epi);                  // rowgemm_ws.cu
+int rowgemm_ws_dispatch(const PclRowGemm &a, int pro, int epi, cudaStream_t st);
 int wgrad_tc_dispatch(const PclRowGemm &al, int pl, const PclRowGemm &ar, int pr, long long P, int M,
                       int N, float *out, int ldo, cudaStream_t st);                 // wgrad_tc.cu
 static PclRowGemm with_ns_shift(PclRowGemm a) {
@@ -655,7 +657,10 @@ extern "C" int pcl_rowgemm(const PclRowGemm *args, int prologue, int epilogue, i
     if (a.P == 0) return PCL_OK;
     cudaStream_t st = (cudaStream_t)stream;
     // x3: 0 = mma.sync TF32, 1 = mma.sync 3xTF32, 2 = tcgen05 3xTF32 (W = [raw | hi | lo] stacked)
-    if (x3 == 2) return rowgemm_tc_dispatch(a, prologue, epilogue, st);
+    // 3 = warp-specialised tcgen05 pipeline (rowgemm_ws.cu) for the shapes it covers, else as 2
+    if (x3 == 3 && rowgemm_ws_supported(a, prologue, epilogue))
+        return rowgemm_ws_dispatch(a, prologue, epilogue, st);
+    if (x3 >= 2) return rowgemm_tc_dispatch(a, prologue, epilogue, st);
     return x3 ? dispatch_pro<true>(a, prologue, epilogue, st)
               : dispatch_pro<false>(a, prologue, epilogue, st);
 }
@@ -669,7 +674,7 @@ extern "C" int pcl_wgrad(const PclRowGemm *args_l, int prologue_l, const PclRowG
     cudaStream_t st = (cudaStream_t)stream;
     const PclRowGemm al = with_ns_shift(*args_l), ar = with_ns_shift(*args_r);
     // x3 == 2: tcgen05 core when the output fits one 128 x 160 accumulator tile
-    if (x3 == 2 && M <= 128 && N <= 160)
+    if (x3 >= 2 && M <= 128 && N <= 160)
         return wgrad_tc_dispatch(al, prologue_l, ar, prologue_r, P, M, N, out, ldo, st);
     return x3 ? wgrad_l<true>(al, prologue_l, ar, prologue_r, P, M, N, out, ldo, st)
               : wgrad_l<false>(al, prologue_l, ar, prologue_r, P, M, N, out, ldo, st);

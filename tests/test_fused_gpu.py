@@ -55,7 +55,7 @@ def _rel(a, b):
     (4, 512, 64, 0.4, 64, 320, (128, 128, 256)),
     (3, 300, 50, 0.3, 64, 5, (32, 64, 64)),        # ragged: P not a multiple of the 128-row tile
 ])
-@pytest.mark.parametrize("mode", [2, 1, 0])   # tcgen05 3xTF32 | mma.sync 3xTF32 | mma.sync TF32
+@pytest.mark.parametrize("mode", [3, 2, 1, 0])   # tcgen05 warp-specialised | tcgen05 | mma.sync 3xTF32 | mma.sync TF32
 def test_fused_sa_branch_matches_reference_sequence(B, N, S, r, ns, C, chans, mode):
     xyz, nrm, _ = modelnet_batch(B, N, seed=N + ns)
     g = torch.Generator().manual_seed(5)

@@ -49,6 +49,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// latency-critical wait of the single MMA-issuing thread: plain spin, no suspend
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            " selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -123,49 +135,60 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 
 // ------------------------------------------------------------------------------------------
 // Prologues, split into issue() (async copy of the raw 16-byte piece(s) into the operand slot)
-// and finish() (the value of the 4 channels k..k+3 of row p, given the landed piece(s)).
+// and finish() (the value of 4 consecutive channels of row p, given the landed piece(s)).
+//   stride(a)  elements per source row;  kbase(a)  first K column of the copied part
+//   ebase      element offset of the source row (p*stride, or src[p]*stride when kSrc)
+//   kcol       K column minus kbase (multiple of 4)
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_s(float z, float slope) { return fmaxf(z, z * slope); }   // 0 <= slope <= 1
 struct WPar2 { float4 sc, sh; };
 __device__ __forceinline__ float4 bn_act_p(float4 y, const WPar2 &w, float slope) {
-    return make_float4(act_f(fmaf(w.sc.x, y.x, w.sh.x), slope), act_f(fmaf(w.sc.y, y.y, w.sh.y), slope),
-                       act_f(fmaf(w.sc.z, y.z, w.sh.z), slope), act_f(fmaf(w.sc.w, y.w, w.sh.w), slope));
+    return make_float4(act_s(fmaf(w.sc.x, y.x, w.sh.x), slope), act_s(fmaf(w.sc.y, y.y, w.sh.y), slope),
+                       act_s(fmaf(w.sc.z, y.z, w.sh.z), slope), act_s(fmaf(w.sc.w, y.w, w.sh.w), slope));
 }
 struct WProBnAct {
-    static constexpr bool kSrc = false;
+    static constexpr bool kSrc = false, kOneHot = false;
     using Par = WPar2;
-    static __device__ __forceinline__ Par params(const PclRowGemm &a, int k) { return {ld4(a.scale + k), ld4(a.shift + k)}; }
-    static __device__ __forceinline__ void issue(const PclRowGemm &a, long long p, int k, bool ok, int, uint32_t hi, uint32_t) {
-        cp_async16_zfill(hi, a.x0 + (ok ? p * a.K + k : 0), ok);
+    static __device__ __forceinline__ int stride(const PclRowGemm &a) { return a.K; }
+    static __device__ __forceinline__ int kbase(const PclRowGemm &) { return 0; }
+    static __device__ __forceinline__ Par params(const PclRowGemm &a, int kcol) { return {ld4(a.scale + kcol), ld4(a.shift + kcol)}; }
+    static __device__ __forceinline__ void issue(const PclRowGemm &a, long long ebase, int kcol, bool ok, uint32_t hi, uint32_t) {
+        cp_async16_zfill(hi, a.x0 + (ok ? ebase + kcol : 0), ok);
     }
     static __device__ __forceinline__ float4 finish(const PclRowGemm &a, const Par &w, long long, int, bool, uint32_t hi, uint32_t) {
         return bn_act_p(lds4(hi), w, a.slope);
     }
 };
 struct WProGatherBnAct {
-    static constexpr bool kSrc = true;
+    static constexpr bool kSrc = true, kOneHot = false;
     using Par = WPar2;
-    static __device__ __forceinline__ Par params(const PclRowGemm &a, int k) { return {ld4(a.scale + k), ld4(a.shift + k)}; }
-    static __device__ __forceinline__ void issue(const PclRowGemm &a, long long, int k, bool ok, int src, uint32_t hi, uint32_t) {
-        cp_async16_zfill(hi, a.U + (ok ? (long long)src * a.K + k : 0), ok);
+    static __device__ __forceinline__ int stride(const PclRowGemm &a) { return a.K; }
+    static __device__ __forceinline__ int kbase(const PclRowGemm &) { return 0; }
+    static __device__ __forceinline__ Par params(const PclRowGemm &a, int kcol) { return {ld4(a.scale + kcol), ld4(a.shift + kcol)}; }
+    static __device__ __forceinline__ void issue(const PclRowGemm &a, long long ebase, int kcol, bool ok, uint32_t hi, uint32_t) {
+        cp_async16_zfill(hi, a.U + (ok ? ebase + kcol : 0), ok);
     }
-    static __device__ __forceinline__ float4 finish(const PclRowGemm &a, const Par &w, long long p, int k, bool ok, uint32_t hi, uint32_t) {
+    static __device__ __forceinline__ float4 finish(const PclRowGemm &a, const Par &w, long long p, int kcol, bool ok, uint32_t hi, uint32_t) {
+        // branch-free so the four pieces' V loads batch: invalid rows read a dummy vector with weight 0
+        const bool use_v = a.V != nullptr && ok;
+        const float vs = use_v ? a.vsign : 0.f;
+        const float4 v = ld4(use_v ? a.V + group_of(a, p) * a.K + kcol : a.scale + kcol);
         float4 u = lds4(hi);
-        if (a.V != nullptr && ok) {
-            const float4 v = ld4(a.V + group_of(a, p) * a.K + k);
-            u = make_float4(fmaf(a.vsign, v.x, u.x), fmaf(a.vsign, v.y, u.y), fmaf(a.vsign, v.z, u.z), fmaf(a.vsign, v.w, u.w));
-        }
+        u = make_float4(fmaf(vs, v.x, u.x), fmaf(vs, v.y, u.y), fmaf(vs, v.z, u.z), fmaf(vs, v.w, u.w));
         return bn_act_p(u, w, a.slope);
     }
 };
 struct WPar5 { float4 mu, rs, bs, m1, m2; };
 struct WProBnBwd {
-    static constexpr bool kSrc = false;
+    static constexpr bool kSrc = false, kOneHot = false;
     using Par = WPar5;
-    static __device__ __forceinline__ Par params(const PclRowGemm &a, int k) {
-        return {ld4(a.mean + k), ld4(a.rstd + k), ld4(a.bscale + k), ld4(a.m1 + k), ld4(a.m2 + k)};
+    static __device__ __forceinline__ int stride(const PclRowGemm &a) { return a.K; }
+    static __device__ __forceinline__ int kbase(const PclRowGemm &) { return 0; }
+    static __device__ __forceinline__ Par params(const PclRowGemm &a, int kcol) {
+        return {ld4(a.mean + kcol), ld4(a.rstd + kcol), ld4(a.bscale + kcol), ld4(a.m1 + kcol), ld4(a.m2 + kcol)};
     }
-    static __device__ __forceinline__ void issue(const PclRowGemm &a, long long p, int k, bool ok, int, uint32_t hi, uint32_t lo) {
-        const long long o = ok ? p * a.K + k : 0;
+    static __device__ __forceinline__ void issue(const PclRowGemm &a, long long ebase, int kcol, bool ok, uint32_t hi, uint32_t lo) {
+        const long long o = ok ? ebase + kcol : 0;
         cp_async16_zfill(hi, a.x0 + o, ok);
         cp_async16_zfill(lo, a.x1 + o, ok);
     }
@@ -177,28 +200,19 @@ struct WProBnBwd {
                            w.bs.w * (d.w - w.m1.w - (y.w - w.mu.w) * w.rs.w * w.m2.w));
     }
 };
-// [one-hot routed max-gradient (k < C3) | act(bn(x0)) (k >= C3)]; C3 % KC == 0, so a chunk is one or the other
+// [one-hot routed max-gradient (k < C3) | act(bn(x0)) (k >= C3)].  C3 % KC == 0, so a chunk is one or
+// the other; the one-hot chunks take the scatter path of the transform loop (kOneHot), the rest is
+// WProBnAct on x0 with row stride K - C3.
 struct WProG3A2 {
-    static constexpr bool kSrc = false;
+    static constexpr bool kSrc = false, kOneHot = true;
     using Par = WPar2;
-    static __device__ __forceinline__ Par params(const PclRowGemm &a, int k) {
-        if (k < a.C3) return {f4zero(), f4zero()};
-        return {ld4(a.scale + (k - a.C3)), ld4(a.shift + (k - a.C3))};
+    static __device__ __forceinline__ int stride(const PclRowGemm &a) { return a.K - a.C3; }
+    static __device__ __forceinline__ int kbase(const PclRowGemm &a) { return a.C3; }
+    static __device__ __forceinline__ Par params(const PclRowGemm &a, int kcol) { return {ld4(a.scale + kcol), ld4(a.shift + kcol)}; }
+    static __device__ __forceinline__ void issue(const PclRowGemm &a, long long ebase, int kcol, bool ok, uint32_t hi, uint32_t) {
+        cp_async16_zfill(hi, a.x0 + (ok ? ebase + kcol : 0), ok);
     }
-    static __device__ __forceinline__ void issue(const PclRowGemm &a, long long p, int k, bool ok, int, uint32_t hi, uint32_t) {
-        if (k < a.C3) return;
-        cp_async16_zfill(hi, a.x0 + (ok ? p * (a.K - a.C3) + (k - a.C3) : 0), ok);
-    }
-    static __device__ __forceinline__ float4 finish(const PclRowGemm &a, const Par &w, long long p, int k, bool ok, uint32_t hi, uint32_t) {
-        if (k < a.C3) {
-            if (!ok) return f4zero();
-            const long long g = group_of(a, p);
-            const int r = (int)(p - g * a.ns);
-            const int4 sp = __ldg(reinterpret_cast<const int4 *>(a.selpos + g * a.C3 + k));
-            const float4 gv = ld4(a.g3s + g * a.C3 + k);
-            return make_float4(sp.x == r ? gv.x : 0.f, sp.y == r ? gv.y : 0.f, sp.z == r ? gv.z : 0.f,
-                               sp.w == r ? gv.w : 0.f);
-        }
+    static __device__ __forceinline__ float4 finish(const PclRowGemm &a, const Par &w, long long, int, bool, uint32_t hi, uint32_t) {
         return bn_act_p(lds4(hi), w, a.slope);
     }
 };
@@ -219,21 +233,21 @@ __device__ __forceinline__ WEpiBwdPar load_bwd_par(const PclRowGemm &a, int n, b
     return e;
 }
 struct WEpiStoreStats {
-    static constexpr bool kMaxMin = false, kFetch = false, kStats = true;
+    static constexpr bool kMaxMin = false, kFetch = false, kStats = true, kSrc = false;
     using Par = int;
     static __device__ __forceinline__ Par params(const PclRowGemm &, int, bool) { return 0; }
-    static __device__ __forceinline__ float fetch(const PclRowGemm &, long long, int) { return 0.f; }
+    static __device__ __forceinline__ const float *fetch_ptr(const PclRowGemm &a, long long, int, int) { return a.W; }
     static __device__ __forceinline__ void apply(const PclRowGemm &, const Par &, float &v, float &q, float) { q = v * v; }
 };
 struct WEpiStore {
-    static constexpr bool kMaxMin = false, kFetch = false, kStats = false;
+    static constexpr bool kMaxMin = false, kFetch = false, kStats = false, kSrc = false;
     using Par = int;
     static __device__ __forceinline__ Par params(const PclRowGemm &, int, bool) { return 0; }
-    static __device__ __forceinline__ float fetch(const PclRowGemm &, long long, int) { return 0.f; }
+    static __device__ __forceinline__ const float *fetch_ptr(const PclRowGemm &a, long long, int, int) { return a.W; }
     static __device__ __forceinline__ void apply(const PclRowGemm &, const Par &, float &, float &q, float) { q = 0.f; }
 };
 struct WEpiMaxMinStats {
-    static constexpr bool kMaxMin = true, kFetch = false, kStats = true;
+    static constexpr bool kMaxMin = true, kFetch = false, kStats = true, kSrc = false;
     using Par = int;
     static __device__ __forceinline__ Par params(const PclRowGemm &, int, bool) { return 0; }
 };
@@ -242,20 +256,20 @@ __device__ __forceinline__ void bwd_act1(const PclRowGemm &a, const WEpiBwdPar &
     q = v * (y - e.mu) * e.rs;
 }
 struct WEpiBwdY {
-    static constexpr bool kMaxMin = false, kFetch = true, kStats = true;
+    static constexpr bool kMaxMin = false, kFetch = true, kStats = true, kSrc = false;
     using Par = WEpiBwdPar;
     static __device__ __forceinline__ Par params(const PclRowGemm &a, int n, bool act) { return load_bwd_par(a, n, act); }
-    static __device__ __forceinline__ float fetch(const PclRowGemm &a, long long p, int n) { return __ldg(a.ey + p * a.N + n); }
+    static __device__ __forceinline__ const float *fetch_ptr(const PclRowGemm &a, long long p, int n, int) { return a.ey + p * a.N + n; }
     static __device__ __forceinline__ void apply(const PclRowGemm &a, const Par &e, float &v, float &q, float y) { bwd_act1(a, e, v, q, y); }
 };
+// ey := U[src[p]] + vsign*V[p/ns]; the src index arrives by shuffle from a lane-distributed prefetch and
+// the V term is hoisted per 16-row block (ns % 16 == 0)
 struct WEpiBwdGather {
-    static constexpr bool kMaxMin = false, kFetch = true, kStats = true;
+    static constexpr bool kMaxMin = false, kFetch = true, kStats = true, kSrc = true;
     using Par = WEpiBwdPar;
     static __device__ __forceinline__ Par params(const PclRowGemm &a, int n, bool act) { return load_bwd_par(a, n, act); }
-    static __device__ __forceinline__ float fetch(const PclRowGemm &a, long long p, int n) {
-        const float u = __ldg(a.U + (long long)__ldg(a.src + p) * a.N + n);
-        if (a.V == nullptr) return u;
-        return fmaf(a.vsign, __ldg(a.V + group_of(a, p) * a.N + n), u);
+    static __device__ __forceinline__ const float *fetch_ptr(const PclRowGemm &a, long long, int n, int src) {
+        return a.U + (long long)src * a.N + n;
     }
     static __device__ __forceinline__ void apply(const PclRowGemm &a, const Par &e, float &v, float &q, float y) { bwd_act1(a, e, v, q, y); }
 };
@@ -265,33 +279,40 @@ constexpr int kThreadsWS = (kTransformWarps + kEpilogueWarps + 1) * 32;   // 544
 constexpr int TILE_ROWS = 256;    // activation rows per macro tile = MMA N
 constexpr int MMA_M = 128;        // output channels per pass, zero padded
 
+constexpr int kEySlots = 8;           // max 16-row slots per epilogue warp set (fetch epilogues)
+constexpr int kSmemMax = 232448 - 512;   // 227 KB per CTA minus the static barriers
+constexpr int kSlack = 8 * 1024;      // the 128-lane weight operand is read past its BN rows
+
 template <int KC>
 struct Cfg {
-    static constexpr int S = KC == 16 ? 4 : 2;               // stages
     static constexpr int CPR = KC / 4;                       // 16-byte chunks per row
     static constexpr int A_BYTES = TILE_ROWS * KC * 4;       // one of hi / lo
     static constexpr int W_BYTES = MMA_M * KC * 4;
     static constexpr int STAGE = 2 * A_BYTES + 2 * W_BYTES;
     static constexpr int RSTEP = 256 / CPR;                  // row step between a thread's pieces
+    static constexpr int NWJ = 2 * MMA_M * CPR / 256;        // weight pieces per thread and chunk (max)
 };
 
-// max / min / stats scan of one 16-row block of the accumulator for groups of NS rows
-// (NS = 16: one group per block; NS = 8: two; NS >= 32 handled by the caller as "group spans blocks")
-struct MM {
-    float mx, mn;
-    int imx, imn;
-};
+// stages of the operand ring; a stage is [act hi 256 x KC | act lo | W hi BN x KC | W lo] floats.  The
+// tensor core reads 128 weight rows: rows >= BN are whatever follows in shared memory and only reach
+// accumulator lanes (= channels) >= BN, which nobody reads.
+template <int KC, class Epi>
+constexpr int stages() { return KC == 16 ? 4 : 2; }
+constexpr int kLag = 2;   // the transform refills the stage of chunk c - kLag (never blocks on the MMAs just issued)
 
 template <int KC, class Pro, class Epi>
 __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowGemm a) {
     using C = Cfg<KC>;
-    constexpr int S = C::S, CPR = C::CPR;
+    constexpr int S = stages<KC, Epi>(), CPR = C::CPR;
     // instruction descriptor: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), both K-major, N>>3, M>>4
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TILE_ROWS >> 3) << 17) |
                                ((uint32_t)(MMA_M >> 4) << 24);
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;   // 1024-byte aligned stage ring
+    const uint32_t w_bytes = (uint32_t)((a.N < MMA_M ? a.N : MMA_M) * KC * 4);
+    const uint32_t stage_bytes = 2 * C::A_BYTES + 2 * w_bytes;
     __shared__ __align__(8) uint64_t s_full[S], s_free[S], s_accfull[2], s_accempty[2];
+    __shared__ __align__(8) uint64_t s_eyfull[2][kEySlots], s_eyempty[2][kEySlots];
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -316,66 +337,93 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
         for (int b = 0; b < 2; ++b) {
             mbar_init(smem_u32(&s_accfull[b]), 1);
             mbar_init(smem_u32(&s_accempty[b]), kEpilogueWarps);
+            for (int e = 0; e < kEySlots; ++e) {
+                mbar_init(smem_u32(&s_eyfull[b][e]), 1);
+                mbar_init(smem_u32(&s_eyempty[b][e]), 4);
+            }
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    // weight rows BN..127 of every stage are never written again: zero them once
-    if (BN < MMA_M) {
-        const int n_pad_chunks = (MMA_M - BN) * CPR;
-        for (int e = tid; e < S * 2 * n_pad_chunks; e += kThreadsWS) {
-            const int s = e / (2 * n_pad_chunks), r = e % (2 * n_pad_chunks);
-            const int half = r / n_pad_chunks, q = r % n_pad_chunks;
-            const int n = BN + q / CPR, c = q % CPR;
-            sts4(sbase + s * C::STAGE + 2 * C::A_BYTES + half * C::W_BYTES + sw_off<KC>(n, c), 0u, 0u, 0u, 0u);
-        }
-        fence_proxy_async();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
+    // profiling knobs (scratch/ws_knobs.py): 1 no MMA, 2 no epilogue body, 4 no activation loads, 8 no weight
+    // loads, 16 no transform math
+    const int dbg = a.c0 >> 16;
     const float *Whi = a.W + (long long)a.N * a.ldw;   // W = [raw | hi | lo]; lo = hi + N*ldw
 
     if (warp < kTransformWarps) {
         // ============================ TRANSFORM warps ============================
         const int a_c = tid % CPR, a_row = tid / CPR;
-        // issue cursor (S-1 chunks ahead of the consume cursor)
+        const int stride = Pro::stride(a), kbase = Pro::kbase(a);
+        uint32_t aoff[CPR];   // swizzled byte offset of this thread's pieces inside an operand tile
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) aoff[i] = sw_off<KC>(a_row + C::RSTEP * i, a_c);
+        // this thread's weight pieces: smem offset inside a stage, global pointer at K column 0
+        uint32_t woff[C::NWJ];
+        const float *wptr[C::NWJ];
+        int n_w = 0;
+        auto set_w = [&](int pass) {
+            const int per_half = BN * CPR;
+            n_w = 0;
+#pragma unroll
+            for (int j = 0; j < C::NWJ; ++j) {
+                const int e = tid + 256 * j;
+                const int half = e >= per_half ? 1 : 0, r = e - half * per_half;
+                const int n = r / CPR, c = r % CPR;
+                woff[j] = 2 * C::A_BYTES + half * w_bytes + sw_off<KC>(n, c);
+                wptr[j] = Whi + (long long)half * a.N * a.ldw + (long long)(pass * BN + n) * a.ldw + c * 4;
+                if (e < 2 * per_half) n_w = j + 1;
+            }
+        };
+        set_w(0);
+
+        // ---- issue cursor (S-1 chunks ahead of the consume cursor) ----
         int i_pass = 0, i_lt = 0, i_kc = 0, i_c = 0;
-        int srcI[CPR], srcN[CPR];
+        long long ebase[CPR];
+        uint32_t i_ok = 0;
+        int srcN[CPR];
         auto load_src = [&](int lt, int (&dst)[CPR]) {
-            if (!Pro::kSrc) return;
-            const long long tile = blockIdx.x + (long long)(lt % (my_tiles > 0 ? my_tiles : 1)) * gridDim.x;
+            const long long row0 = (blockIdx.x + (long long)(lt % my_tiles) * gridDim.x) * TILE_ROWS;
 #pragma unroll
             for (int i = 0; i < CPR; ++i) {
-                const long long p = tile * TILE_ROWS + a_row + C::RSTEP * i;
+                const long long p = row0 + a_row + C::RSTEP * i;
                 dst[i] = p < a.P ? __ldg(a.src + p) : 0;
             }
         };
-        if (Pro::kSrc && total_chunks > 0) {
-            load_src(0, srcI);
-            load_src(1, srcN);
+        auto enter_tile = [&](int lt, const int (&srcv)[CPR]) {
+            const long long row0 = (blockIdx.x + (long long)lt * gridDim.x) * TILE_ROWS;
+            i_ok = 0;
+#pragma unroll
+            for (int i = 0; i < CPR; ++i) {
+                const long long p = row0 + a_row + C::RSTEP * i;
+                if (p < a.P) i_ok |= 1u << i;
+                ebase[i] = (Pro::kSrc ? (long long)srcv[i] : p) * stride;
+            }
+        };
+        if (total_chunks > 0) {
+            int src0[CPR] = {};
+            if (Pro::kSrc) {
+                load_src(0, src0);
+                load_src(1, srcN);
+            }
+            enter_tile(0, src0);
         }
         auto issue_next = [&]() {
             if (i_c < total_chunks) {
-                const int s = i_c % S;
-                const uint32_t st = sbase + s * C::STAGE;
-                const long long tile = blockIdx.x + (long long)i_lt * gridDim.x;
-                const int k0 = i_kc * KC + a_c * 4;
+                const uint32_t st = sbase + (i_c % S) * stage_bytes;
+                const int k0 = i_kc * KC;
+                if (!(Pro::kOneHot && k0 < kbase) && !(dbg & 4)) {
+                    const int kcol = k0 - kbase + a_c * 4;
 #pragma unroll
-                for (int i = 0; i < CPR; ++i) {
-                    const int row = a_row + C::RSTEP * i;
-                    const long long p = tile * TILE_ROWS + row;
-                    const uint32_t off = sw_off<KC>(row, a_c);
-                    Pro::issue(a, p, k0, p < a.P, Pro::kSrc ? srcI[i] : 0, st + off, st + C::A_BYTES + off);
+                    for (int i = 0; i < CPR; ++i)
+                        Pro::issue(a, ebase[i], kcol, (i_ok >> i) & 1u, st + aoff[i], st + C::A_BYTES + aoff[i]);
                 }
-                const int n0 = i_pass * BN;
-                const int per_half = BN * CPR;
-                for (int e = tid; e < 2 * per_half; e += kTransformWarps * 32) {
-                    const int half = e >= per_half ? 1 : 0, r = e - half * per_half;
-                    const int n = r / CPR, c = r % CPR;
-                    cp_async16_zfill(st + 2 * C::A_BYTES + half * C::W_BYTES + sw_off<KC>(n, c),
-                                     Whi + (long long)half * a.N * a.ldw + (long long)(n0 + n) * a.ldw + i_kc * KC + c * 4,
-                                     true);
+                if (!(dbg & 8)) {
+#pragma unroll
+                    for (int j = 0; j < C::NWJ; ++j)
+                        if (j < n_w) cp_async16_zfill(st + woff[j], wptr[j] + k0, true);
                 }
                 ++i_c;
                 if (++i_kc == nk) {
@@ -383,37 +431,84 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
                     if (++i_lt == my_tiles) {
                         i_lt = 0;
                         ++i_pass;
+                        if (i_pass < n_pass) set_w(i_pass);
                     }
                     if (Pro::kSrc) {
+                        int cur[CPR];
 #pragma unroll
-                        for (int i = 0; i < CPR; ++i) srcI[i] = srcN[i];
+                        for (int i = 0; i < CPR; ++i) cur[i] = srcN[i];
                         load_src(i_lt + 1, srcN);
+                        enter_tile(i_lt, cur);
+                    } else {
+                        const int none[CPR] = {};
+                        enter_tile(i_lt, none);
                     }
                 }
             }
             cp_async_commit();   // one group per call, even when empty: keeps wait_group counting uniform
         };
-        for (int j = 0; j < S - 1; ++j) issue_next();
+        for (int j = 0; j < S - kLag; ++j) issue_next();
 
+        // ---- consume cursor ----
         int c_lt = 0, c_kc = 0;
+        long long c_row0 = (long long)blockIdx.x * TILE_ROWS;
         for (int c = 0; c < total_chunks; ++c) {
             const int s = c % S;
-            const uint32_t st = sbase + s * C::STAGE;
-            const long long tile = blockIdx.x + (long long)c_lt * gridDim.x;
-            const int k0 = c_kc * KC + a_c * 4;
-            const typename Pro::Par par = Pro::params(a, k0);
-            cp_async_wait<S - 2>();   // this thread's pieces of chunk c have landed
+            const uint32_t st = sbase + s * stage_bytes;
+            const int k0 = c_kc * KC;
+            if (Pro::kOneHot && k0 < kbase) {
+                // routed one-hot chunk: per (group, channel) ONE row carries g3s; everything else is 0.
+                // Zero the tile, then scatter the (256/ns)*KC entries (instead of 1024 compare-selects).
+                const int sh = a.reserved, gpt = TILE_ROWS >> sh;       // groups per macro tile
+                const long long g0 = c_row0 >> sh;
+                const int n_ent = gpt * KC;
+                int sp[CPR];
+                float gv[CPR];
 #pragma unroll
-            for (int i = 0; i < CPR; ++i) {
-                const int row = a_row + C::RSTEP * i;
-                const long long p = tile * TILE_ROWS + row;
-                const uint32_t off = sw_off<KC>(row, a_c);
-                const float4 x4 = Pro::finish(a, par, p, k0, p < a.P, st + off, st + C::A_BYTES + off);
-                const float x[4] = {x4.x, x4.y, x4.z, x4.w};
-                uint32_t hi[4], lo[4];
-                split_tf32_trunc<4>(x, hi, lo);
-                sts4(st + off, hi[0], hi[1], hi[2], hi[3]);
-                sts4(st + C::A_BYTES + off, lo[0], lo[1], lo[2], lo[3]);
+                for (int j = 0; j < CPR; ++j) {      // entries tid + 256*j: prefetch selpos / g3s
+                    const int e = tid + 256 * j;
+                    const long long g = g0 + e / KC;
+                    sp[j] = -1;
+                    gv[j] = 0.f;
+                    if (e < n_ent && (g << sh) < a.P && !(dbg & 16)) {
+                        sp[j] = __ldg(a.selpos + g * a.C3 + k0 + (e % KC));
+                        gv[j] = __ldg(a.g3s + g * a.C3 + k0 + (e % KC));
+                    }
+                }
+                cp_async_wait<S - kLag - 1>();   // (the weights of this chunk)
+#pragma unroll
+                for (int i = 0; i < CPR; ++i) {
+                    sts4(st + aoff[i], 0u, 0u, 0u, 0u);
+                    sts4(st + C::A_BYTES + aoff[i], 0u, 0u, 0u, 0u);
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < CPR; ++j) {
+                    if (sp[j] >= 0) {
+                        const int e = tid + 256 * j;
+                        const int row = ((e / KC) << sh) + sp[j], kk = e % KC;
+                        const uint32_t hi = __float_as_uint(gv[j]) & 0xFFFFE000u;
+                        const uint32_t lo = __float_as_uint(gv[j] - __uint_as_float(hi));
+                        const uint32_t o = st + sw_off<KC>(row, kk >> 2) + (uint32_t)((kk & 3) << 2);
+                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(o), "r"(hi) : "memory");
+                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(o + C::A_BYTES), "r"(lo) : "memory");
+                    }
+                }
+            } else {
+                const int kcol = k0 - kbase + a_c * 4;
+                const typename Pro::Par par = Pro::params(a, kcol);
+                cp_async_wait<S - kLag - 1>();   // this thread's pieces of chunk c have landed
+#pragma unroll
+                for (int i = 0; i < CPR; ++i) {
+                    if (dbg & 16) break;
+                    const long long p = c_row0 + a_row + C::RSTEP * i;
+                    const float4 x4 = Pro::finish(a, par, p, kcol, p < a.P, st + aoff[i], st + C::A_BYTES + aoff[i]);
+                    const float x[4] = {x4.x, x4.y, x4.z, x4.w};
+                    uint32_t hi[4], lo[4];
+                    split_tf32_trunc<4>(x, hi, lo);
+                    sts4(st + aoff[i], hi[0], hi[1], hi[2], hi[3]);
+                    sts4(st + C::A_BYTES + aoff[i], lo[0], lo[1], lo[2], lo[3]);
+                }
             }
             fence_proxy_async();   // generic-proxy writes (st.shared and cp.async) -> async proxy (tensor core)
             __syncwarp();
@@ -421,118 +516,243 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
             if (++c_kc == nk) {
                 c_kc = 0;
                 if (++c_lt == my_tiles) c_lt = 0;
+                c_row0 = (blockIdx.x + (long long)c_lt * gridDim.x) * TILE_ROWS;
             }
-            // refill the stage chunk c-1 used (its MMAs were issued a whole transform ago)
-            if (c >= 1 && i_c < total_chunks) mbar_wait(smem_u32(&s_free[(c - 1) % S]), (uint32_t)(((c - 1) / S) & 1));
+            // refill the stage chunk c - kLag used: its MMAs were issued more than a whole transform ago, so
+            // this wait does not tie the transform to the tensor core's pace
+            if (c >= kLag && i_c < total_chunks)
+                mbar_wait(smem_u32(&s_free[(c - kLag) % S]), (uint32_t)(((c - kLag) / S) & 1));
             issue_next();
         }
         cp_async_wait<0>();
     } else if (warp < kTransformWarps + kEpilogueWarps) {
         // ============================ EPILOGUE warps ============================
-        const int q = warp & 3, h = (warp - kTransformWarps) >> 2;   // TMEM lane quarter, row half
+        const int q = warp & 3, h = (warp - kTransformWarps) >> 2;   // TMEM lane quarter, row half / block parity
         const int ch = q * 32 + lane;
         const bool act = ch < BN;
-        int tl = 0;   // local tile counter across passes (accumulator buffer = tl & 1)
-        for (int pass = 0; pass < n_pass; ++pass) {
-            const int n = pass * BN + ch;
-            const typename Epi::Par par = Epi::params(a, n, act);
-            double acc_s = 0.0, acc_q = 0.0;
-            for (int lt = 0; lt < my_tiles; ++lt, ++tl) {
-                const int buf = tl & 1;
-                mbar_wait(smem_u32(&s_accfull[buf]), (uint32_t)((tl >> 1) & 1));
-                tc_fence_after();
-                const long long tile = blockIdx.x + (long long)lt * gridDim.x;
-                const long long p0 = tile * TILE_ROWS + h * 128;
-                const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TILE_ROWS + h * 128);
-                float fs = 0.f, fq = 0.f;
-                if (p0 < a.P) {
-                    if constexpr (Epi::kMaxMin) {
-                        const int ns = a.ns, sh = a.reserved;
-                        float mx = -3.402823466e38f, mn = 3.402823466e38f;
-                        int imx = 0, imn = 0;
-                        for (int blk = 0; blk < 8; ++blk) {
-                            const long long pb = p0 + blk * 16;
-                            if (pb >= a.P) break;
-                            float v[16];
-                            tc_ld16(tbase + blk * 16, v);
-                            if (ns >= 16) {
-                                const int l0 = (int)(pb & (ns - 1));   // offset of this block inside its group
+        if constexpr (!Epi::kFetch) {
+            // ---- max/min and plain store epilogues: warp (q, h) owns rows [128h, 128h+128) of the tile ----
+            int tl = 0;   // local tile counter across passes (accumulator buffer = tl & 1)
+            for (int pass = 0; pass < n_pass; ++pass) {
+                const int n = pass * BN + ch;
+                double acc_s = 0.0, acc_q = 0.0;
+                for (int lt = 0; lt < my_tiles; ++lt, ++tl) {
+                    const int buf = tl & 1;
+                    const long long tile = blockIdx.x + (long long)lt * gridDim.x;
+                    const long long p0 = tile * TILE_ROWS + h * 128;
+                    const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TILE_ROWS + h * 128);
+                    float fs = 0.f, fq = 0.f;
+                    while (!mbar_try_wait(smem_u32(&s_accfull[buf]), (uint32_t)((tl >> 1) & 1))) __nanosleep(64);
+                    tc_fence_after();
+                    if (p0 < a.P && !(dbg & 2)) {
+                        if constexpr (Epi::kMaxMin) {
+                            const int ns = a.ns, sh = a.reserved;
+                            float mx = -3.402823466e38f, mn = 3.402823466e38f;
+                            int imx = 0, imn = 0;
+                            for (int blk = 0; blk < 8; ++blk) {
+                                const long long pb = p0 + blk * 16;
+                                if (pb >= a.P) break;
+                                float v[16];
+                                tc_ld16(tbase + blk * 16, v);
+                                if (ns >= 16) {
+                                    const int l0 = (int)(pb & (ns - 1));   // offset of this block inside its group
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) {
-                                    fs += v[i];
-                                    fq = fmaf(v[i], v[i], fq);
-                                    if (v[i] > mx) { mx = v[i]; imx = l0 + i; }
-                                    if (v[i] < mn) { mn = v[i]; imn = l0 + i; }
-                                }
-                                if (l0 + 16 == ns) {
-                                    if (act) {
-                                        const long long o = (pb >> sh) * a.N + n;
-                                        a.gmax[o] = mx; a.gmin[o] = mn; a.amax[o] = imx; a.amin[o] = imn;
+                                    for (int i = 0; i < 16; ++i) {
+                                        fs += v[i];
+                                        fq = fmaf(v[i], v[i], fq);
+                                        if (v[i] > mx) { mx = v[i]; imx = l0 + i; }
+                                        if (v[i] < mn) { mn = v[i]; imn = l0 + i; }
                                     }
-                                    mx = -3.402823466e38f; mn = 3.402823466e38f; imx = 0; imn = 0;
-                                }
-                            } else {   // ns = 8: two groups per block
-#pragma unroll
-                                for (int gq = 0; gq < 2; ++gq) {
-                                    if (pb + gq * 8 < a.P) {
-                                        mx = -3.402823466e38f; mn = 3.402823466e38f; imx = 0; imn = 0;
-#pragma unroll
-                                        for (int i = 0; i < 8; ++i) {
-                                            const float x = v[gq * 8 + i];
-                                            fs += x;
-                                            fq = fmaf(x, x, fq);
-                                            if (x > mx) { mx = x; imx = i; }
-                                            if (x < mn) { mn = x; imn = i; }
-                                        }
+                                    if (l0 + 16 == ns) {
                                         if (act) {
-                                            const long long o = ((pb + gq * 8) >> sh) * a.N + n;
+                                            const long long o = (pb >> sh) * a.N + n;
                                             a.gmax[o] = mx; a.gmin[o] = mn; a.amax[o] = imx; a.amin[o] = imn;
+                                        }
+                                        mx = -3.402823466e38f; mn = 3.402823466e38f; imx = 0; imn = 0;
+                                    }
+                                } else {   // ns = 8: two groups per block
+#pragma unroll
+                                    for (int gq = 0; gq < 2; ++gq) {
+                                        if (pb + gq * 8 < a.P) {
+                                            mx = -3.402823466e38f; mn = 3.402823466e38f; imx = 0; imn = 0;
+#pragma unroll
+                                            for (int i = 0; i < 8; ++i) {
+                                                const float x = v[gq * 8 + i];
+                                                fs += x;
+                                                fq = fmaf(x, x, fq);
+                                                if (x > mx) { mx = x; imx = i; }
+                                                if (x < mn) { mn = x; imn = i; }
+                                            }
+                                            if (act) {
+                                                const long long o = ((pb + gq * 8) >> sh) * a.N + n;
+                                                a.gmax[o] = mx; a.gmin[o] = mn; a.amax[o] = imx; a.amin[o] = imn;
+                                            }
+                                        }
+                                    }
+                                }
+                            }
+                        } else {
+                            const typename Epi::Par par = Epi::params(a, n, act);
+                            for (int blk = 0; blk < 8; ++blk) {
+                                const long long pb = p0 + blk * 16;
+                                if (pb >= a.P) break;
+                                float v[16];
+                                tc_ld16(tbase + blk * 16, v);
+                                if (act) {
+                                    float *op = a.out + pb * a.N + n;
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) {
+                                        if (pb + i < a.P) {
+                                            float x = v[i], qq;
+                                            Epi::apply(a, par, x, qq, 0.f);
+                                            if (!(dbg & 32)) op[(long long)i * a.N] = x;
+                                            if (Epi::kStats) { fs += x; fq += qq; }
                                         }
                                     }
                                 }
                             }
                         }
-                    } else {
-                        float yv[16], yn[16];
-                        auto fetch_blk = [&](int blk, float (&y)[16]) {
-                            if (!Epi::kFetch) return;
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&s_accempty[buf]));
+                    acc_s += (double)fs;
+                    acc_q += (double)fq;
+                }
+                if (Epi::kStats && act) {
+                    atomicAdd(a.stats + n, acc_s);
+                    atomicAdd(a.stats + a.N + n, acc_q);
+                }
+            }
+        } else {
+            // ---- store epilogues with an extra per-element operand (ey, or the gathered y1 rows) ----
+            // The operand rows reach shared memory by cp.async.bulk (one row per lane, completion on an
+            // mbarrier) E-1 blocks of 16 rows ahead: loads issued from registers would sit behind the
+            // transform warps' deep prefetch queue with only 16 rows in flight per warp.
+            // The four quarter-warps with the same h form a set; set h owns the 16-row blocks 2*bi + h of
+            // every tile, its own ring of E slots and its own full / empty barriers; warp q == 0 issues.
+            const int slot_bytes = 16 * BN * 4;
+            int E = a.c1 / (2 * slot_bytes);   // a.c1 = bytes of the operand ring (set by the launcher)
+            E = E > kEySlots ? kEySlots : E;
+            const uint32_t ey_base = sbase + S * stage_bytes + (uint32_t)(h * E * slot_bytes);
+            const int total_blocks = my_tiles * n_pass * 8;
+            auto block_row0 = [&](int kk) {   // first row of block kk of this set
+                const int tlk = kk >> 3, ltk = tlk % my_tiles;
+                return (blockIdx.x + (long long)ltk * gridDim.x) * TILE_ROWS + 16 * (2 * (kk & 7) + h);
+            };
+            // gather only: the src indices of this set's 128 rows of a tile, lane-distributed (set-row
+            // r = 16*bi + i lives in lane r % 32, register r / 32), loaded one whole tile ahead
+            int srcv[4] = {0, 0, 0, 0}, srcn[4] = {0, 0, 0, 0};
+            auto load_src_tile = [&](int tlk, int (&dst)[4]) {
+                if (!Epi::kSrc || tlk * 8 >= total_blocks) return;
+                const long long row0 = (blockIdx.x + (long long)(tlk % my_tiles) * gridDim.x) * TILE_ROWS;
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const long long p = p0 + blk * 16 + i;
-                                y[i] = (act && p < a.P) ? Epi::fetch(a, p, n) : 0.f;
-                            }
-                        };
-                        fetch_blk(0, yv);
-                        for (int blk = 0; blk < 8; ++blk) {
-                            const long long pb = p0 + blk * 16;
-                            if (pb >= a.P) break;
-                            if (blk + 1 < 8) fetch_blk(blk + 1, yn);
-                            float v[16];
-                            tc_ld16(tbase + blk * 16, v);
-                            if (act) {
-                                float *op = a.out + pb * a.N + n;
+                for (int j = 0; j < 4; ++j) {
+                    const int r = lane + 32 * j;
+                    const long long p = row0 + 16 * (2 * (r >> 4) + h) + (r & 15);
+                    dst[j] = p < a.P ? __ldg(a.src + p) : 0;
+                }
+            };
+            auto issue_blk = [&](int kk) {   // warp-uniform, q == 0 only
+                if (kk >= total_blocks) return;
+                const int slot = kk % E;
+                const uint32_t fullb = smem_u32(&s_eyfull[h][slot]);
+                if (kk >= E) mbar_wait(smem_u32(&s_eyempty[h][slot]), (uint32_t)(((kk / E) - 1) & 1));
+                const long long p = block_row0(kk) + lane;
+                const bool valid = lane < 16 && p < a.P && !(dbg & (2 | 64));
+                const int n0k = ((kk >> 3) / my_tiles) * BN;
+                if (Epi::kSrc && (kk & 7) == 0 && kk > 0) {   // the issue cursor enters a new tile
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) {
-                                    if (pb + i < a.P) {
-                                        float x = v[i], qq;
-                                        Epi::apply(a, par, x, qq, yv[i]);
-                                        op[(long long)i * a.N] = x;
-                                        if (Epi::kStats) { fs += x; fq += qq; }
-                                    }
-                                }
-                            }
-                            if (Epi::kFetch) {
+                    for (int j = 0; j < 4; ++j) srcv[j] = srcn[j];
+                    load_src_tile((kk >> 3) + 1, srcn);
+                }
+                int srow = 0;
+                if (Epi::kSrc) {
+                    const int bi = kk & 7;
+                    const int sv = bi < 4 ? (bi < 2 ? srcv[0] : srcv[1]) : (bi < 6 ? srcv[2] : srcv[3]);
+                    srow = __shfl_sync(0xffffffffu, sv, (bi & 1) * 16 + (lane & 15));
+                }
+                const float *g = (Epi::kSrc ? a.U + (long long)srow * a.N : a.ey + p * a.N) + n0k;
+                const int nvalid = __popc(__ballot_sync(0xffffffffu, valid));
+                if (lane == 0) {
+                    if (nvalid > 0)
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fullb),
+                                     "r"(nvalid * BN * 4)
+                                     : "memory");
+                    else
+                        mbar_arrive(fullb);
+                }
+                __syncwarp();
+                if (valid)
+                    asm volatile(
+                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                            ey_base + (uint32_t)(slot * slot_bytes + lane * BN * 4)),
+                        "l"(g), "r"(BN * 4), "r"(fullb)
+                        : "memory");
+            };
+            if (q == 0) {
+                load_src_tile(0, srcv);
+                load_src_tile(1, srcn);
+                for (int kk = 0; kk < E - 1 && !(dbg & 128); ++kk) issue_blk(kk);
+            }
+            double acc_s = 0.0, acc_q = 0.0;
+            float fs = 0.f, fq = 0.f;
+            int n = ch;
+            typename Epi::Par par = Epi::params(a, n, act);
+            for (int k = 0; k < total_blocks; ++k) {
+                const int bi = k & 7, tl = k >> 3, buf = tl & 1;
+                if (bi == 0 && tl > 0 && tl % my_tiles == 0) {   // next pass: flush the statistics, new channel
+                    if (Epi::kStats && act) {
+                        atomicAdd(a.stats + n, acc_s);
+                        atomicAdd(a.stats + a.N + n, acc_q);
+                    }
+                    acc_s = acc_q = 0.0;
+                    n = (tl / my_tiles) * BN + ch;
+                    par = Epi::params(a, n, act);
+                }
+                if (q == 0 && !(dbg & 128)) issue_blk(k + E - 1);
+                const long long pb = block_row0(k);
+                const bool use_v = Epi::kSrc && a.V != nullptr && act && pb < a.P;
+                const float vterm = __ldg(use_v ? a.V + group_of(a, pb) * a.N + n : a.escale) * (use_v ? a.vsign : 0.f);
+                if (bi == 0) {
+                    while (!mbar_try_wait(smem_u32(&s_accfull[buf]), (uint32_t)((tl >> 1) & 1))) __nanosleep(64);
+                    tc_fence_after();
+                }
+                const int slot = k % E;
+                if (!(dbg & 128)) mbar_wait(smem_u32(&s_eyfull[h][slot]), (uint32_t)((k / E) & 1));
+                float y[16];
+                {
+                    const uint32_t ys = ey_base + (uint32_t)(slot * slot_bytes + (act ? ch : 0) * 4);
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) yv[i] = yn[i];
+                    for (int i = 0; i < 16; ++i)
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y[i]) : "r"(ys + (uint32_t)(i * BN * 4)));
+                }
+                __syncwarp();
+                if (lane == 0 && !(dbg & 128)) mbar_arrive(smem_u32(&s_eyempty[h][slot]));
+                if (pb < a.P && !(dbg & 2)) {
+                    float v[16];
+                    tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TILE_ROWS + 16 * (2 * bi + h)), v);
+                    if (act) {
+                        float *op = a.out + pb * a.N + n;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            if (pb + i < a.P) {
+                                float x = v[i], qq;
+                                Epi::apply(a, par, x, qq, y[i] + vterm);
+                                if (!(dbg & 32)) op[(long long)i * a.N] = x;
+                                if (Epi::kStats) { fs += x; fq += qq; }
                             }
                         }
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&s_accempty[buf]));
-                acc_s += (double)fs;
-                acc_q += (double)fq;
+                if (bi == 7) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&s_accempty[buf]));
+                    acc_s += (double)fs;
+                    acc_q += (double)fq;
+                    fs = fq = 0.f;
+                }
             }
             if (Epi::kStats && act) {
                 atomicAdd(a.stats + n, acc_s);
@@ -545,19 +765,20 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
         for (int pass = 0; pass < n_pass; ++pass) {
             for (int lt = 0; lt < my_tiles; ++lt, ++tl) {
                 const int buf = tl & 1;
-                if (tl >= 2) mbar_wait(smem_u32(&s_accempty[buf]), (uint32_t)(((tl >> 1) - 1) & 1));
+                if (tl >= 2) mbar_wait_spin(smem_u32(&s_accempty[buf]), (uint32_t)(((tl >> 1) - 1) & 1));
                 tc_fence_after();
                 const uint32_t d = tmem + (uint32_t)(buf * TILE_ROWS);
                 for (int kc = 0; kc < nk; ++kc, ++c) {
                     const int s = c % S;
-                    mbar_wait(smem_u32(&s_full[s]), (uint32_t)((c / S) & 1));
+                    mbar_wait_spin(smem_u32(&s_full[s]), (uint32_t)((c / S) & 1));
                     tc_fence_after();
-                    const uint32_t st = sbase + s * C::STAGE;
+                    const uint32_t st = sbase + s * stage_bytes;
                     const uint64_t dXhi = umma_desc<KC>(st), dXlo = umma_desc<KC>(st + C::A_BYTES);
                     const uint64_t dWhi = umma_desc<KC>(st + 2 * C::A_BYTES);
-                    const uint64_t dWlo = umma_desc<KC>(st + 2 * C::A_BYTES + C::W_BYTES);
+                    const uint64_t dWlo = umma_desc<KC>(st + 2 * C::A_BYTES + w_bytes);
 #pragma unroll
                     for (int ks = 0; ks < KC / 8; ++ks) {
+                        if (dbg & 1) break;
                         const uint64_t adv = (uint64_t)(ks * 2);   // 32 bytes per K = 8 step, in 16-byte units
                         tc_mma_tf32(d, dWhi + adv, dXlo + adv, IDESC, (kc > 0 || ks > 0) ? 1u : 0u);
                         tc_mma_tf32(d, dWlo + adv, dXhi + adv, IDESC, 1u);
@@ -576,10 +797,26 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
     }
 }
 
+// bytes left for the epilogue-operand ring of the fetch epilogues (KC = 16, 4 stages)
+static int ws_ey_bytes(int N) {
+    const int BN = N < MMA_M ? N : MMA_M;
+    const int ring = 4 * (2 * Cfg<16>::A_BYTES + 2 * BN * 16 * 4);
+    int ey = kSmemMax - 1024 - ring;
+    ey = ey / 1024 * 1024;
+    return ey > 64 * 1024 ? 64 * 1024 : ey;
+}
+
 template <int KC, class Pro, class Epi>
 static int launch_ws(const PclRowGemm &a, cudaStream_t st) {
     using C = Cfg<KC>;
-    const size_t smem = 1024 + (size_t)C::S * C::STAGE;
+    const int BN = a.N < MMA_M ? a.N : MMA_M;
+    const size_t ring = (size_t)stages<KC, Epi>() * (2 * C::A_BYTES + 2 * BN * KC * 4);
+    PclRowGemm b = a;
+    size_t smem = 1024 + ring + kSlack;
+    if (Epi::kFetch) {
+        b.c1 = ws_ey_bytes(a.N);
+        smem = 1024 + ring + (size_t)b.c1;
+    }
     auto kern = rowgemm_ws_kernel<KC, Pro, Epi>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
@@ -588,7 +825,7 @@ static int launch_ws(const PclRowGemm &a, cudaStream_t st) {
     }
     const long long n_tiles = (a.P + TILE_ROWS - 1) / TILE_ROWS;
     const long long grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-    kern<<<(unsigned)grid, kThreadsWS, smem, st>>>(a);
+    kern<<<(unsigned)grid, kThreadsWS, smem, st>>>(b);
     return check_launch("pcl_rowgemm(ws)");
 }
 
@@ -604,9 +841,22 @@ bool rowgemm_ws_supported(const PclRowGemm &a, int pro, int epi) {
                        (pro == PCL_PRO_BN_BWD && epi == PCL_EPI_BWD_GATHER) ||
                        (pro == PCL_PRO_BN_BWD && epi == PCL_EPI_STORE);
     if (!combo) return false;
+    // The store epilogues that need an extra per-element operand (BWD_Y / BWD_GATHER) work and pass the
+    // parity tests, but their operand ring (cp.async.bulk + mbarrier hand-off every 16 rows) is slower
+    // than rowgemm_tc_kernel on B200 (1.18 vs 1.23 ms and 1.28 vs 0.97 ms at P = 2M): opt-in only.
+    if ((epi == PCL_EPI_BWD_Y || epi == PCL_EPI_BWD_GATHER) && !(a.c0 & (1 << 15))) return false;
     if (a.K % 16 != 0 || a.N % 32 != 0) return false;
     if (a.N > 128 && a.N % 128 != 0) return false;
-    if (pro == PCL_PRO_G3_A2 && (a.C3 % 16 != 0 || a.C3 > a.K)) return false;
+    // one-hot scatter: whole groups inside a 256-row tile, at most 4 entries per transform thread
+    if (pro == PCL_PRO_G3_A2 && (a.C3 % 16 != 0 || a.C3 > a.K || a.reserved < 2 || a.reserved > 8 || a.P % a.ns != 0))
+        return false;
+    // fetch epilogues: at least 3 slots of 16 rows per warp set must fit beside the 4-stage operand ring
+    if (epi == PCL_EPI_BWD_Y || epi == PCL_EPI_BWD_GATHER) {
+        const int BN = a.N < ws::MMA_M ? a.N : ws::MMA_M;
+        if (ws::ws_ey_bytes(a.N) / (2 * 16 * BN * 4) < 3) return false;
+    }
+    // gathered epilogue operand: the V term is hoisted per 16-row block
+    if (epi == PCL_EPI_BWD_GATHER && a.V != nullptr && (a.reserved < 4 || a.P % a.ns != 0)) return false;
     if (epi == PCL_EPI_MAXMIN_STATS) {
         if (!(a.ns == 8 || a.ns == 16 || a.ns == 32 || a.ns == 64 || a.ns == 128)) return false;
         if (a.P % a.ns != 0 || a.reserved < 0) return false;

@@ -39,10 +39,11 @@ class PclRowGemm(ctypes.Structure):
                 + [(n, ctypes.c_int) for n in _INT_FIELDS] + [(n, ctypes.c_float) for n in _FLT_FIELDS])
 
 
-# MMA core of the row GEMMs: 2 = tcgen05.mma kind::tf32 + TMEM accumulators, 3xTF32 split (default);
+# MMA core of the row GEMMs: 3 = warp-specialised tcgen05 pipeline (rowgemm_ws.cu) where it covers the
+# shape, else as 2 (default); 2 = tcgen05.mma kind::tf32 + TMEM accumulators, 3xTF32 split;
 # 1 = mma.sync 3xTF32 (fallback / A-B comparison); 0 = mma.sync single-pass TF32 (experiment).
 # pcl_wgrad follows the same switch (tcgen05 when the output fits one 128 x 160 accumulator tile).
-MODE = int(__import__("os").environ.get("PCL_MMA_MODE", "2"))
+MODE = int(__import__("os").environ.get("PCL_MMA_MODE", "3"))
 
 _bound = False
 
@@ -109,9 +110,15 @@ def pack_weight(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
+WS_DBG = 0   # profiling knobs of rowgemm_ws.cu (scratch/ws_branch_knobs.py); 0 in production
+WS_FETCH_EPI = 0   # 1: also route the BWD_Y / BWD_GATHER epilogues to rowgemm_ws.cu (slower today)
+
+
 def rowgemm(pro: int, epi: int, name: str, **kw):
     _bind()
     a, keep = _args(**kw)
+    if pro != PRO_PLAIN2:
+        a.c0 = (WS_DBG << 16) | (WS_FETCH_EPI << 15)
     _lib.call("pcl_rowgemm", ctypes.byref(a), pro, epi, int(MODE), stream(), key=(name, pro, epi, a.P, a.K, a.N))
     return keep
 

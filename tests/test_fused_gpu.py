@@ -55,7 +55,8 @@ def _rel(a, b):
     (4, 512, 64, 0.4, 64, 320, (128, 128, 256)),
     (3, 300, 50, 0.3, 64, 5, (32, 64, 64)),        # ragged: P not a multiple of the 128-row tile
 ])
-@pytest.mark.parametrize("mode", [3, 2, 1, 0])   # tcgen05 warp-specialised | tcgen05 | mma.sync 3xTF32 | mma.sync TF32
+# 4 = 3 + the opt-in fetch epilogues of rowgemm_ws.cu | tcgen05 warp-specialised | tcgen05 | mma.sync 3xTF32 | mma.sync TF32
+@pytest.mark.parametrize("mode", [4, 3, 2, 1, 0])
 def test_fused_sa_branch_matches_reference_sequence(B, N, S, r, ns, C, chans, mode):
     xyz, nrm, _ = modelnet_batch(B, N, seed=N + ns)
     g = torch.Generator().manual_seed(5)
@@ -80,7 +81,8 @@ def test_fused_sa_branch_matches_reference_sequence(B, N, S, r, ns, C, chans, mo
     seq_d = copy.deepcopy(seq).to(DEV)
     fd = feat.to(DEV).requires_grad_(True)
     old = fused.MODE
-    fused.MODE = mode
+    fused.MODE = min(mode, 3)
+    fused.WS_FETCH_EPI = 1 if mode == 4 else 0
     try:
         assert sa.FUSED and fused.supported(ns, list(chans), 3)
         out = sa.sa_branch(grouper, seq_d, new_xyz.to(DEV), xyz.to(DEV), fd)
@@ -88,6 +90,7 @@ def test_fused_sa_branch_matches_reference_sequence(B, N, S, r, ns, C, chans, mo
         torch.cuda.synchronize()
     finally:
         fused.MODE = old
+        fused.WS_FETCH_EPI = 0
     # single-pass TF32 (10-bit mantissa) is an opt-in experiment, not the product default: its
     # gradients are only sanity-bounded here
     ftol, gtol = (1e-3, 2e-3) if mode else (1e-2, 2e-1)

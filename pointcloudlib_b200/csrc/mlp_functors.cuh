@@ -62,6 +62,7 @@ __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0
 // ------------------------------------------------------------------------------------------
 struct ProPlain2 {
     static __device__ __forceinline__ float4 load(const PclRowGemm &a, long long p, int k) {
+        if ((a.c0 & 3) == 0 && k + 3 < a.c0) return ld4(a.x0 + p * a.c0 + k);   // aligned quad inside x0
         float v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {

@@ -243,6 +243,7 @@ int wgrad_tc_dispatch(const PclRowGemm &al, int pl, const PclRowGemm &ar, int pr
     }
 #define PCL_COMBO(L_, R_, PL_, PR_) \
     if (pl == L_ && pr == R_) return wgrad_tc_nb<PL_, PR_>(al, ar, P, M, N, out, ldo, st)
+    PCL_COMBO(PCL_PRO_PLAIN2, PCL_PRO_PLAIN2, ProPlain2, ProPlain2);
     PCL_COMBO(PCL_PRO_BN_ACT, PCL_PRO_BN_ACT_ONES, ProBnAct, ProBnActOnes);
     PCL_COMBO(PCL_PRO_BN_BWD, PCL_PRO_BN_ACT, ProBnBwd, ProBnAct);
     PCL_COMBO(PCL_PRO_BN_BWD, PCL_PRO_GATHER_BN_ACT, ProBnBwd, ProGatherBnAct);

@@ -286,14 +286,23 @@ class FusedSAFn(torch.autograd.Function):
         _lib.call("pcl_gather_bn_backward", ptr(dyh1), ptr(U), ptr(V), ptr(src), ptr(mu1), ptr(rs1),
                   ptr(sc1), ptr(m1_1), ptr(m2_1), P, ns, C1, -1.0, ptr(dU), ptr(dV), stream(),
                   key=("sa_b1_scatter", P, C1))
-        # plain dense GEMMs over the N source points (small): dW1 = dU^T [xyz|feat] + dV^T [cen|0]
-        dW1 = torch.empty((C1, 3 + C), **f32)
-        dW1[:, :3] = dU.t() @ xyz_r + dV.t() @ nxyz_r
+        # dW1 = dU^T [xyz|feat] + dV^T [cen|0] over the B*N source points / G centres, dfeat = dU . W1[:, 3:]
+        if 3 + C <= 160 and C1 <= 128 and C1 % 4 == 0:
+            # narrow outputs over 131k rows: the Gram / weight-gradient kernel (tcgen05, atomics into dW1)
+            dW1 = torch.zeros((C1, 3 + C), **f32)
+            wgrad(PRO_PLAIN2, dict(x0=dU, c0=C1, c1=0, K=C1), PRO_PLAIN2,
+                  dict(x0=xyz_r, x1=feat_r if has_feat else None, c0=3, c1=C if has_feat else 0, K=3 + C),
+                  B * N, C1, 3 + C if has_feat else 3, dW1, name="sa_dw1")
+            wgrad(PRO_PLAIN2, dict(x0=dV, c0=C1, c1=0, K=C1), PRO_PLAIN2, dict(x0=nxyz_r, c0=3, c1=0, K=3),
+                  G, C1, 3, dW1, name="sa_dw1v")
+        else:
+            dW1 = torch.empty((C1, 3 + C), **f32)
+            dW1[:, :3] = dU.t() @ xyz_r + dV.t() @ nxyz_r
+            if has_feat:
+                dW1[:, 3:] = dU.t() @ feat_r
         dfeat = None
-        if has_feat:
-            dW1[:, 3:] = dU.t() @ feat_r
-            if ctx.needs_input_grad[2]:
-                dfeat = (dU @ W1m[:, 3:]).view(B, N, C)
+        if has_feat and ctx.needs_input_grad[2]:
+            dfeat = (dU @ W1m[:, 3:]).view(B, N, C)
 
         s1, s2, s3s = ctx.w_shapes
         return (None, None, dfeat, None, dW1.view(s1), dW2.view(s2), dW3.view(s3s),

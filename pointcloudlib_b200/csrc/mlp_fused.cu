@@ -626,6 +626,9 @@ static int wgrad_l(const PclRowGemm &al, int pl, const PclRowGemm &ar, int pr, l
 
 namespace pcl {
 int rowgemm_tc_dispatch(const PclRowGemm &a, int pro, int epi, cudaStream_t st);  // rowgemm_tc.cu
+bool wgrad_ws_supported(const PclRowGemm &al, int pl, const PclRowGemm &ar, int pr, long long P, int M, int N);
+int wgrad_ws_dispatch(const PclRowGemm &al, int pl, const PclRowGemm &ar, int pr, long long P, int M, int N,
+                      float *out, int ldo, cudaStream_t st);                           // wgrad_ws.cu
 bool rowgemm_ws_supported(const PclRowGemm &a, int pro, int epi);                  // rowgemm_ws.cu
 int rowgemm_ws_dispatch(const PclRowGemm &a, int pro, int epi, cudaStream_t st);
 int wgrad_tc_dispatch(const PclRowGemm &al, int pl, const PclRowGemm &ar, int pr, long long P, int M,
@@ -673,7 +676,10 @@ extern "C" int pcl_wgrad(const PclRowGemm *args_l, int prologue_l, const PclRowG
     if (P == 0) return PCL_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const PclRowGemm al = with_ns_shift(*args_l), ar = with_ns_shift(*args_r);
-    // x3 == 2: tcgen05 core when the output fits one 128 x 160 accumulator tile
+    // x3 == 3: warp-specialised tcgen05 pipeline (wgrad_ws.cu) for the pairs / shapes it covers
+    if (x3 == 3 && wgrad_ws_supported(al, prologue_l, ar, prologue_r, P, M, N))
+        return wgrad_ws_dispatch(al, prologue_l, ar, prologue_r, P, M, N, out, ldo, st);
+    // x3 >= 2: tcgen05 core when the output fits one 128 x 160 accumulator tile
     if (x3 >= 2 && M <= 128 && N <= 160)
         return wgrad_tc_dispatch(al, prologue_l, ar, prologue_r, P, M, N, out, ldo, st);
     return x3 ? wgrad_l<true>(al, prologue_l, ar, prologue_r, P, M, N, out, ldo, st)

@@ -1,0 +1,449 @@
+// wgrad_ws.cu — warp-specialised, software-pipelined weight-gradient / Gram kernel (tcgen05 + TMEM).
+//
+// Same contract as wgrad_tc_kernel (wgrad_tc.cu): OUT (M,N) += sum over rows p of L(p)[m] * R(p)[n],
+// 3xTF32 split, both operands MN-major in the UMMA SWIZZLE_128B_BASE32B layout, M <= 128, N <= 160.
+// wgrad_tc_kernel stages, multiplies and prefetches in sequence inside a CTA (two CTAs per SM); here
+//   * warps 0-7 TRANSFORM: cp.async the raw 16-byte pieces of a 32-row chunk two chunks ahead straight
+//     into the operand slot they will occupy, then apply the prologue math in place (BatchNorm
+//     backward, BatchNorm+ReLU, gather - V), split into TF32 hi / lo, fence.proxy.async, arrive;
+//   * warp 8 MMA: one thread issues the 12 tcgen05.mma of a chunk and commits to the stage-free barrier;
+//   * one persistent CTA per SM reduces a contiguous slice of the rows into one TMEM accumulator and adds
+//     it to OUT with atomics at the end.
+// The L tile holds only ceil(M/32) channel blocks: the tensor core still reads 128 lanes, the lanes
+// >= M see whatever follows in shared memory and land in accumulator rows nobody reads.
+#include "ws_common.cuh"
+
+namespace pcl {
+namespace ws {
+
+// MN-major descriptor for tf32 (cutlass: "for mn-major tf32 operands, SW128_32B is the only available
+// smem layout"): layout type 1, atoms of 4 rows x 128 bytes, 32-byte granules XOR-swizzled by row % 4.
+// LBO = stride between 32-channel blocks, SBO = stride between 4-row groups.
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
+// byte offset of channel quad cq (16 B) of row `row` (0..31) in a [32 rows][32*nblk channels] tile
+__device__ __forceinline__ uint32_t mn_off(int row, int cq) {
+    const int c = cq & 7;
+    return (uint32_t)((cq >> 3) * 4096 + (row >> 2) * 512 + (row & 3) * 128 + ((((c >> 1) ^ (row & 3)) & 3) << 5) +
+                      ((c & 1) << 4));
+}
+
+// ------------------------------------------------------------------------------------------
+// Operand functors of the weight-gradient kernel.  A piece = 4 consecutive channels (k..k+3) of one
+// row.  The per-channel vectors are combined once per CTA into a small shared-memory table (T floats
+// per channel quad), the global pointer of a piece advances by a constant per chunk, and the math of a
+// piece is 2-3 FMAs per element: the transform warps are instruction-issue bound, not memory bound.
+//   table(a, k, t)   float4 #t of the parameter table for channels k..k+3
+//   ptr(a, row, k)   global address of the piece's first (or only) raw 16 bytes (kSrc: row = src[p])
+//   finish(...)      value of the piece given the landed raw data and the table entries
+// ------------------------------------------------------------------------------------------
+struct GBnAct {          // act(scale*x0 + shift)
+    static constexpr bool kSrc = false, kTwo = false, kOnes = false;
+    static constexpr int T = 2;
+    static __device__ __forceinline__ float4 table(const PclRowGemm &a, int k, int t) { return ld4((t == 0 ? a.scale : a.shift) + k); }
+    static __device__ __forceinline__ const float *ptr(const PclRowGemm &a, long long row, int k) { return a.x0 + row * a.K + k; }
+    static __device__ __forceinline__ long long delta(const PclRowGemm &) { return 0; }
+    static __device__ __forceinline__ float4 finish(const PclRowGemm &a, float4 x, float4, const float4 *t, float4) {
+        const WPar2 w = {t[0], t[1]};
+        return bn_act_p(x, w, a.slope);
+    }
+};
+struct GBnActOnes : GBnAct {   // [act(scale*x0 + shift) | 1 | 0 ...]: Gram -> (A^T.A | column sums)
+    static constexpr bool kOnes = true;
+};
+struct GBnBwd {          // bscale*(x0 - m1 - (x1 - mean)*rstd*m2) = A*x0 + B*x1 + C
+    static constexpr bool kSrc = false, kTwo = true, kOnes = false;
+    static constexpr int T = 3;
+    static __device__ __forceinline__ float4 table(const PclRowGemm &a, int k, int t) {
+        const float4 mu = ld4(a.mean + k), rs = ld4(a.rstd + k), bs = ld4(a.bscale + k), m1 = ld4(a.m1 + k), m2 = ld4(a.m2 + k);
+        if (t == 0) return bs;
+        const float4 B = make_float4(-bs.x * rs.x * m2.x, -bs.y * rs.y * m2.y, -bs.z * rs.z * m2.z, -bs.w * rs.w * m2.w);
+        if (t == 1) return B;
+        return make_float4(-fmaf(B.x, mu.x, bs.x * m1.x), -fmaf(B.y, mu.y, bs.y * m1.y), -fmaf(B.z, mu.z, bs.z * m1.z),
+                           -fmaf(B.w, mu.w, bs.w * m1.w));
+    }
+    static __device__ __forceinline__ const float *ptr(const PclRowGemm &a, long long row, int k) { return a.x0 + row * a.K + k; }
+    static __device__ __forceinline__ long long delta(const PclRowGemm &a) { return a.x1 - a.x0; }
+    static __device__ __forceinline__ float4 finish(const PclRowGemm &, float4 d, float4 y, const float4 *t, float4) {
+        return make_float4(fmaf(t[0].x, d.x, fmaf(t[1].x, y.x, t[2].x)), fmaf(t[0].y, d.y, fmaf(t[1].y, y.y, t[2].y)),
+                           fmaf(t[0].z, d.z, fmaf(t[1].z, y.z, t[2].z)), fmaf(t[0].w, d.w, fmaf(t[1].w, y.w, t[2].w)));
+    }
+};
+struct GGatherBnAct {    // act(scale*(U[src[p]] + vsign*V[p/ns]) + shift)
+    static constexpr bool kSrc = true, kTwo = false, kOnes = false;
+    static constexpr int T = 2;
+    static __device__ __forceinline__ float4 table(const PclRowGemm &a, int k, int t) { return ld4((t == 0 ? a.scale : a.shift) + k); }
+    static __device__ __forceinline__ const float *ptr(const PclRowGemm &a, long long row, int k) { return a.U + row * a.K + k; }
+    static __device__ __forceinline__ long long delta(const PclRowGemm &) { return 0; }
+    static __device__ __forceinline__ float4 finish(const PclRowGemm &a, float4 u, float4, const float4 *t, float4 v) {
+        const WPar2 w = {t[0], t[1]};
+        u = make_float4(fmaf(a.vsign, v.x, u.x), fmaf(a.vsign, v.y, u.y), fmaf(a.vsign, v.z, u.z), fmaf(a.vsign, v.w, u.w));
+        return bn_act_p(u, w, a.slope);
+    }
+};
+
+constexpr int kWgThreads = 9 * 32;
+constexpr int WG_ROWS = 32;     // rows per chunk = MMA K of 4 x 8
+constexpr int WG_BLK = 4096;    // bytes of one 32-channel block of a tile (hi or lo)
+constexpr int NPL = 4, NPR = 5; // max 16-byte pieces per thread and chunk: L (128 ch), R (160 ch)
+constexpr int kTabQuads = 40;
+constexpr int kSlackBytes = 4 * WG_BLK * 2 + 1024;   // the 128-lane operand read past the last staged block
+constexpr int kSrcBytes = 7 * NPR * 256 * 4;         // gather-index slots: up to PD + 1 = 5 chunks (+ spare)   // channel quads covered by a parameter table (160 channels)
+
+// one operand (L or R) of the transform: piece bookkeeping of this thread
+template <int NP, class Pro>
+struct Operand {
+    uint32_t off[NP];        // byte offset of the piece in the hi tile (relative to the stage)
+    const float *gp[NP];     // global pointer of the piece's raw data for the next chunk to ISSUE
+    int row[NP], kq[NP];     // row inside the chunk, channel quad
+    int n_live;              // pieces i < n_live are live (the rest are pre-written constants)
+};
+
+// SHARE: the Gram case L = R[:, :M] (same rows, same prologue): the L operand descriptors point into the
+// R tile (lanes >= M pick up the ones column / zeros / the lo tile and land in accumulator rows nobody
+// reads), so one copy of the data is loaded, transformed and staged.
+template <int S, int LAG, bool SHARE, class ProL, class ProR>
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_ws_kernel(const PclRowGemm al, const PclRowGemm ar, long long P, int M, int N, float *__restrict__ out, int ldo) {
+    constexpr int PD = S - LAG;   // chunks in flight ahead of the transform
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    __shared__ __align__(8) uint64_t s_full[S], s_free[S], s_done;
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(16) float4 s_tabL[3][kTabQuads], s_tabR[3][kTabQuads];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Npad = (N + 15) & ~15;
+    const int MB = (M + 31) / 32, NB = (Npad + 31) / 32;
+    const uint32_t l_tile = SHARE ? 0u : MB * WG_BLK, r_tile = NB * WG_BLK;
+    const uint32_t stage_bytes = 2 * (l_tile + r_tile);   // [L hi | L lo | R hi | R lo]
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"(256u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(smem_u32(&s_full[s]), 8);
+            mbar_init(smem_u32(&s_free[s]), 1);
+        }
+        mbar_init(smem_u32(&s_done), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // parameter tables (channels past the operand width read as 0)
+    for (int e = tid; e < 3 * kTabQuads; e += kWgThreads) {
+        const int t = e / kTabQuads, qd = e % kTabQuads;
+        s_tabL[t][qd] = (t < ProL::T && qd * 4 < M) ? ProL::table(al, qd * 4, t) : f4zero();
+        s_tabR[t][qd] = (t < ProR::T && qd * 4 < ar.K) ? ProR::table(ar, qd * 4, t) : f4zero();
+    }
+    // constant pieces, written once per stage: zeros for channel quads past the operand width, and the
+    // ones column of the Gram operand.  (The live pieces never touch these slots.)
+    {
+        const int qL = SHARE ? 0 : 8 * MB, qR = 8 * NB;
+        for (int e = tid; e < S * WG_ROWS * (qL + qR); e += kWgThreads) {
+            const int s = e / (WG_ROWS * (qL + qR)), r = e % (WG_ROWS * (qL + qR));
+            const bool isR = r >= WG_ROWS * qL;
+            const int rr = isR ? r - WG_ROWS * qL : r;
+            const int qd = rr % (isR ? qR : qL), row = rr / (isR ? qR : qL);
+            const int width = isR ? ar.K : M;
+            if (qd * 4 >= width) {
+                const uint32_t o = sbase + s * stage_bytes + (isR ? 2 * l_tile : 0) + mn_off(row, qd);
+                const bool one = isR && ProR::kOnes && qd * 4 == ar.K;
+                sts4(o, one ? 0x3F800000u : 0u, 0u, 0u, 0u);
+                sts4(o + (isR ? r_tile : l_tile), 0u, 0u, 0u, 0u);
+            }
+        }
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const int dbg = al.c0 >> 16;   // profiling knobs: 1 no MMA, 4 no loads, 16 no transform math
+
+    const long long n_chunks = (P + WG_ROWS - 1) / WG_ROWS;
+    const long long per = (n_chunks + gridDim.x - 1) / gridDim.x;
+    const long long c_begin = blockIdx.x * per;
+    const long long c_end = n_chunks < c_begin + per ? n_chunks : c_begin + per;
+    const int total = c_end > c_begin ? (int)(c_end - c_begin) : 0;
+
+    if (warp < 8) {
+        // ============================ TRANSFORM warps ============================
+        Operand<NPL, ProL> L;
+        Operand<NPR, ProR> R;
+        const int qL = 8 * MB, qR = 8 * NB;
+        const int liveL = (M + 3) / 4, liveR = (ar.K + 3) / 4;   // live quads per row
+        // live pieces are enumerated over [32 rows][live quads]
+        L.n_live = 0;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+            const int e = tid + 256 * i;
+            L.row[i] = e / liveL;
+            L.kq[i] = e % liveL;
+            L.off[i] = mn_off(L.row[i] & 31, L.kq[i]);
+            L.gp[i] = ProL::kSrc ? nullptr : ProL::ptr(al, c_begin * WG_ROWS + L.row[i], L.kq[i] * 4);
+            if (e < WG_ROWS * liveL && !SHARE) L.n_live = i + 1;
+        }
+        R.n_live = 0;
+#pragma unroll
+        for (int i = 0; i < NPR; ++i) {
+            const int e = tid + 256 * i;
+            R.row[i] = e / liveR;
+            R.kq[i] = e % liveR;
+            R.off[i] = 2 * l_tile + mn_off(R.row[i] & 31, R.kq[i]);
+            R.gp[i] = ProR::kSrc ? nullptr : ProR::ptr(ar, c_begin * WG_ROWS + R.row[i], R.kq[i] * 4);
+            if (e < WG_ROWS * liveR) R.n_live = i + 1;
+        }
+        (void)qL; (void)qR;
+        const long long stepL = (long long)WG_ROWS * al.K, stepR = (long long)WG_ROWS * ar.K;
+        const long long dL = ProL::delta(al), dR = ProR::delta(ar);
+        // gathered R operand: the src index of each live piece's row travels through shared memory: the
+        // issue of chunk k also cp.asyncs (4 bytes, private slot per thread) the indices chunk k + PD will
+        // need, so they arrive with a whole pipeline depth of lead time instead of a dependent register load
+        static_assert(!ProL::kSrc, "gathered L operands are not implemented");
+        const uint32_t src_base = sbase + S * stage_bytes + kSlackBytes;   // [PD + 1][NPR][256] ints
+        auto src_slot = [&](int k, int i) { return src_base + (uint32_t)((((k % (PD + 1)) * NPR + i) * 256 + tid) * 4); };
+        int i_c = 0;
+        auto issue_next = [&]() {
+            if (i_c < total) {
+                const uint32_t st = sbase + (i_c % S) * stage_bytes;
+                const long long c = c_begin + i_c;
+                const long long left = P - c * WG_ROWS;
+                const int rows_valid = left < WG_ROWS ? (int)left : WG_ROWS;
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) {
+                    if (i < L.n_live && !(dbg & 4)) {
+                        const bool ok = L.row[i] < rows_valid;
+                        const float *g = L.gp[i];
+                        cp_async16_zfill(st + L.off[i], ok ? g : al.scale, ok);
+                        if (ProL::kTwo) cp_async16_zfill(st + l_tile + L.off[i], ok ? g + dL : al.scale, ok);
+                        if (!ProL::kSrc) L.gp[i] += stepL;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NPR; ++i) {
+                    if (i < R.n_live && !(dbg & 4)) {
+                        const bool ok = R.row[i] < rows_valid;
+                        const float *g = R.gp[i];
+                        if (ProR::kSrc) {
+                            int sidx;
+                            if (i_c < PD) {
+                                sidx = ok ? __ldg(ar.src + c * WG_ROWS + R.row[i]) : 0;
+                            } else {
+                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(sidx) : "r"(src_slot(i_c, i)));
+                            }
+                            g = ProR::ptr(ar, sidx, R.kq[i] * 4);
+                            const long long pn = (c + PD) * WG_ROWS + R.row[i];   // indices for chunk i_c + PD
+                            const bool okn = i_c + PD < total && pn < P;
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(src_slot(i_c + PD, i)),
+                                         "l"(ar.src + (okn ? pn : 0)), "r"(okn ? 4 : 0));
+                        }
+                        cp_async16_zfill(st + R.off[i], ok ? g : ar.scale, ok);
+                        if (ProR::kTwo) cp_async16_zfill(st + r_tile + R.off[i], ok ? g + dR : ar.scale, ok);
+                        if (!ProR::kSrc) R.gp[i] += stepR;
+                    }
+                }
+                ++i_c;
+            }
+            cp_async_commit();
+        };
+        for (int j = 0; j < PD; ++j) issue_next();
+
+        for (int cc = 0; cc < total; ++cc) {
+            const uint32_t st = sbase + (cc % S) * stage_bytes;
+            const long long c = c_begin + cc;
+            const long long left = P - c * WG_ROWS;
+            const int rows_valid = left < WG_ROWS ? (int)left : WG_ROWS;
+            cp_async_wait<PD - 1>();
+            // pass 1: all raw pieces, table entries and V rows in flight together; pass 2: math, split, stores
+            float4 l0[NPL], l1[NPL], lv[NPL], r0[NPR], r1[NPR], rv[NPR];
+            const int nl = (dbg & 16) ? 0 : L.n_live, nr = (dbg & 16) ? 0 : R.n_live;
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) {
+                l0[i] = l1[i] = lv[i] = f4zero();
+                if (i < nl) {
+                    const uint32_t o = st + L.off[i];
+                    l0[i] = lds4(o);
+                    if (ProL::kTwo) l1[i] = lds4(o + l_tile);
+                    if (ProL::kSrc && al.V != nullptr && L.row[i] < rows_valid)
+                        lv[i] = ld4(al.V + group_of(al, c * WG_ROWS + L.row[i]) * al.K + L.kq[i] * 4);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NPR; ++i) {
+                r0[i] = r1[i] = rv[i] = f4zero();
+                if (i < nr) {
+                    const uint32_t o = st + R.off[i];
+                    r0[i] = lds4(o);
+                    if (ProR::kTwo) r1[i] = lds4(o + r_tile);
+                    if (ProR::kSrc && ar.V != nullptr && R.row[i] < rows_valid)
+                        rv[i] = ld4(ar.V + group_of(ar, c * WG_ROWS + R.row[i]) * ar.K + R.kq[i] * 4);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) {
+                if (i < nl) {
+                    const uint32_t o = st + L.off[i];
+                    const float4 t[3] = {s_tabL[0][L.kq[i]], s_tabL[1][L.kq[i]], s_tabL[2][L.kq[i]]};
+                    float4 v = ProL::finish(al, l0[i], l1[i], t, lv[i]);
+                    if (L.row[i] >= rows_valid) v = f4zero();   // rows past P contribute nothing
+                    const float x[4] = {v.x, v.y, v.z, v.w};
+                    uint32_t hi[4], lo[4];
+                    split_tf32_trunc<4>(x, hi, lo);
+                    sts4(o, hi[0], hi[1], hi[2], hi[3]);
+                    sts4(o + l_tile, lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NPR; ++i) {
+                if (i < nr) {
+                    const uint32_t o = st + R.off[i];
+                    const float4 t[3] = {s_tabR[0][R.kq[i]], s_tabR[1][R.kq[i]], s_tabR[2][R.kq[i]]};
+                    float4 v = ProR::finish(ar, r0[i], r1[i], t, rv[i]);
+                    if (R.row[i] >= rows_valid) v = f4zero();
+                    const float x[4] = {v.x, v.y, v.z, v.w};
+                    uint32_t hi[4], lo[4];
+                    split_tf32_trunc<4>(x, hi, lo);
+                    sts4(o, hi[0], hi[1], hi[2], hi[3]);
+                    sts4(o + r_tile, lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+            if (ProR::kOnes && rows_valid < WG_ROWS) {
+                // ragged last chunk: the pre-written ones column must be 0 for the rows past P
+                const int qd = ar.K / 4;
+                if (tid < WG_ROWS && tid >= rows_valid) sts4(st + 2 * l_tile + mn_off(tid, qd), 0u, 0u, 0u, 0u);
+            }
+            if (!(dbg & 32)) fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && !(dbg & 64)) mbar_arrive(smem_u32(&s_full[cc % S]));
+            if (cc >= LAG && i_c < total && !(dbg & 64))
+                mbar_wait(smem_u32(&s_free[(cc - LAG) % S]), (uint32_t)(((cc - LAG) / S) & 1));
+            issue_next();
+        }
+        cp_async_wait<0>();
+        // ---- epilogue: TMEM accumulator -> atomics on OUT ----
+        if (total > 0 && !(dbg & 128)) {
+            mbar_wait(smem_u32(&s_done), 0);
+            tc_fence_after();
+            const int q = warp & 3, h = warp >> 2;
+            const int m = q * 32 + lane;
+            for (int c0 = h * 16; c0 < Npad; c0 += 32) {
+                float v[16];
+                tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                if (m < M) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < N) atomicAdd(out + (long long)m * ldo + c0 + j, v[j]);
+                }
+            }
+        }
+    } else if (lane == 0) {
+        // ============================ MMA issuer ============================
+        // instruction descriptor: D=F32, A=B=TF32, both MN-major (bits 15,16), N>>3, M=128>>4
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(Npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        for (int cc = 0; cc < total; ++cc) {
+            const int s = cc % S;
+            if (!(dbg & 64)) mbar_wait_spin(smem_u32(&s_full[s]), (uint32_t)((cc / S) & 1));
+            tc_fence_after();
+            const uint32_t st = sbase + s * stage_bytes;
+#pragma unroll
+            for (int kg = 0; kg < 4; ++kg) {
+                if (dbg & 1) break;
+                const uint32_t o = kg * 1024;   // 8 rows = two 4-row groups of 512 B
+                const uint64_t dRhi = umma_desc_mn(st + 2 * l_tile + o, WG_BLK, 512);
+                const uint64_t dRlo = umma_desc_mn(st + 2 * l_tile + r_tile + o, WG_BLK, 512);
+                const uint64_t dLhi = SHARE ? dRhi : umma_desc_mn(st + o, WG_BLK, 512);
+                const uint64_t dLlo = SHARE ? dRlo : umma_desc_mn(st + l_tile + o, WG_BLK, 512);
+                tc_mma_tf32(tmem, dLlo, dRhi, idesc, (cc > 0 || kg > 0) ? 1u : 0u);
+                tc_mma_tf32(tmem, dLhi, dRlo, idesc, 1u);
+                tc_mma_tf32(tmem, dLhi, dRhi, idesc, 1u);
+            }
+            if (!(dbg & 256)) tc_commit(smem_u32(&s_free[s]));
+        }
+        if (total > 0) tc_commit(smem_u32(&s_done));
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+}
+
+static void wgrad_ws_geometry(int M, int N, bool share, size_t &stage, size_t &slack, int &S) {
+    const int Npad = (N + 15) & ~15;
+    const int MB = share ? 0 : (M + 31) / 32, NB = (Npad + 31) / 32;
+    stage = (size_t)2 * (MB + NB) * WG_BLK;
+    slack = (size_t)kSlackBytes + kSrcBytes;   // operand over-read + the gather-index slots
+    const size_t budget = 232448 - 4096 - 1024 - slack;   // static: barriers + parameter tables
+    S = stage * 6 <= budget ? 6 : (stage * 4 <= budget ? 4 : (stage * 3 <= budget ? 3 : 0));
+}
+
+template <bool SHARE, class ProL, class ProR>
+static int launch_wgrad_ws(const PclRowGemm &al, const PclRowGemm &ar, long long P, int M, int N, float *out,
+                           int ldo, cudaStream_t st) {
+    size_t stage, slack;
+    int S;
+    wgrad_ws_geometry(M, N, SHARE, stage, slack, S);
+    if (S == 0) {
+        set_error("pcl_wgrad(ws): M=%d N=%d does not fit three stages", M, N);
+        return PCL_ERR_UNSUPPORTED;
+    }
+    const size_t smem = 1024 + S * stage + slack;
+    const long long n_chunks = (P + WG_ROWS - 1) / WG_ROWS;
+    const long long grid = n_chunks < kNumSMs ? n_chunks : kNumSMs;
+    cudaError_t e = cudaSuccess;
+#define PCL_LAUNCH(S_, LAG_)                                                                      \
+    do {                                                                                          \
+        auto kern = wgrad_ws_kernel<S_, LAG_, SHARE, ProL, ProR>;                                 \
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+        if (e == cudaSuccess) kern<<<(unsigned)grid, kWgThreads, smem, st>>>(al, ar, P, M, N, out, ldo); \
+    } while (0)
+    if (S == 6) PCL_LAUNCH(6, 2);
+    else if (S == 4) PCL_LAUNCH(4, 2);
+    else PCL_LAUNCH(3, 1);
+#undef PCL_LAUNCH
+    if (e != cudaSuccess) {
+        set_error("pcl_wgrad(ws): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    return check_launch("pcl_wgrad(ws)");
+}
+
+// Gram with both operands built from the same rows by the same BatchNorm+activation
+static bool gram_shares(const PclRowGemm &al, int pl, const PclRowGemm &ar, int pr, int M) {
+    return pl == PCL_PRO_BN_ACT && pr == PCL_PRO_BN_ACT_ONES && al.x0 == ar.x0 && al.scale == ar.scale &&
+           al.shift == ar.shift && al.slope == ar.slope && al.K == ar.K && M == ar.K;
+}
+
+}  // namespace ws
+
+bool wgrad_ws_supported(const PclRowGemm &al, int pl, const PclRowGemm &ar, int pr, long long P, int M, int N) {
+    const bool combo = (pl == PCL_PRO_BN_ACT && pr == PCL_PRO_BN_ACT_ONES) ||
+                       (pl == PCL_PRO_BN_BWD && pr == PCL_PRO_BN_ACT) ||
+                       (pl == PCL_PRO_BN_BWD && pr == PCL_PRO_GATHER_BN_ACT);
+    if (!combo || M > 128 || N > 160 || M % 4 != 0 || P < 1) return false;
+    if (al.K % 4 != 0 || ar.K % 4 != 0 || al.K < M) return false;
+    size_t stage, slack;
+    int S;
+    ws::wgrad_ws_geometry(M, N, ws::gram_shares(al, pl, ar, pr, M), stage, slack, S);
+    return S != 0;
+}
+
+int wgrad_ws_dispatch(const PclRowGemm &al, int pl, const PclRowGemm &ar, int pr, long long P, int M, int N,
+                      float *out, int ldo, cudaStream_t st) {
+    using namespace ws;
+#define PCL_WS(L_, R_, PL_, PR_) \
+    if (pl == L_ && pr == R_) return launch_wgrad_ws<false, PL_, PR_>(al, ar, P, M, N, out, ldo, st)
+    if (gram_shares(al, pl, ar, pr, M)) return launch_wgrad_ws<true, GBnAct, GBnActOnes>(al, ar, P, M, N, out, ldo, st);
+    PCL_WS(PCL_PRO_BN_ACT, PCL_PRO_BN_ACT_ONES, GBnAct, GBnActOnes);
+    PCL_WS(PCL_PRO_BN_BWD, PCL_PRO_BN_ACT, GBnBwd, GBnAct);
+    PCL_WS(PCL_PRO_BN_BWD, PCL_PRO_GATHER_BN_ACT, GBnBwd, GGatherBnAct);
+#undef PCL_WS
+    set_error("pcl_wgrad(ws): unsupported (L prologue %d, R prologue %d) pair", pl, pr);
+    return PCL_ERR_UNSUPPORTED;
+}
+
+}  // namespace pcl

@@ -127,6 +127,8 @@ def wgrad(pro_l, kw_l, pro_r, kw_r, P, M, N, out, name="wgrad"):
     _bind()
     al, k1 = _args(**kw_l)
     ar, k2 = _args(**kw_r)
+    if WS_DBG and pro_l != PRO_PLAIN2:
+        al.c0 = WS_DBG << 16
     _lib.call("pcl_wgrad", ctypes.byref(al), pro_l, ctypes.byref(ar), pro_r, P, M, N, ptr(out),
               out.stride(0), int(MODE), stream(), key=(name, P, M, N))
 

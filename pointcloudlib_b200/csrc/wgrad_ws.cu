@@ -89,7 +89,7 @@ constexpr int WG_ROWS = 32;     // rows per chunk = MMA K of 4 x 8
 constexpr int WG_BLK = 4096;    // bytes of one 32-channel block of a tile (hi or lo)
 constexpr int NPL = 4, NPR = 5; // max 16-byte pieces per thread and chunk: L (128 ch), R (160 ch)
 constexpr int kTabQuads = 40;
-constexpr int kSlackBytes = 4 * WG_BLK * 2 + 1024;   // the 128-lane operand read past the last staged block
+constexpr int kSlackBytes = 2 * WG_BLK + 1024;       // the 128-lane operand read past the last staged block
 constexpr int kSrcBytes = 7 * NPR * 256 * 4;         // gather-index slots: up to PD + 1 = 5 chunks (+ spare)   // channel quads covered by a parameter table (160 channels)
 
 // one operand (L or R) of the transform: piece bookkeeping of this thread
@@ -372,11 +372,11 @@ wgrad_ws_kernel(const PclRowGemm al, const PclRowGemm ar, long long P, int M, in
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
 }
 
-static void wgrad_ws_geometry(int M, int N, bool share, size_t &stage, size_t &slack, int &S) {
+static void wgrad_ws_geometry(int M, int N, bool share, bool gather, size_t &stage, size_t &slack, int &S) {
     const int Npad = (N + 15) & ~15;
     const int MB = share ? 0 : (M + 31) / 32, NB = (Npad + 31) / 32;
     stage = (size_t)2 * (MB + NB) * WG_BLK;
-    slack = (size_t)kSlackBytes + kSrcBytes;   // operand over-read + the gather-index slots
+    slack = (size_t)kSlackBytes + (gather ? kSrcBytes : 0);   // operand over-read + the gather-index slots
     const size_t budget = 232448 - 4096 - 1024 - slack;   // static: barriers + parameter tables
     S = stage * 6 <= budget ? 6 : (stage * 4 <= budget ? 4 : (stage * 3 <= budget ? 3 : 0));
 }
@@ -386,7 +386,7 @@ static int launch_wgrad_ws(const PclRowGemm &al, const PclRowGemm &ar, long long
                            int ldo, cudaStream_t st) {
     size_t stage, slack;
     int S;
-    wgrad_ws_geometry(M, N, SHARE, stage, slack, S);
+    wgrad_ws_geometry(M, N, SHARE, ProR::kSrc, stage, slack, S);
     if (S == 0) {
         set_error("pcl_wgrad(ws): M=%d N=%d does not fit three stages", M, N);
         return PCL_ERR_UNSUPPORTED;
@@ -428,7 +428,7 @@ bool wgrad_ws_supported(const PclRowGemm &al, int pl, const PclRowGemm &ar, int 
     if (al.K % 4 != 0 || ar.K % 4 != 0 || al.K < M) return false;
     size_t stage, slack;
     int S;
-    ws::wgrad_ws_geometry(M, N, ws::gram_shares(al, pl, ar, pr, M), stage, slack, S);
+    ws::wgrad_ws_geometry(M, N, ws::gram_shares(al, pl, ar, pr, M), pr == PCL_PRO_GATHER_BN_ACT, stage, slack, S);
     return S != 0;
 }
 

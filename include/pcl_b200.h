@@ -153,6 +153,10 @@ int pcl_compute_density(const float *xyz, int B, int N, float bandwidth, float *
  *     PCL_EPI_BWD_Y        v = (acc+ebias)*act'(escale*ey+eshift); out = v;
  *                          stats += (sum v, sum v*(ey-emean)*erstd)
  *     PCL_EPI_BWD_GATHER   same with ey := U[src[p]] + vsign*V[p/ns]
+ *     PCL_EPI_BWD_Y_ROUTED PCL_EPI_BWD_Y after adding the routed max-gradient term in fp32:
+ *                          acc[g*ns + selpos[g,k], :] += g3s[g,k] * x1[k, :], x1 = (C3, N) row-major
+ *                          (the sparse form of PCL_PRO_G3_A2's one-hot block; tcgen05 cores only,
+ *                          ns a power of two <= 128, P % ns == 0)
  */
 typedef struct PclRowGemm {
     const float *W, *x0, *x1, *U, *V, *scale, *shift, *mean, *rstd, *bscale, *m1, *m2, *g3s;
@@ -168,7 +172,7 @@ typedef struct PclRowGemm {
 enum { PCL_PRO_PLAIN2 = 0, PCL_PRO_BN_ACT = 1, PCL_PRO_GATHER_BN_ACT = 2, PCL_PRO_BN_BWD = 3,
        PCL_PRO_G3_A2 = 4, PCL_PRO_BN_ACT_ONES = 5 /* pcl_wgrad only: [act(bn(x0)) | 1] */ };
 enum { PCL_EPI_STORE = 0, PCL_EPI_STORE_STATS = 1, PCL_EPI_MAXMIN_STATS = 2, PCL_EPI_BWD_Y = 3,
-       PCL_EPI_BWD_GATHER = 4 };
+       PCL_EPI_BWD_GATHER = 4, PCL_EPI_BWD_Y_ROUTED = 5 };
 int pcl_rowgemm(const PclRowGemm *args, int prologue, int epilogue, int x3, void *stream);
 
 /* pcl_wgrad: OUT (M,N) += sum over rows p of L(p)[m] * R(p)[n]  (weight gradients, Gram

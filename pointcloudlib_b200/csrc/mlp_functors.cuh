@@ -148,7 +148,7 @@ struct ProG3A2 {
 // ------------------------------------------------------------------------------------------
 struct EpiNoParams {};
 struct EpiStore {
-    static constexpr bool kStore = true, kStats = false, kMaxMin = false;
+    static constexpr bool kStore = true, kStats = false, kMaxMin = false, kRouted = false;
     using Params = EpiNoParams;
     static __device__ __forceinline__ Params load_params(const PclRowGemm &, int) { return {}; }
     static __device__ __forceinline__ void rowpass(const PclRowGemm &, const Params &, float4 &, float4 &, long long, int) {}
@@ -156,7 +156,7 @@ struct EpiStore {
     static __device__ __forceinline__ void apply(const PclRowGemm &, const Params &, float4 &, float4 &, float4) {}
 };
 struct EpiStoreStats {
-    static constexpr bool kStore = true, kStats = true, kMaxMin = false;
+    static constexpr bool kStore = true, kStats = true, kMaxMin = false, kRouted = false;
     using Params = EpiNoParams;
     static __device__ __forceinline__ Params load_params(const PclRowGemm &, int) { return {}; }
     static __device__ __forceinline__ void rowpass(const PclRowGemm &, const Params &, float4 &v, float4 &q, long long, int) {
@@ -168,7 +168,7 @@ struct EpiStoreStats {
     }
 };
 struct EpiMaxMinStats {
-    static constexpr bool kStore = false, kStats = true, kMaxMin = true;
+    static constexpr bool kStore = false, kStats = true, kMaxMin = true, kRouted = false;
     using Params = EpiNoParams;
     static __device__ __forceinline__ Params load_params(const PclRowGemm &, int) { return {}; }
     static __device__ __forceinline__ void rowpass(const PclRowGemm &, const Params &, float4 &v, float4 &q, long long, int) {
@@ -202,7 +202,7 @@ __device__ __forceinline__ void bwd_act4(const PclRowGemm &a, const EpiBwdParams
                     v.z * (y.z - e.mu.z) * e.rs.z, v.w * (y.w - e.mu.w) * e.rs.w);
 }
 struct EpiBwdY {
-    static constexpr bool kStore = true, kStats = true, kMaxMin = false;
+    static constexpr bool kStore = true, kStats = true, kMaxMin = false, kRouted = false;
     using Params = EpiBwdParams;
     static __device__ __forceinline__ Params load_params(const PclRowGemm &a, int n) { return load_bwd_params(a, n); }
     static __device__ __forceinline__ void rowpass(const PclRowGemm &a, const Params &e, float4 &v, float4 &q, long long p, int n) {
@@ -211,8 +211,15 @@ struct EpiBwdY {
     static __device__ __forceinline__ float4 fetch(const PclRowGemm &a, long long p, int n) { return ld4(a.ey + p * a.N + n); }
     static __device__ __forceinline__ void apply(const PclRowGemm &a, const Params &e, float4 &v, float4 &q, float4 y) { bwd_act4(a, e, v, q, y); }
 };
+// EpiBwdY preceded by the ROUTED (sparse) term of the last-layer backward: before the row pass,
+// acc[g*ns + selpos[g,k], :] += g3s[g,k] * x1[k, :] for every (group g, channel k < C3) of the tile
+// (x1 = W3 (C3, N) row-major).  Replaces the dense one-hot block [G3s | a2] of PCL_PRO_G3_A2:
+// K = C2 instead of C3 + C2, and the routed term is exact fp32.  tcgen05 kernels only.
+struct EpiBwdYRouted : EpiBwdY {
+    static constexpr bool kRouted = true;
+};
 struct EpiBwdGather {
-    static constexpr bool kStore = true, kStats = true, kMaxMin = false;
+    static constexpr bool kStore = true, kStats = true, kMaxMin = false, kRouted = false;
     using Params = EpiBwdParams;
     static __device__ __forceinline__ Params load_params(const PclRowGemm &a, int n) { return load_bwd_params(a, n); }
     static __device__ __forceinline__ void rowpass(const PclRowGemm &a, const Params &e, float4 &v, float4 &q, long long p, int n) {

@@ -253,6 +253,53 @@ __global__ void __launch_bounds__(256, 2) rowgemm_tc_kernel(const PclRowGemm a) 
                 }
                 tc_fence_before();
                 __syncthreads();
+                if (Epi::kRouted) {
+                    // routed (sparse) term: one warp per (group, channel k) entry of this row tile, lanes
+                    // over the output columns; entries of one row may collide -> shared-memory atomics
+                    const int sh = a.reserved, gpt = BMt >> sh;   // groups per row tile (ns | 128)
+                    const long long g0 = p0 >> sh;
+                    const int n_ent = gpt * a.C3;
+                    constexpr int NW4 = (BN + 31) / 32;           // output columns per lane
+                    for (int base = warp * 32; base < n_ent; base += 256) {
+                        // 32 entries per warp at a time: their (value, row) loads are coalesced and in
+                        // flight together; the non-zero ones are then applied one by one, the W3 row of
+                        // the next entry prefetched while the current one is added
+                        const int e = base + lane;
+                        float val = 0.f;
+                        int row = 0, k = 0;
+                        if (e < n_ent) {
+                            const int gl = e / a.C3;
+                            k = e - gl * a.C3;
+                            const long long g = g0 + gl;
+                            if ((g << sh) < a.P) {
+                                val = __ldg(a.g3s + g * a.C3 + k);
+                                row = (gl << sh) + __ldg(a.selpos + g * a.C3 + k);
+                            }
+                        }
+                        unsigned nz = __ballot_sync(0xffffffffu, val != 0.f);
+                        float wn[NW4];
+                        auto load_w = [&](int j, float (&w)[NW4]) {
+                            const float *wr = a.x1 + (long long)__shfl_sync(0xffffffffu, k, j) * a.N + n0;
+#pragma unroll
+                            for (int i = 0; i < NW4; ++i) w[i] = (lane + 32 * i < BN) ? __ldg(wr + lane + 32 * i) : 0.f;
+                        };
+                        if (nz) load_w(__ffs(nz) - 1, wn);
+                        while (nz) {
+                            const int j = __ffs(nz) - 1;
+                            nz &= nz - 1;
+                            float wc[NW4];
+#pragma unroll
+                            for (int i = 0; i < NW4; ++i) wc[i] = wn[i];
+                            if (nz) load_w(__ffs(nz) - 1, wn);
+                            const float v = __shfl_sync(0xffffffffu, val, j);
+                            float *tr = T + __shfl_sync(0xffffffffu, row, j) * LDT;
+#pragma unroll
+                            for (int i = 0; i < NW4; ++i)
+                                if (lane + 32 * i < BN) atomicAdd(tr + lane + 32 * i, v * wc[i]);
+                        }
+                    }
+                    __syncthreads();
+                }
                 if (!Epi::kMaxMin && e_active) {
                     float4 s = f4zero(), q2 = f4zero();
                     const typename Epi::Params epar = Epi::load_params(a, n0 + e_q * 4);
@@ -437,6 +484,7 @@ int rowgemm_tc_dispatch(const PclRowGemm &a, int pro, int epi, cudaStream_t st) 
     PCL_COMBO(PCL_PRO_PLAIN2, PCL_EPI_STORE_STATS, ProPlain2, EpiStoreStats);
     PCL_COMBO(PCL_PRO_BN_ACT, PCL_EPI_STORE_STATS, ProBnAct, EpiStoreStats);
     PCL_COMBO(PCL_PRO_BN_ACT, PCL_EPI_MAXMIN_STATS, ProBnAct, EpiMaxMinStats);
+    PCL_COMBO(PCL_PRO_BN_ACT, PCL_EPI_BWD_Y_ROUTED, ProBnAct, EpiBwdYRouted);
     PCL_COMBO(PCL_PRO_GATHER_BN_ACT, PCL_EPI_STORE_STATS, ProGatherBnAct, EpiStoreStats);
     PCL_COMBO(PCL_PRO_GATHER_BN_ACT, PCL_EPI_MAXMIN_STATS, ProGatherBnAct, EpiMaxMinStats);
     PCL_COMBO(PCL_PRO_BN_BWD, PCL_EPI_STORE, ProBnBwd, EpiStore);

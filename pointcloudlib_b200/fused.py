@@ -24,7 +24,7 @@ from . import _lib
 from ._lib import lib, ptr, stream
 
 PRO_PLAIN2, PRO_BN_ACT, PRO_GATHER_BN_ACT, PRO_BN_BWD, PRO_G3_A2, PRO_BN_ACT_ONES = range(6)
-EPI_STORE, EPI_STORE_STATS, EPI_MAXMIN_STATS, EPI_BWD_Y, EPI_BWD_GATHER = range(5)
+EPI_STORE, EPI_STORE_STATS, EPI_MAXMIN_STATS, EPI_BWD_Y, EPI_BWD_GATHER, EPI_BWD_Y_ROUTED = range(6)
 
 _PTR_FIELDS = ("W", "x0", "x1", "U", "V", "scale", "shift", "mean", "rstd", "bscale", "m1", "m2",
                "g3s", "src", "selpos", "out", "gmax", "gmin", "amax", "amin", "stats", "ebias",
@@ -244,16 +244,26 @@ class FusedSAFn(torch.autograd.Function):
         t = s3 * c2 * rs3.double() / P                    # (C3)
         Q = W3d.t() @ (t.view(-1, 1) * W3d)               # (C2, C2)
         const = ((t * mu3.double()) - (s3 * c1 / P)) @ W3d  # q0 - r0, (C2)
-        Wb = pack_weight(torch.cat([W3d.t(), -Q.t()], dim=1).float())      # (C2, C3 + C2)
 
         # ---- da2 -> dyhat2 (grad at the BN2 output masked by ReLU'), BN2 sums -----------------
         dyh2 = torch.empty((P, C2), **f32)
         sums2 = torch.zeros((2, C2), **f64)
         constf = const.float().contiguous()
-        rowgemm(PRO_G3_A2, EPI_BWD_Y, "sa_b3", W=Wb, g3s=g3s, selpos=selpos, C3=C3, ns=ns, x0=y2,
-                scale=sc2, shift=sh2, slope=slope, P=P, K=C3 + C2, N=C2, ldw=Wb.shape[-1], out=dyh2,
-                stats=sums2, ebias=constf, ey=y2, escale=sc2, eshift=sh2, emean=mu2, erstd=rs2,
-                eslope=slope)
+        if MODE >= 2:
+            # dense part -a2.Q on the tensor core (K = C2); the routed part G3s.W3 is one row update per
+            # (group, channel) added in fp32 by the epilogue (PCL_EPI_BWD_Y_ROUTED)
+            Wq = pack_weight((-Q.t()).float().contiguous())                  # (C2, C2)
+            W3f = W3m.contiguous()
+            rowgemm(PRO_BN_ACT, EPI_BWD_Y_ROUTED, "sa_b3", W=Wq, x0=y2, x1=W3f, g3s=g3s, selpos=selpos, C3=C3,
+                    ns=ns, scale=sc2, shift=sh2, slope=slope, P=P, K=C2, N=C2, ldw=Wq.shape[-1], out=dyh2,
+                    stats=sums2, ebias=constf, ey=y2, escale=sc2, eshift=sh2, emean=mu2, erstd=rs2,
+                    eslope=slope)
+        else:
+            Wb = pack_weight(torch.cat([W3d.t(), -Q.t()], dim=1).float())      # (C2, C3 + C2)
+            rowgemm(PRO_G3_A2, EPI_BWD_Y, "sa_b3", W=Wb, g3s=g3s, selpos=selpos, C3=C3, ns=ns, x0=y2,
+                    scale=sc2, shift=sh2, slope=slope, P=P, K=C3 + C2, N=C2, ldw=Wb.shape[-1], out=dyh2,
+                    stats=sums2, ebias=constf, ey=y2, escale=sc2, eshift=sh2, emean=mu2, erstd=rs2,
+                    eslope=slope)
 
         # ---- dW3 from the Gram matrix of a2 and the sparse routed term -------------------------
         gram = torch.zeros((C2, C2 + 4), **f32)            # [:, :C2] = a2^T a2, [:, C2] = colsum(a2)

@@ -174,10 +174,15 @@ def bq_group_bytes(key):
     return 4 * (B * N * (3 + C) + 3 * B * S + B * S * ns + B * S * ns * W)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch, from profiles/rowgemm_tc_r01_ncu_full.txt
-# (ncu --set full capture of the same kernel and shape).
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, from profiles/ws_r01_ncu_full.txt (ncu --set
+# full captures of the same kernels at the same shapes: the P = 2,097,152-row branch of SA1).
 NCU_TRAFFIC = {
-    ("pcl_rowgemm", ("sa_b3", "4", "3", "2097152", "224", "96")): 822381000 + 766228992,
+    ("pcl_rowgemm", ("sa_b3", "1", "5", "2097152", "96", "96")): 1033961000 + 765846784,
+    ("pcl_rowgemm", ("sa_b2", "3", "4", "2097152", "96", "64")): 1656425000 + 507462144,
+    ("pcl_rowgemm", ("sa_l3", "1", "2", "2097152", "96", "128")): 805442000 + 33350912,
+    ("pcl_rowgemm", ("sa_l2", "2", "1", "2097152", "64", "96")): 43436000 + 747486976,
+    ("pcl_wgrad", ("sa_gram", "2097152", "96", "97")): 805384000 + 4113920,
+    ("pcl_wgrad", ("sa_dw2", "2097152", "96", "64")): 1860347000 + 4392448,
 }
 
 
@@ -343,7 +348,10 @@ def run_product_arm(args):
             k.update({"algorithmic_MB": by / 1e6, "GBps": by / (mean_ms * 1e-3) / 1e9,
                       "hbm_frac": by / (mean_ms * 1e-3) / 1e9 / peak})
         if fl:
-            k["TFLOPs"] = fl / (mean_ms * 1e-3) / 1e12
+            k["TFLOPs"] = fl / (mean_ms * 1e-3) / 1e12   # logical fp32 flops; the 3xTF32 split issues 3x
+        tr = NCU_TRAFFIC.get((name, tuple(str(x) for x in key) if key else ()))
+        if tr:
+            k["ncu_dram_traffic_MB"] = tr / 1e6
         kernels.append(k)
     top = next((k for k in kernels if "GBps" in k), kernels[0])
     traffic = NCU_TRAFFIC.get((top["call"], tuple(top["key"] or ())))

@@ -239,6 +239,8 @@ def run_product_arm(args):
     torch.manual_seed(0)  # identical initial weights on every rank
     model = PointNetMSG(n_classes=N_CLASSES).to(dev)
     model.train()
+    # zero-grad + forward + loss + backward replay as ONE CUDA graph; the NCCL all-reduce and the SGD kernel
+    # are launched after it (capturing the all-reduce hung the 2-GPU run on this image, round 1)
     trainer = Trainer(model, lr=0.02, momentum=0.9, graph=not args.no_graph)
 
     # distinct synthetic batches per rank and per step slot (rotated), resident in HBM
@@ -286,7 +288,7 @@ def run_product_arm(args):
     ev1.record()
     sync_all()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    launches = trainer.graph_launches * args.steps if graphed else _lib.LAUNCHES - launches0
+    launches = (trainer.graph_launches + 1) * args.steps if graphed else _lib.LAUNCHES - launches0
     clocks = sampler.stop() if rank == 0 else None
     final_loss = float(loss.item())
 

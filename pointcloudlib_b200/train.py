@@ -60,10 +60,12 @@ class FlatSGD:
 class Trainer:
     """One fwd + loss + bwd + (all-reduce) + SGD step of a classification network.
 
-    graph=True captures the whole step (about a thousand kernel launches: ours, torch's, the NCCL
-    all-reduce) in ONE CUDA graph after `graph_warmup` eager steps and replays it from then on: inputs
-    are copied into static buffers, parameters / momentum / BatchNorm running statistics are updated
-    in place by the replay.  The returned loss tensor is a static buffer, overwritten by the next step."""
+    graph=True captures zero-grad + forward + loss + backward (about a thousand kernel launches, ours
+    and torch's) in ONE CUDA graph after `graph_warmup` eager steps and replays it from then on: inputs
+    are copied into static buffers, gradients land in the flat bucket, BatchNorm running statistics are
+    updated in place by the replay.  The gradient all-reduce and the SGD kernel are launched after the
+    replay, outside the graph (a captured NCCL all-reduce hung the 2-GPU run on this image).  The
+    returned loss tensor is a static buffer, overwritten by the next step."""
 
     def __init__(self, model, lr=0.02, momentum=0.9, weight_decay=0.0, distributed=None, graph=False,
                  graph_warmup=3):
@@ -87,13 +89,17 @@ class Trainer:
             dist.all_reduce(self.opt.grads)
         return 1.0 / self.world
 
-    def _eager_step(self, *inputs, labels):
+    def _fwd_bwd(self, *inputs, labels):
         self.opt.zero_grad()
         logits = self.model(*inputs)
         loss = soft_cross_entropy_loss(logits, labels)
         loss.backward()
-        self.opt.step(grad_scale=self.reduce_gradients())
         return loss.detach()
+
+    def _eager_step(self, *inputs, labels):
+        loss = self._fwd_bwd(*inputs, labels=labels)
+        self.opt.step(grad_scale=self.reduce_gradients())
+        return loss
 
     def _capture(self, inputs, labels):
         from . import _lib
@@ -106,7 +112,7 @@ class Trainer:
         n0 = _lib.LAUNCHES
         # thread_local: other threads (NCCL watchdog, clock sampler) may touch CUDA during the capture
         with torch.cuda.graph(g, capture_error_mode="thread_local"):
-            self._static_loss = self._eager_step(*self._static[0], labels=self._static[1])
+            self._static_loss = self._fwd_bwd(*self._static[0], labels=self._static[1])
         self.graph_launches = _lib.LAUNCHES - n0
         self._graph = g
 
@@ -129,4 +135,5 @@ class Trainer:
             s.copy_(t, non_blocking=True)
         self._static[1].copy_(labels, non_blocking=True)
         self._graph.replay()
+        self.opt.step(grad_scale=self.reduce_gradients())
         return self._static_loss

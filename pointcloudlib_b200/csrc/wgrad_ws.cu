@@ -90,7 +90,7 @@ constexpr int WG_BLK = 4096;    // bytes of one 32-channel block of a tile (hi o
 constexpr int NPL = 4, NPR = 5; // max 16-byte pieces per thread and chunk: L (128 ch), R (160 ch)
 constexpr int kTabQuads = 40;
 constexpr int kSlackBytes = 2 * WG_BLK + 1024;       // the 128-lane operand read past the last staged block
-constexpr int kSrcBytes = 7 * NPR * 256 * 4;         // gather-index slots: up to PD + 1 = 5 chunks (+ spare)   // channel quads covered by a parameter table (160 channels)
+constexpr int kSrcSlot = NPR * 256 * 4;              // gather-index slots of one chunk   // channel quads covered by a parameter table (160 channels)
 
 // one operand (L or R) of the transform: piece bookkeeping of this thread
 template <int NP, class Pro>
@@ -248,7 +248,7 @@ wgrad_ws_kernel(const PclRowGemm al, const PclRowGemm ar, long long P, int M, in
                 }
                 ++i_c;
             }
-            cp_async_commit();
+            if (!(dbg & 512)) cp_async_commit();
         };
         for (int j = 0; j < PD; ++j) issue_next();
 
@@ -257,7 +257,7 @@ wgrad_ws_kernel(const PclRowGemm al, const PclRowGemm ar, long long P, int M, in
             const long long c = c_begin + cc;
             const long long left = P - c * WG_ROWS;
             const int rows_valid = left < WG_ROWS ? (int)left : WG_ROWS;
-            cp_async_wait<PD - 1>();
+            if (!(dbg & 512)) cp_async_wait<PD - 1>();
             // pass 1: all raw pieces, table entries and V rows in flight together; pass 2: math, split, stores
             float4 l0[NPL], l1[NPL], lv[NPL], r0[NPR], r1[NPR], rv[NPR];
             const int nl = (dbg & 16) ? 0 : L.n_live, nr = (dbg & 16) ? 0 : R.n_live;
@@ -376,9 +376,11 @@ static void wgrad_ws_geometry(int M, int N, bool share, bool gather, size_t &sta
     const int Npad = (N + 15) & ~15;
     const int MB = share ? 0 : (M + 31) / 32, NB = (Npad + 31) / 32;
     stage = (size_t)2 * (MB + NB) * WG_BLK;
-    slack = (size_t)kSlackBytes + (gather ? kSrcBytes : 0);   // operand over-read + the gather-index slots
-    const size_t budget = 232448 - 4096 - 1024 - slack;   // static: barriers + parameter tables
-    S = stage * 6 <= budget ? 6 : (stage * 4 <= budget ? 4 : (stage * 3 <= budget ? 3 : 0));
+    // operand over-read + the gather-index slots (PD + 1 chunks: PD = S - 2, or 2 at S = 3)
+    const size_t total = 232448 - 4096 - 1024 - kSlackBytes;   // static: barriers + parameter tables
+    auto fits = [&](int s_, int pd) { return stage * s_ + (gather ? (size_t)(pd + 1) * kSrcSlot : 0) <= total; };
+    S = fits(6, 4) ? 6 : (fits(4, 2) ? 4 : (fits(3, 2) ? 3 : 0));
+    slack = (size_t)kSlackBytes + (gather ? (size_t)((S == 6 ? 4 : 2) + 1) * kSrcSlot : 0);
 }
 
 template <bool SHARE, class ProL, class ProR>

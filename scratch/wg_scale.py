@@ -16,7 +16,7 @@ for P in (4736*32, 2097152):
     gram=torch.zeros(C2,C2+4,device=dev)
     a2kw=dict(x0=y2, scale=sc, shift=sh, slope=0.0, K=C2)
     res=[]
-    for dbg in (0,245,245+256,117+256):
+    for dbg in (0,245,245+512):
         fused.WS_DBG=dbg
         res.append((dbg, round(timeit(lambda: fused.wgrad(fused.PRO_BN_ACT, a2kw, fused.PRO_BN_ACT_ONES, a2kw, P, C2, C2+1, gram, name="g")))))
     print("gram P",P,res, flush=True)

@@ -248,3 +248,29 @@ def dgcnn_partseg(model, x, l):
     h = model.dp1(model.conv8(h))
     h = model.dp2(model.conv9(h))
     return model.conv11(model.conv10(h))
+
+
+def pointcnn_cls(model, xyz, normal=None):
+    """networks/cls/pointcnn.py:34-47 + misc/layers.py:306-407 evaluated on the CPU: the dense
+    layers are the model's own modules (torch CPU, any dtype); sampling and neighbourhoods come from
+    the C oracle (oracle.fps / oracle.knn incl. the dilation slice), the regional gather is the
+    reference's per-sample fancy index (layers.py:381-388)."""
+    def rand_pointcnn(m, pts, fts):
+        if 0 < m.P < pts.shape[1]:
+            rep = furthest_point_sampler(pts, m.P)
+        else:
+            rep = pts
+        pc = m.pointcnn
+        f = pc.dense(fts) if fts is not None else fts
+        q = rep.permute(0, 2, 1).contiguous().detach().float().numpy()
+        r = pts.permute(0, 2, 1).contiguous().detach().float().numpy()
+        idx = _t(oracle.knn(q, r, pc.K * pc.D))[:, 0::pc.D, :].permute(0, 2, 1)   # (N, P, K)
+        region = lambda t: torch.stack([t[n][i.long(), :] for n, i in enumerate(torch.unbind(idx, dim=0))], dim=0)
+        return rep, pc.x_conv((rep, region(pts), region(f) if f is not None else f))
+
+    x = (xyz, xyz if normal is None else normal)
+    x = rand_pointcnn(model.pcnn1, *x)
+    for m in model.pcnn2:
+        x = rand_pointcnn(m, *x)
+    logits = model.fcn(x[1].permute(0, 2, 1))
+    return torch.mean(logits, dim=2)

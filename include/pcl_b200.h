@@ -174,6 +174,10 @@ enum { PCL_PRO_PLAIN2 = 0, PCL_PRO_BN_ACT = 1, PCL_PRO_GATHER_BN_ACT = 2, PCL_PR
 enum { PCL_EPI_STORE = 0, PCL_EPI_STORE_STATS = 1, PCL_EPI_MAXMIN_STATS = 2, PCL_EPI_BWD_Y = 3,
        PCL_EPI_BWD_GATHER = 4, PCL_EPI_BWD_Y_ROUTED = 5 };
 int pcl_rowgemm(const PclRowGemm *args, int prologue, int epilogue, int x3, void *stream);
+/* Weight operand of pcl_rowgemm: w (N,K) fp32, row stride ldi -> out (3, N, ld), ld = K rounded up to
+ * 32, zero padded: [sign*w | tf32 hi | tf32 lo] with hi = rna_tf32(sign*w), lo = rna_tf32(sign*w - hi).
+ * (The conv weights of networks/cls/pointnet2.py:25-29 in the form the 3xTF32 tensor-core MMA reads.) */
+int pcl_pack_weight(const float *w, int N, int K, int ldi, float sign, float *out, void *stream);
 
 /* pcl_wgrad: OUT (M,N) += sum over rows p of L(p)[m] * R(p)[n]  (weight gradients, Gram
  * matrices).  L and R rows are produced by the same prologue functors as pcl_rowgemm (args_l /

@@ -44,6 +44,7 @@ _SIGNATURES = {
     "pcl_graph_feature_backward": [P, P, c_int, c_int, c_int, c_int, P, P],
     "pcl_compute_density": [P, c_int, c_int, c_float, P, P],
     "pcl_sgd_momentum": [P, P, P, c_size_t, c_float, c_float, c_float, c_float, P],
+    "pcl_pack_weight": [P, c_int, c_int, c_int, c_float, P, P],
 }
 
 

@@ -195,6 +195,28 @@ extern "C" int pcl_compute_density(const float *xyz, int B, int N, float bandwid
     return check_launch("pcl_compute_density");
 }
 
+// w (N,K) row stride ldi -> out (3, N, ld): [w zero-padded | tf32_rna(w) | tf32_rna(w - hi)], ld % 32 == 0.
+// cvt.rna on the magnitude: round to 10 mantissa bits, ties away ((bits + 0x1000) & ~0x1FFF).
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float *__restrict__ w, int N, int K, int ldi,
+                                                          int ld, float sign, float *__restrict__ out) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= N * ld) return;
+    const int n = i / ld, k = i - n * ld;
+    const float x = k < K ? sign * __ldg(w + (long long)n * ldi + k) : 0.f;
+    const float hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    const float lo = __uint_as_float((__float_as_uint(__fsub_rn(x, hi)) + 0x1000u) & 0xFFFFE000u);
+    out[i] = x;
+    out[(long long)N * ld + i] = hi;
+    out[2LL * N * ld + i] = lo;
+}
+
+extern "C" int pcl_pack_weight(const float *w, int N, int K, int ldi, float sign, float *out, void *stream) {
+    PCL_REQUIRE(w && out && N >= 1 && K >= 1 && ldi >= 1, "pcl_pack_weight: bad arguments");
+    const int ld = (K + 31) / 32 * 32;
+    pack_weight_kernel<<<(unsigned)ceil_div(N * ld, 256), 256, 0, (cudaStream_t)stream>>>(w, N, K, ldi, ld, sign, out);
+    return check_launch("pcl_pack_weight");
+}
+
 extern "C" int pcl_sgd_momentum(float *param, const float *grad, float *momentum_buf, size_t n,
                                 float lr, float mu, float weight_decay, float grad_scale,
                                 void *stream) {

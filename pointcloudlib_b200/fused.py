@@ -99,14 +99,19 @@ def _tf32_rna(x: torch.Tensor) -> torch.Tensor:
     return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
-def pack_weight(w: torch.Tensor) -> torch.Tensor:
-    """(N, K) -> (3, N, ceil32(K)) zero-padded fp32: [raw | tf32 hi | tf32 lo] (w = hi + lo + O(2^-22))."""
+def pack_weight(w: torch.Tensor, sign: float = 1.0) -> torch.Tensor:
+    """(N, K) -> (3, N, ceil32(K)) zero-padded fp32: [sign*w | tf32 hi | tf32 lo] (w = hi + lo + O(2^-22)).
+    One kernel (pcl_pack_weight); w may be any 2-D view with unit inner stride (fp32 or fp64)."""
+    if w.dtype != torch.float32:
+        w = w.float()
+    if w.stride(1) != 1:
+        w = w.contiguous()
     N, K = w.shape
     ld = (K + 31) // 32 * 32
-    out = torch.zeros((3, N, ld), dtype=torch.float32, device=w.device)
-    out[0, :, :K] = w
-    out[1] = _tf32_rna(out[0])
-    out[2] = _tf32_rna(out[0] - out[1])
+    out = torch.empty((3, N, ld), dtype=torch.float32, device=w.device)
+    if not w.is_cuda:
+        raise RuntimeError("libpcl_b200 operators need CUDA tensors: there is no CPU fallback")
+    _lib.call("pcl_pack_weight", w.data_ptr(), N, K, w.stride(0), float(sign), ptr(out), stream())
     return out
 
 
@@ -252,7 +257,7 @@ class FusedSAFn(torch.autograd.Function):
         if MODE >= 2:
             # dense part -a2.Q on the tensor core (K = C2); the routed part G3s.W3 is one row update per
             # (group, channel) added in fp32 by the epilogue (PCL_EPI_BWD_Y_ROUTED)
-            Wq = pack_weight((-Q.t()).float().contiguous())                  # (C2, C2)
+            Wq = pack_weight(Q.t(), sign=-1.0)                               # (C2, C2) = -Q^T
             W3f = W3m.contiguous()
             rowgemm(PRO_BN_ACT, EPI_BWD_Y_ROUTED, "sa_b3", W=Wq, x0=y2, x1=W3f, g3s=g3s, selpos=selpos, C3=C3,
                     ns=ns, scale=sc2, shift=sh2, slope=slope, P=P, K=C2, N=C2, ldw=Wq.shape[-1], out=dyh2,

@@ -168,10 +168,12 @@ def test_pointconv_cls_forward_backward():
 
 def test_cuda_graph_step_equals_eager_step():
     """Trainer(graph=True): the captured + replayed step is the eager step (same kernels, same
-    order).  Training itself amplifies the run-to-run noise of the floating-point atomics (two EAGER
-    trainers drift apart by 1e-2 within five steps at this batch size), so the graph trainer is
-    required to stay as close to an eager trainer as a second eager trainer does, step by step.
-    Dropout off: the Philox offsets of a captured graph differ from eager by construction."""
+    order).  Training amplifies the run-to-run noise of the floating-point atomics chaotically (two
+    EAGER trainers drift apart by 1e-2 within five steps at this batch size), so every step starts
+    from IDENTICAL state: the eager trainer's parameters, momentum and BatchNorm buffers are copied
+    into the graph trainer (in place: the captured addresses stay valid) before each step, and one
+    step later the two must agree to atomics noise.  Dropout off: the Philox offsets of a captured
+    graph differ from eager by construction."""
     import copy
     from pointcloudlib_b200.networks.cls.pointnet2 import PointNet2_cls
     torch.manual_seed(3)
@@ -179,20 +181,26 @@ def test_cuda_graph_step_equals_eager_step():
     for m in m0.modules():
         if isinstance(m, torch.nn.Dropout):
             m.p = 0.0
-    m1, m2 = copy.deepcopy(m0), copy.deepcopy(m0)
-    m0, m1, m2 = m0.to(DEV).train(), m1.to(DEV).train(), m2.to(DEV).train()
-    t0, t2 = Trainer(m0, lr=0.002), Trainer(m2, lr=0.002)
-    t1 = Trainer(m1, lr=0.002, graph=True, graph_warmup=2)
-    for s in range(5):
+    m1 = copy.deepcopy(m0)
+    m0, m1 = m0.to(DEV).train(), m1.to(DEV).train()
+    t0 = Trainer(m0, lr=0.01)
+    t1 = Trainer(m1, lr=0.01, graph=True, graph_warmup=2)
+    for s in range(6):
+        with torch.no_grad():
+            t1.opt.params.copy_(t0.opt.params)
+            t1.opt.momentum_buf.copy_(t0.opt.momentum_buf)
+            for b1, b0 in zip(m1.buffers(), m0.buffers()):
+                b1.copy_(b0)
         xyz, nrm, lab = modelnet_batch(4, 1024, seed=40 + s)
         x, n, l = xyz.to(DEV), nrm.to(DEV), lab.to(DEV)
         a = t0.step(x, n, labels=l).item()
         b = t1.step(x, n, labels=l).item()
-        c = t2.step(x, n, labels=l).item()
-        d_graph = ((t0.opt.params - t1.opt.params).norm() / t0.opt.params.norm()).item()
-        d_eager = ((t0.opt.params - t2.opt.params).norm() / t0.opt.params.norm()).item()
-        assert d_graph <= 5 * d_eager + 1e-5, (s, d_graph, d_eager)
-        assert abs(a - b) <= 5 * abs(a - c) + 1e-3, (s, a, b, c)
+        d = ((t0.opt.params - t1.opt.params).norm() / t0.opt.params.norm()).item()
+        assert abs(a - b) <= 1e-3 * max(1.0, abs(a)), (s, a, b)
+        assert d <= 3e-4, (s, d)
+        rm = max(((b1.float() - b0.float()).norm() / b0.float().norm().clamp_min(1e-6)).item()
+                 for b1, b0 in zip(m1.buffers(), m0.buffers()))
+        assert rm <= 1e-3, (s, rm)
     assert t1.graph_error is None and t1._graph is not None and t1.graph_launches > 0
 
 

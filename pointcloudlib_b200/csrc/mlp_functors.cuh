@@ -61,6 +61,7 @@ __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0
 // Prologue functors: 4 consecutive channels k..k+3 (k % 4 == 0) of operand row p (p < P).
 // ------------------------------------------------------------------------------------------
 struct ProPlain2 {
+    static constexpr bool kRaw = false;
     static __device__ __forceinline__ float4 load(const PclRowGemm &a, long long p, int k) {
         if ((a.c0 & 3) == 0 && k + 3 < a.c0) return ld4(a.x0 + p * a.c0 + k);   // aligned quad inside x0
         float v[4];
@@ -88,6 +89,16 @@ struct ProBnAct {
         if (k >= a.K) return f4zero();
         return bn_act4(ld4(a.x0 + p * a.K + k), a.scale, a.shift, k, a.slope);
     }
+    // deferred form (rowgemm_tc_kernel): the raw load is issued a chunk ahead and the BatchNorm + activation
+    // is applied when the tile is staged, so nothing waits on the load at the prefetch point
+    static constexpr bool kRaw = true;
+    static __device__ __forceinline__ float4 load_raw(const PclRowGemm &a, long long p, int k) {
+        return k < a.K ? ld4(a.x0 + p * a.K + k) : f4zero();
+    }
+    static __device__ __forceinline__ float4 finish(const PclRowGemm &a, float4 raw, int k) {
+        if (k >= a.K) return f4zero();
+        return bn_act4(raw, a.scale, a.shift, k, a.slope);
+    }
 };
 // group index of row p.  `reserved` carries log2(ns) when ns is a power of two (set by the C entry
 // points), which turns a 64-bit software division per row into a shift.
@@ -103,18 +114,21 @@ __device__ __forceinline__ float4 gather_y4(const PclRowGemm &a, long long p, in
 }
 // [act(bn(x0)) | 1 | 0 ...]: the extra ones column turns a Gram wgrad into (A^T.A | column sums)
 struct ProBnActOnes {
+    static constexpr bool kRaw = false;
     static __device__ __forceinline__ float4 load(const PclRowGemm &a, long long p, int k) {
         if (k >= a.K) return make_float4(k == a.K ? 1.f : 0.f, 0.f, 0.f, 0.f);
         return bn_act4(ld4(a.x0 + p * a.K + k), a.scale, a.shift, k, a.slope);
     }
 };
 struct ProGatherBnAct {
+    static constexpr bool kRaw = false;
     static __device__ __forceinline__ float4 load(const PclRowGemm &a, long long p, int k) {
         if (k >= a.K) return f4zero();
         return bn_act4(gather_y4(a, p, k, a.K), a.scale, a.shift, k, a.slope);
     }
 };
 struct ProBnBwd {
+    static constexpr bool kRaw = false;
     static __device__ __forceinline__ float4 load(const PclRowGemm &a, long long p, int k) {
         if (k >= a.K) return f4zero();
         const float4 d = ld4(a.x0 + p * a.K + k), y = ld4(a.x1 + p * a.K + k);
@@ -127,6 +141,7 @@ struct ProBnBwd {
     }
 };
 struct ProG3A2 {
+    static constexpr bool kRaw = false;
     static __device__ __forceinline__ float4 load(const PclRowGemm &a, long long p, int k) {
         if (k < a.C3) {
             const long long g = group_of(a, p);

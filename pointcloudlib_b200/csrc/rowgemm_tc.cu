@@ -168,7 +168,10 @@ __global__ void __launch_bounds__(256, 2) rowgemm_tc_kernel(const PclRowGemm a) 
 #pragma unroll
             for (int i = 0; i < 4 * RT; ++i) {
                 const long long p = tl * (RT * BMt) + a_row + 32 * i;
-                ra[i] = (p < a.P && !(dbg & 4)) ? Pro::load(a, p, kcc * 32 + a_c * 4) : f4zero();
+                if constexpr (Pro::kRaw)
+                    ra[i] = (p < a.P && !(dbg & 4)) ? Pro::load_raw(a, p, kcc * 32 + a_c * 4) : f4zero();
+                else
+                    ra[i] = (p < a.P && !(dbg & 4)) ? Pro::load(a, p, kcc * 32 + a_c * 4) : f4zero();
             }
         };
         if (have) prefetch(tile, 0);
@@ -190,7 +193,12 @@ __global__ void __launch_bounds__(256, 2) rowgemm_tc_kernel(const PclRowGemm a) 
             for (int i = 0; i < 4 * RT; ++i) {
                 uint8_t *hi_t = sA + (i / 4) * 2 * A_TILE, *lo_t = hi_t + A_TILE;
                 const uint32_t off = sw128_off(a_row + 32 * (i % 4), a_c);
-                float x[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w};
+                float4 rv = ra[i];
+                if constexpr (Pro::kRaw) {
+                    // applied to every row: rows past P only reach accumulator rows the epilogue skips
+                    rv = Pro::finish(a, rv, kc * 32 + a_c * 4);
+                }
+                float x[4] = {rv.x, rv.y, rv.z, rv.w};
                 uint32_t hi[4], lo[4];
                 split_tf32_trunc<4>(x, hi, lo);
                 *reinterpret_cast<uint4 *>(hi_t + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);

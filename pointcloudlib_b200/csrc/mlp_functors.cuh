@@ -61,6 +61,7 @@ __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0
 // Prologue functors: 4 consecutive channels k..k+3 (k % 4 == 0) of operand row p (p < P).
 // ------------------------------------------------------------------------------------------
 struct ProPlain2 {
+    static constexpr bool kRaw2 = false;
     static constexpr bool kRaw = false;
     static __device__ __forceinline__ float4 load(const PclRowGemm &a, long long p, int k) {
         if ((a.c0 & 3) == 0 && k + 3 < a.c0) return ld4(a.x0 + p * a.c0 + k);   // aligned quad inside x0
@@ -85,6 +86,7 @@ __device__ __forceinline__ float4 bn_act4(float4 y, const float *scale, const fl
                        act_f(fmaf(s.z, y.z, h.z), slope), act_f(fmaf(s.w, y.w, h.w), slope));
 }
 struct ProBnAct {
+    static constexpr bool kRaw2 = false;
     static __device__ __forceinline__ float4 load(const PclRowGemm &a, long long p, int k) {
         if (k >= a.K) return f4zero();
         return bn_act4(ld4(a.x0 + p * a.K + k), a.scale, a.shift, k, a.slope);
@@ -114,6 +116,7 @@ __device__ __forceinline__ float4 gather_y4(const PclRowGemm &a, long long p, in
 }
 // [act(bn(x0)) | 1 | 0 ...]: the extra ones column turns a Gram wgrad into (A^T.A | column sums)
 struct ProBnActOnes {
+    static constexpr bool kRaw2 = false;
     static constexpr bool kRaw = false;
     static __device__ __forceinline__ float4 load(const PclRowGemm &a, long long p, int k) {
         if (k >= a.K) return make_float4(k == a.K ? 1.f : 0.f, 0.f, 0.f, 0.f);
@@ -121,6 +124,7 @@ struct ProBnActOnes {
     }
 };
 struct ProGatherBnAct {
+    static constexpr bool kRaw2 = false;
     static constexpr bool kRaw = false;
     static __device__ __forceinline__ float4 load(const PclRowGemm &a, long long p, int k) {
         if (k >= a.K) return f4zero();
@@ -129,6 +133,26 @@ struct ProGatherBnAct {
 };
 struct ProBnBwd {
     static constexpr bool kRaw = false;
+    // two-operand deferred form (rowgemm_tc_kernel): raw dyhat and y a chunk ahead, the BatchNorm-backward
+    // arithmetic at staging time
+    static constexpr bool kRaw2 = true;
+    static __device__ __forceinline__ void load_raw2(const PclRowGemm &a, long long p, int k, float4 &d, float4 &y) {
+        if (k < a.K) {
+            d = ld4(a.x0 + p * a.K + k);
+            y = ld4(a.x1 + p * a.K + k);
+        } else {
+            d = y = f4zero();
+        }
+    }
+    static __device__ __forceinline__ float4 finish2(const PclRowGemm &a, float4 d, float4 y, int k) {
+        if (k >= a.K) return f4zero();
+        const float4 mu = ld4(a.mean + k), rs = ld4(a.rstd + k), bs = ld4(a.bscale + k);
+        const float4 m1 = ld4(a.m1 + k), m2 = ld4(a.m2 + k);
+        return make_float4(bs.x * (d.x - m1.x - (y.x - mu.x) * rs.x * m2.x),
+                           bs.y * (d.y - m1.y - (y.y - mu.y) * rs.y * m2.y),
+                           bs.z * (d.z - m1.z - (y.z - mu.z) * rs.z * m2.z),
+                           bs.w * (d.w - m1.w - (y.w - mu.w) * rs.w * m2.w));
+    }
     static __device__ __forceinline__ float4 load(const PclRowGemm &a, long long p, int k) {
         if (k >= a.K) return f4zero();
         const float4 d = ld4(a.x0 + p * a.K + k), y = ld4(a.x1 + p * a.K + k);
@@ -141,6 +165,7 @@ struct ProBnBwd {
     }
 };
 struct ProG3A2 {
+    static constexpr bool kRaw2 = false;
     static constexpr bool kRaw = false;
     static __device__ __forceinline__ float4 load(const PclRowGemm &a, long long p, int k) {
         if (k < a.C3) {

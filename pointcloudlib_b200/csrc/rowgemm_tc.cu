@@ -164,11 +164,17 @@ __global__ void __launch_bounds__(256, 2) rowgemm_tc_kernel(const PclRowGemm a) 
         int kc = 0;
         bool have = tile < n_tiles;
         float4 ra[4 * RT];
+        // two raw operands per piece cost 32 more registers: spills at BN = 128, a win up to BN = 96
+        constexpr bool RAW2 = Pro::kRaw2 && BN <= 96;
+        float4 rb[RAW2 ? 4 * RT : 1];
         auto prefetch = [&](long long tl, int kcc) {
 #pragma unroll
             for (int i = 0; i < 4 * RT; ++i) {
                 const long long p = tl * (RT * BMt) + a_row + 32 * i;
-                if constexpr (Pro::kRaw)
+                if constexpr (RAW2) {
+                    if (p < a.P && !(dbg & 4)) Pro::load_raw2(a, p, kcc * 32 + a_c * 4, ra[i], rb[i]);
+                    else ra[i] = rb[i] = f4zero();
+                } else if constexpr (Pro::kRaw)
                     ra[i] = (p < a.P && !(dbg & 4)) ? Pro::load_raw(a, p, kcc * 32 + a_c * 4) : f4zero();
                 else
                     ra[i] = (p < a.P && !(dbg & 4)) ? Pro::load(a, p, kcc * 32 + a_c * 4) : f4zero();
@@ -198,6 +204,7 @@ __global__ void __launch_bounds__(256, 2) rowgemm_tc_kernel(const PclRowGemm a) 
                     // applied to every row: rows past P only reach accumulator rows the epilogue skips
                     rv = Pro::finish(a, rv, kc * 32 + a_c * 4);
                 }
+                if constexpr (RAW2) rv = Pro::finish2(a, rv, rb[i], kc * 32 + a_c * 4);
                 float x[4] = {rv.x, rv.y, rv.z, rv.w};
                 uint32_t hi[4], lo[4];
                 split_tf32_trunc<4>(x, hi, lo);

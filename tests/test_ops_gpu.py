@@ -264,3 +264,23 @@ def test_sgd_momentum():
     mm = 0.9 * m + gg
     np.testing.assert_allclose(_np(md), mm.numpy(), rtol=1e-6, atol=1e-6)
     np.testing.assert_allclose(_np(pd), (p - 0.1 * mm).numpy(), rtol=1e-6, atol=1e-6)
+
+
+def test_pack_weight_is_the_3xtf32_split():
+    """pcl_pack_weight: [sign*w zero-padded | hi | lo] with hi = rna_tf32(sign*w) (round to 10 mantissa
+    bits, ties away), lo = rna_tf32(sign*w - hi); bit-exact against the integer formula, on a
+    non-contiguous view with K not a multiple of 32."""
+    import torch
+    from pointcloudlib_b200 import fused
+    torch.manual_seed(0)
+    big = torch.randn(70, 50, device="cuda") * torch.logspace(-6, 6, 50, device="cuda")
+    w = big[:, 3:40]                                             # (70, 37), row stride 50
+    out = fused.pack_weight(w, sign=-1.0)
+    assert out.shape == (3, 70, 64)
+    ref0 = torch.zeros(70, 64, device="cuda")
+    ref0[:, :37] = -w
+    rna = lambda x: ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    hi = rna(ref0)
+    lo = rna(ref0 - hi)
+    assert torch.equal(out[0], ref0) and torch.equal(out[1], hi) and torch.equal(out[2], lo)
+    assert ((out[1] + out[2] - ref0).abs() <= 2.0 ** -21 * ref0.abs()).all()

@@ -45,6 +45,45 @@ __device__ __forceinline__ void group_rows(const BQArgs &a, int b, int s, const 
     float *o = a.out + ((long long)b * a.S + s) * total;
     const float *fb = a.feat ? a.feat + (long long)b * a.N * a.C : nullptr;
     const float *pb = a.xyz + (long long)b * a.N * 3;
+    if (W >= 64) {
+        // wide rows (SA2 and deeper: 3 + 320 channels): one grouped row (neighbour l) at a time, lanes
+        // across its channels.  No flat-index bookkeeping: per element one load, one store and a compare;
+        // two rows (up to 2 x 11 loads per lane) are in flight before the first store.
+        const int nj = (W + 31) / 32;
+        for (int l = 0; l < a.ns; l += 2) {
+            const int k0 = sidx[l], k1 = l + 1 < a.ns ? sidx[l + 1] : k0;
+            const float *f0 = fb ? fb + (long long)k0 * a.C - off : nullptr;
+            const float *f1 = fb ? fb + (long long)k1 * a.C - off : nullptr;
+            float *o0 = o + (long long)l * W, *o1 = o0 + W;
+            for (int j0 = 0; j0 < nj; j0 += 6) {
+                float v0[6], v1[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const int c = lane + 32 * (j0 + j);
+                    v0[j] = v1[j] = 0.f;
+                    if (c < W) {
+                        if (c < off) {
+                            const float ctr = c == 0 ? cx : (c == 1 ? cy : cz);
+                            v0[j] = __fsub_rn(SMEM_XYZ ? s_xyz[c * a.N + k0] : __ldg(pb + 3 * k0 + c), ctr);
+                            v1[j] = __fsub_rn(SMEM_XYZ ? s_xyz[c * a.N + k1] : __ldg(pb + 3 * k1 + c), ctr);
+                        } else {
+                            v0[j] = __ldg(f0 + c);
+                            v1[j] = __ldg(f1 + c);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const int c = lane + 32 * (j0 + j);
+                    if (c < W) {
+                        o0[c] = v0[j];
+                        if (l + 1 < a.ns) o1[c] = v1[j];
+                    }
+                }
+            }
+        }
+        return;
+    }
     int l = lane / W, c = lane % W;
     const int dl = 32 / W, dc = 32 % W;
     // kGU elements per lane per iteration: all gathers are in flight before the first store

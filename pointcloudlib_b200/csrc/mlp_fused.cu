@@ -489,6 +489,54 @@ __global__ void __launch_bounds__(256) gather_bn_backward_kernel(
     const long long gi = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (gi >= G) return;
     const int nq = C / 4;
+    if (nq <= 32 && 32 % nq == 0) {
+        // C = 32 / 64 / 128: the warp covers 32/nq rows at once (lane = (row offset, channel quad)), four
+        // row batches are in flight before the first atomic, and one 16-byte vector atomic (sm_90+)
+        // replaces four scalar ones
+        const int rpp = 32 / nq, sub = lane / nq, k = (lane % nq) * 4;
+        const float4 mu = ld4(mean + k), rs = ld4(rstd + k), bs = ld4(bscale + k), a1 = ld4(m1 + k),
+                     a2 = ld4(m2 + k);
+        const float4 v = V ? ld4(V + gi * C + k) : f4zero();
+        float4 sum = f4zero();
+        for (int l0 = 0; l0 < ns; l0 += 4 * rpp) {
+            long long sr[4];
+            float4 u[4], d[4];
+            bool ok[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int l = l0 + j * rpp + sub;
+                ok[j] = l < ns;
+                sr[j] = ok[j] ? __ldg(src + gi * ns + l) : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int l = l0 + j * rpp + sub;
+                u[j] = ok[j] ? ld4(U + sr[j] * C + k) : f4zero();
+                d[j] = ok[j] ? ld4(dyh + (gi * ns + l) * C + k) : f4zero();
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (!ok[j]) continue;
+                float4 dz;
+                dz.x = bs.x * (d[j].x - a1.x - (fmaf(vsign, v.x, u[j].x) - mu.x) * rs.x * a2.x);
+                dz.y = bs.y * (d[j].y - a1.y - (fmaf(vsign, v.y, u[j].y) - mu.y) * rs.y * a2.y);
+                dz.z = bs.z * (d[j].z - a1.z - (fmaf(vsign, v.z, u[j].z) - mu.z) * rs.z * a2.z);
+                dz.w = bs.w * (d[j].w - a1.w - (fmaf(vsign, v.w, u[j].w) - mu.w) * rs.w * a2.w);
+                atomicAdd(reinterpret_cast<float4 *>(dU + sr[j] * C + k), dz);
+                sum.x += dz.x; sum.y += dz.y; sum.z += dz.z; sum.w += dz.w;
+            }
+        }
+        for (int o = nq; o < 32; o <<= 1) {
+            sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o);
+            sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
+            sum.z += __shfl_xor_sync(0xffffffffu, sum.z, o);
+            sum.w += __shfl_xor_sync(0xffffffffu, sum.w, o);
+        }
+        if (dV && sub == 0)
+            *reinterpret_cast<float4 *>(dV + gi * C + k) =
+                make_float4(vsign * sum.x, vsign * sum.y, vsign * sum.z, vsign * sum.w);
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         const int qd = lane + 32 * i;

@@ -360,16 +360,34 @@ __global__ void __launch_bounds__(256) gather_stats_kernel(const float *__restri
     __syncthreads();
     if (tid < RPI * QC) {
         float4 s = f4zero(), s2 = f4zero();
-        for (long long p = (long long)blockIdx.x * RPI + r; p < P; p += (long long)gridDim.x * RPI) {
-            float4 y = ld4(U + (long long)__ldg(src + p) * C + q * 4);
-            if (V) {
-                const float4 v = ld4(V + (p / ns) * C + q * 4);
-                y.x = fmaf(vsign, v.x, y.x); y.y = fmaf(vsign, v.y, y.y);
-                y.z = fmaf(vsign, v.z, y.z); y.w = fmaf(vsign, v.w, y.w);
+        // four rows per iteration: index loads, then gathers, all in flight together; the group index is a
+        // shift when ns is a power of two (a 64-bit division per row otherwise)
+        const int sh = (ns & (ns - 1)) == 0 ? 31 - __clz(ns) : -1;
+        const long long step = (long long)gridDim.x * RPI;
+        for (long long p0 = (long long)blockIdx.x * RPI + r; p0 < P; p0 += 4 * step) {
+            long long sr[4];
+            float4 y[4], v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long p = p0 + j * step;
+                sr[j] = p < P ? (long long)__ldg(src + p) : -1;
             }
-            s.x += y.x; s.y += y.y; s.z += y.z; s.w += y.w;
-            s2.x = fmaf(y.x, y.x, s2.x); s2.y = fmaf(y.y, y.y, s2.y);
-            s2.z = fmaf(y.z, y.z, s2.z); s2.w = fmaf(y.w, y.w, s2.w);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long p = p0 + j * step;
+                y[j] = sr[j] >= 0 ? ld4(U + sr[j] * C + q * 4) : f4zero();
+                v[j] = (V && sr[j] >= 0) ? ld4(V + (sh >= 0 ? (p >> sh) : p / ns) * C + q * 4) : f4zero();
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (sr[j] < 0) continue;
+                float4 t = y[j];
+                t.x = fmaf(vsign, v[j].x, t.x); t.y = fmaf(vsign, v[j].y, t.y);
+                t.z = fmaf(vsign, v[j].z, t.z); t.w = fmaf(vsign, v[j].w, t.w);
+                s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+                s2.x = fmaf(t.x, t.x, s2.x); s2.y = fmaf(t.y, t.y, s2.y);
+                s2.z = fmaf(t.z, t.z, s2.z); s2.w = fmaf(t.w, t.w, s2.w);
+            }
         }
         atomicAdd(&s_acc[q * 4 + 0], (double)s.x); atomicAdd(&s_acc[q * 4 + 1], (double)s.y);
         atomicAdd(&s_acc[q * 4 + 2], (double)s.z); atomicAdd(&s_acc[q * 4 + 3], (double)s.w);
@@ -454,17 +472,31 @@ __global__ void __launch_bounds__(256) sel_outer_kernel(
     if (slice >= slices) return;
     const int nq = C2 / 4;  // float4 per row; lane handles quads lane, lane+32, ...
     float4 acc[2] = {f4zero(), f4zero()};  // C2 <= 256
-    for (long long gi = slice; gi < G; gi += slices) {
-        const float gv = __ldg(g3s + gi * C3 + c3);
-        if (gv == 0.f) continue;
-        const long long row = gi * ns + __ldg(selpos + gi * C3 + c3);
+    // four groups per iteration: their (gradient, position) loads and then their y2 row gathers are in
+    // flight together (a single group per iteration is a chain of three dependent DRAM round trips)
+    for (long long g0 = slice; g0 < G; g0 += 4LL * slices) {
+        float gv[4];
+        long long row[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long gi = g0 + (long long)j * slices;
+            gv[j] = gi < G ? __ldg(g3s + gi * C3 + c3) : 0.f;
+            row[j] = gi < G ? gi * ns + __ldg(selpos + gi * C3 + c3) : 0;
+        }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const int qd = lane + 32 * i;
             if (qd < nq) {
-                const float4 a2 = bn_act4(ld4(y2 + row * C2 + qd * 4), scale2, shift2, qd * 4, slope);
-                acc[i].x = fmaf(gv, a2.x, acc[i].x); acc[i].y = fmaf(gv, a2.y, acc[i].y);
-                acc[i].z = fmaf(gv, a2.z, acc[i].z); acc[i].w = fmaf(gv, a2.w, acc[i].w);
+                float4 y[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) y[j] = gv[j] != 0.f ? ld4(y2 + row[j] * C2 + qd * 4) : f4zero();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (gv[j] == 0.f) continue;
+                    const float4 a2 = bn_act4(y[j], scale2, shift2, qd * 4, slope);
+                    acc[i].x = fmaf(gv[j], a2.x, acc[i].x); acc[i].y = fmaf(gv[j], a2.y, acc[i].y);
+                    acc[i].z = fmaf(gv[j], a2.z, acc[i].z); acc[i].w = fmaf(gv[j], a2.w, acc[i].w);
+                }
             }
         }
     }

@@ -1,0 +1,8 @@
+"""misc/layers.py of the reference, served by pointcloudlib_b200.misc.layers (same names and signatures);
+module outputs are jittor-compat Vars so the reference's network files can keep calling
+``.transpose(0,3,1,2)``, ``.argmax(dim)[1]`` etc. on them."""
+from pointcloudlib_b200.misc import layers as _src
+
+from ._bridge import export as _export
+
+_export(_src, globals())

@@ -26,187 +26,142 @@ from .. import functional as F
 from .ops import KNN, FurthestPointSampler, Module
 
 
-class STN3d(Module):
+class _TNet(Module):
+    """Shared body of the two PointNet T-Nets (layers.py:11-92): three 1x1 convs k -> 64 -> 128 ->
+    1024, max over the points, three FC layers 1024 -> 512 -> 256 -> k*k, plus the identity.  Attribute
+    names (conv1..3, fc1..3, bn1..5, relu) are the reference's, so state dicts line up."""
+
+    _CONV = (64, 128, 1024)
+    _FC = (512, 256)
+
+    def _build(self, k):
+        self.k = k
+        widths = (k,) + self._CONV
+        for i in range(3):
+            setattr(self, f"conv{i + 1}", nn.Conv1d(widths[i], widths[i + 1], 1))
+        fcs = (self._CONV[-1],) + self._FC + (k * k,)
+        for i in range(3):
+            setattr(self, f"fc{i + 1}", nn.Linear(fcs[i], fcs[i + 1]))
+        self.relu = nn.ReLU()
+        for i, c in enumerate(self._CONV + self._FC):
+            setattr(self, f"bn{i + 1}", nn.BatchNorm1d(c))
+
+    def execute(self, x):
+        for i in (1, 2, 3):
+            x = self.relu(getattr(self, f"bn{i}")(getattr(self, f"conv{i}")(x)))
+        x = torch.max(x, 2).values.reshape(-1, self._CONV[-1])
+        for i in (1, 2):
+            x = self.relu(getattr(self, f"bn{i + 3}")(getattr(self, f"fc{i}")(x)))
+        x = self.fc3(x) + torch.eye(self.k, dtype=x.dtype, device=x.device).reshape(1, self.k * self.k)
+        return x.reshape(-1, self.k, self.k)
+
+
+class STN3d(_TNet):
     """layers.py:11-50: x (B,3,N) -> (B,3,3)."""
 
     def __init__(self):
         super().__init__()
-        self.conv1 = nn.Conv1d(3, 64, 1)
-        self.conv2 = nn.Conv1d(64, 128, 1)
-        self.conv3 = nn.Conv1d(128, 1024, 1)
-        self.fc1 = nn.Linear(1024, 512)
-        self.fc2 = nn.Linear(512, 256)
-        self.fc3 = nn.Linear(256, 9)
-        self.relu = nn.ReLU()
-        self.bn1 = nn.BatchNorm1d(64)
-        self.bn2 = nn.BatchNorm1d(128)
-        self.bn3 = nn.BatchNorm1d(1024)
-        self.bn4 = nn.BatchNorm1d(512)
-        self.bn5 = nn.BatchNorm1d(256)
-
-    def execute(self, x):
-        batchsize = x.shape[0]
-        x = self.relu(self.bn1(self.conv1(x)))
-        x = self.relu(self.bn2(self.conv2(x)))
-        x = self.relu(self.bn3(self.conv3(x)))
-        x = torch.max(x, 2).values
-        x = x.reshape(-1, 1024)
-        x = self.relu(self.bn4(self.fc1(x)))
-        x = self.relu(self.bn5(self.fc2(x)))
-        x = self.fc3(x)
-        iden = torch.eye(3, dtype=x.dtype, device=x.device).reshape(1, 9).repeat(batchsize, 1)
-        x = x + iden
-        return x.reshape(-1, 3, 3)
+        self._build(3)
 
 
-class STNkd(Module):
+class STNkd(_TNet):
     """layers.py:53-92: x (B,k,N) -> (B,k,k)."""
 
     def __init__(self, k=64):
         super().__init__()
-        self.conv1 = nn.Conv1d(k, 64, 1)
-        self.conv2 = nn.Conv1d(64, 128, 1)
-        self.conv3 = nn.Conv1d(128, 1024, 1)
-        self.fc1 = nn.Linear(1024, 512)
-        self.fc2 = nn.Linear(512, 256)
-        self.fc3 = nn.Linear(256, k * k)
-        self.relu = nn.ReLU()
-        self.bn1 = nn.BatchNorm1d(64)
-        self.bn2 = nn.BatchNorm1d(128)
-        self.bn3 = nn.BatchNorm1d(1024)
-        self.bn4 = nn.BatchNorm1d(512)
-        self.bn5 = nn.BatchNorm1d(256)
-        self.k = k
+        self._build(k)
+
+
+class _ChannelsLast(Module):
+    """Run a channels-first layer on a channels-last tensor (layers.py:97-135)."""
+
+    def __init__(self, f, to_first, to_last):
+        super().__init__()
+        self.f = f
+        self._to_first, self._to_last = to_first, to_last
 
     def execute(self, x):
-        x = self.relu(self.bn1(self.conv1(x)))
-        x = self.relu(self.bn2(self.conv2(x)))
-        x = self.relu(self.bn3(self.conv3(x)))
-        x = torch.max(x, 2).values
-        x = x.reshape(-1, 1024)
-        x = self.relu(self.bn4(self.fc1(x)))
-        x = self.relu(self.bn5(self.fc2(x)))
-        x = self.fc3(x)
-        iden = torch.eye(self.k, dtype=x.dtype, device=x.device).reshape(1, self.k * self.k)
-        x = x + iden
-        return x.reshape(-1, self.k, self.k)
+        return self.f(x.permute(*self._to_first)).permute(*self._to_last)
 
 
 def EndChannels(f, make_contiguous=False):
     """layers.py:97-115: apply a 2-D (channels-first) layer to a channels-last (B,P,K,C) tensor."""
-
-    class WrappedLayer(Module):
-        def __init__(self):
-            super().__init__()
-            self.f = f
-
-        def execute(self, x):
-            x = x.permute(0, 3, 1, 2)
-            x = self.f(x)
-            return x.permute(0, 2, 3, 1)
-
-    return WrappedLayer()
+    return _ChannelsLast(f, (0, 3, 1, 2), (0, 2, 3, 1))
 
 
 def EndChannels1d(f, make_contiguous=False):
     """layers.py:117-135: apply a 1-D (channels-first) layer to a channels-last (B,N,C) tensor."""
-
-    class WrappedLayer(Module):
-        def __init__(self):
-            super().__init__()
-            self.f = f
-
-        def execute(self, x):
-            x = x.permute(0, 2, 1)
-            x = self.f(x)
-            return x.permute(0, 2, 1)
-
-    return WrappedLayer()
+    return _ChannelsLast(f, (0, 2, 1), (0, 2, 1))
 
 
-class SepConv(Module):
-    """layers.py:138-176: depthwise-separable conv -> activation -> BatchNorm (in that order)."""
+class _ConvActBn(Module):
+    """conv -> activation -> BatchNorm(momentum 0.9), in THAT order (layers.py:170-176, :206-212)."""
+
+    def _finish(self, out_channels, with_bn, activation):
+        self.activation = activation
+        self.bn = nn.BatchNorm2d(out_channels, momentum=0.9) if with_bn else None
+
+    def execute(self, x):
+        x = self.conv(x)
+        x = self.activation(x) if self.activation else x
+        return self.bn(x) if self.bn else x
+
+
+class SepConv(_ConvActBn):
+    """layers.py:138-176: depthwise (groups = in_channels, x depth_multiplier) then pointwise conv."""
 
     def __init__(self, in_channels, out_channels, kernel_size, depth_multiplier=1, with_bn=True,
                  activation=nn.ReLU()):
         super().__init__()
-        self.conv = nn.Sequential(
-            nn.Conv2d(in_channels, in_channels * depth_multiplier, kernel_size, groups=in_channels),
-            nn.Conv2d(in_channels * depth_multiplier, out_channels, 1, bias=not with_bn),
-        )
-        self.activation = activation
-        self.bn = nn.BatchNorm2d(out_channels, momentum=0.9) if with_bn else None
-
-    def execute(self, x):
-        x = self.conv(x)
-        if self.activation:
-            x = self.activation(x)
-        if self.bn:
-            x = self.bn(x)
-        return x
+        mid = in_channels * depth_multiplier
+        self.conv = nn.Sequential(nn.Conv2d(in_channels, mid, kernel_size, groups=in_channels),
+                                  nn.Conv2d(mid, out_channels, 1, bias=not with_bn))
+        self._finish(out_channels, with_bn, activation)
 
 
-class Conv(Module):
-    """layers.py:179-212: conv -> activation -> BatchNorm (in that order)."""
+class Conv(_ConvActBn):
+    """layers.py:179-212: plain 2-D convolution block."""
 
     def __init__(self, in_channels, out_channels, kernel_size, with_bn=True, activation=nn.ReLU()):
         super().__init__()
         self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, bias=not with_bn)
+        self._finish(out_channels, with_bn, activation)
+
+
+class _Dense(Module):
+    """1x1 conv -> BatchNorm -> activation -> dropout (layers.py:215-270)."""
+
+    def _finish(self, out_features, drop_rate, with_bn, activation, bn_cls):
         self.activation = activation
-        self.bn = nn.BatchNorm2d(out_channels, momentum=0.9) if with_bn else None
+        self.with_bn = with_bn
+        self.drop = nn.Dropout(drop_rate) if drop_rate > 0 else None
+        self.bn = bn_cls(out_features) if with_bn else None
 
     def execute(self, x):
-        x = self.conv(x)
-        if self.activation:
-            x = self.activation(x)
-        if self.bn:
-            x = self.bn(x)
+        x = self.linear(x)
+        for stage in (self.bn if self.with_bn else None, self.activation, self.drop):
+            if stage:
+                x = stage(x)
         return x
 
 
-class Dense_Conv1d(Module):
-    """layers.py:215-242: Conv1d(k=1) -> BatchNorm1d -> activation -> dropout on (B,C,N)."""
+class Dense_Conv1d(_Dense):
+    """layers.py:215-242, on (B,C,N)."""
 
     def __init__(self, in_features, out_features, drop_rate=0, with_bn=True, activation=nn.ReLU()):
         super().__init__()
         self.linear = nn.Conv1d(in_features, out_features, 1)
-        self.activation = activation
-        self.with_bn = with_bn
-        self.drop = nn.Dropout(drop_rate) if drop_rate > 0 else None
-        self.bn = nn.BatchNorm1d(out_features) if with_bn else None
-
-    def execute(self, x):
-        x = self.linear(x)
-        if self.with_bn:
-            x = self.bn(x)
-        if self.activation:
-            x = self.activation(x)
-        if self.drop:
-            x = self.drop(x)
-        return x
+        self._finish(out_features, drop_rate, with_bn, activation, nn.BatchNorm1d)
 
 
-class Dense_Conv2d(Module):
-    """layers.py:244-270: Conv2d(k=1) -> BatchNorm -> activation -> dropout on (B,C,P,K)."""
+class Dense_Conv2d(_Dense):
+    """layers.py:244-270, on (B,C,P,K)."""
 
     def __init__(self, in_features, out_features, drop_rate=0, with_bn=True, activation=nn.ReLU(),
                  groups=1):
         super().__init__()
         self.linear = nn.Conv2d(in_features, out_features, 1, groups=groups)
-        self.activation = activation
-        self.with_bn = with_bn
-        self.drop = nn.Dropout(drop_rate) if drop_rate > 0 else None
-        self.bn = nn.BatchNorm2d(out_features) if with_bn else None
-
-    def execute(self, x):
-        x = self.linear(x)
-        if self.with_bn:
-            x = self.bn(x)
-        if self.activation:
-            x = self.activation(x)
-        if self.drop:
-            x = self.drop(x)
-        return x
+        self._finish(out_features, drop_rate, with_bn, activation, nn.BatchNorm2d)
 
 
 class RandPointCNN_Decoder(Module):

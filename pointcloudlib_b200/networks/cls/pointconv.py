@@ -10,33 +10,36 @@ from ...misc.ops import Module
 from ...misc.pointconv_utils import PointConvDensitySetAbstraction
 
 
+# (npoint, nsample, extra input channels, mlp, KDE bandwidth, group_all) of the three density-SA levels
+_LEVELS = ((512, 32, 0, (64, 64, 128), 0.1, False),
+           (128, 64, 128, (128, 128, 256), 0.2, False),
+           (1, None, 256, (256, 512, 1024), 0.4, True))
+
+
 class PointConvDensityClsSsg(Module):
-    """networks/cls/pointconv.py:8-36."""
+    """networks/cls/pointconv.py:8-36: sa1..sa3 (density set abstraction), then fc1/bn1/drop1,
+    fc2/bn2/drop2, fc3 (attribute names as in the reference)."""
 
     def __init__(self, n_classes=40):
         super().__init__()
-        self.sa1 = PointConvDensitySetAbstraction(npoint=512, nsample=32, in_channel=3,
-                                                  mlp=[64, 64, 128], bandwidth=0.1, group_all=False)
-        self.sa2 = PointConvDensitySetAbstraction(npoint=128, nsample=64, in_channel=128 + 3,
-                                                  mlp=[128, 128, 256], bandwidth=0.2, group_all=False)
-        self.sa3 = PointConvDensitySetAbstraction(npoint=1, nsample=None, in_channel=256 + 3,
-                                                  mlp=[256, 512, 1024], bandwidth=0.4, group_all=True)
-        self.fc1 = nn.Linear(1024, 512)
-        self.bn1 = nn.BatchNorm1d(512)
-        self.drop1 = nn.Dropout(0.4)
-        self.fc2 = nn.Linear(512, 256)
-        self.bn2 = nn.BatchNorm1d(256)
-        self.drop2 = nn.Dropout(0.4)
-        self.fc3 = nn.Linear(256, n_classes)
+        for i, (npoint, nsample, c_extra, mlp, bw, all_) in enumerate(_LEVELS, start=1):
+            setattr(self, f"sa{i}", PointConvDensitySetAbstraction(
+                npoint=npoint, nsample=nsample, in_channel=c_extra + 3, mlp=list(mlp), bandwidth=bw,
+                group_all=all_))
+        widths = (1024, 512, 256)
+        for i in (1, 2):
+            setattr(self, f"fc{i}", nn.Linear(widths[i - 1], widths[i]))
+            setattr(self, f"bn{i}", nn.BatchNorm1d(widths[i]))
+            setattr(self, f"drop{i}", nn.Dropout(0.4))
+        self.fc3 = nn.Linear(widths[-1], n_classes)
         self.relu = nn.ReLU()
 
     def execute(self, xyz):
-        xyz = xyz.permute(0, 2, 1)
-        B, _, _ = xyz.shape
-        l1_xyz, l1_points = self.sa1(xyz, None)
-        l2_xyz, l2_points = self.sa2(l1_xyz, l1_points)
-        l3_xyz, l3_points = self.sa3(l2_xyz, l2_points)
-        x = l3_points.reshape(B, 1024)
-        x = self.drop1(self.relu(self.bn1(self.fc1(x))))
-        x = self.drop2(self.relu(self.bn2(self.fc2(x))))
+        xyz = xyz.permute(0, 2, 1)                      # the model takes (B,N,3), the layers (B,3,N)
+        points = None
+        for sa in (self.sa1, self.sa2, self.sa3):
+            xyz, points = sa(xyz, points)
+        x = points.reshape(points.shape[0], 1024)
+        for i in (1, 2):
+            x = getattr(self, f"drop{i}")(self.relu(getattr(self, f"bn{i}")(getattr(self, f"fc{i}")(x))))
         return self.fc3(x)

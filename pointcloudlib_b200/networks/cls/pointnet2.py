@@ -89,8 +89,28 @@ class PointnetModuleMSG(PointNetModuleBase):
             self.mlps.append(self.build_mlps(mlp, use_xyz))
 
 
+def _fc_head(n_classes: int) -> nn.Sequential:
+    """Linear(no bias) -> BatchNorm1d -> ReLU twice, dropout 0.5, classifier (pointnet2.py:137-146)."""
+    mods, c = [], 1024
+    for width in (512, 256):
+        mods += [nn.Linear(c, width, bias=False), nn.BatchNorm1d(width), nn.ReLU()]
+        c = width
+    return nn.Sequential(*mods, nn.Dropout(0.5), nn.Linear(c, n_classes))
+
+
+# (n_points, radius, n_samples, mlp): the three set-abstraction levels of pointnet2.py:108-135
+_SSG_LEVELS = ((512, 0.2, 64, (3, 64, 64, 128)),
+               (128, 0.4, 64, (128, 128, 128, 256)),
+               (None, None, None, (256, 256, 512, 1024)))
+# (n_points, radii, n_samples, mlps) of the two multi-scale levels, pointnet2.py:165-190
+_MSG_LEVELS = ((512, (0.1, 0.2, 0.4), (16, 32, 128), ((3, 32, 32, 64), (3, 64, 64, 128), (3, 64, 96, 128))),
+               (128, (0.2, 0.4, 0.8), (32, 64, 128),
+                ((320, 64, 64, 128), (320, 128, 128, 256), (320, 128, 128, 256))))
+_MSG_GLOBAL = (128 + 256 + 256, 256, 512, 1024)
+
+
 class PointNet2_cls(Module):
-    """networks/cls/pointnet2.py:100-158."""
+    """networks/cls/pointnet2.py:100-158 (single-scale grouping)."""
 
     def __init__(self, n_classes=40, use_xyz=True):
         super().__init__()
@@ -99,59 +119,24 @@ class PointNet2_cls(Module):
         self.build_model()
 
     def build_model(self):
-        self.pointnet_modules = nn.ModuleList()
-        self.pointnet_modules.append(
-            PointnetModule(n_points=512, radius=0.2, n_samples=64, mlp=[3, 64, 64, 128],
-                           use_xyz=self.use_xyz))
-        self.pointnet_modules.append(
-            PointnetModule(n_points=128, radius=0.4, n_samples=64, mlp=[128, 128, 128, 256],
-                           use_xyz=self.use_xyz))
-        self.pointnet_modules.append(
-            PointnetModule(mlp=[256, 256, 512, 1024], use_xyz=self.use_xyz))
-        self.fc_layer = nn.Sequential(
-            nn.Linear(1024, 512, bias=False),
-            nn.BatchNorm1d(512),
-            nn.ReLU(),
-            nn.Linear(512, 256, bias=False),
-            nn.BatchNorm1d(256),
-            nn.ReLU(),
-            nn.Dropout(0.5),
-            nn.Linear(256, self.n_classes),
-        )
+        self.pointnet_modules = nn.ModuleList(
+            PointnetModule(mlp=list(mlp), n_points=n, radius=r, n_samples=ns, use_xyz=self.use_xyz)
+            for n, r, ns, mlp in _SSG_LEVELS)
+        self.fc_layer = _fc_head(self.n_classes)
 
     def execute(self, xyz, feature):
         for module in self.pointnet_modules:
             xyz, feature = module(xyz, feature)
-        feature = feature.squeeze(dim=1)
-        return self.fc_layer(feature)
+        return self.fc_layer(feature.squeeze(dim=1))
 
 
 class PointNetMSG(PointNet2_cls):
     """networks/cls/pointnet2.py:161-196 — BASELINE.json config 2 (B=32, N=4096, xyz+normal)."""
 
     def build_model(self):
-        super().build_model()
-        self.pointnet_modules = nn.ModuleList()
-        self.pointnet_modules.append(
-            PointnetModuleMSG(
-                n_points=512,
-                radius=[0.1, 0.2, 0.4],
-                n_samples=[16, 32, 128],
-                mlps=[[3, 32, 32, 64], [3, 64, 64, 128], [3, 64, 96, 128]],
-                use_xyz=self.use_xyz,
-            ))
-        input_channels = 64 + 128 + 128
-        self.pointnet_modules.append(
-            PointnetModuleMSG(
-                n_points=128,
-                radius=[0.2, 0.4, 0.8],
-                n_samples=[32, 64, 128],
-                mlps=[
-                    [input_channels, 64, 64, 128],
-                    [input_channels, 128, 128, 256],
-                    [input_channels, 128, 128, 256],
-                ],
-                use_xyz=self.use_xyz,
-            ))
-        self.pointnet_modules.append(
-            PointnetModule(mlp=[128 + 256 + 256, 256, 512, 1024], use_xyz=self.use_xyz))
+        levels = [PointnetModuleMSG(n_points=n, radius=list(radii), n_samples=list(ns),
+                                    mlps=[list(m) for m in mlps], use_xyz=self.use_xyz)
+                  for n, radii, ns, mlps in _MSG_LEVELS]
+        levels.append(PointnetModule(mlp=list(_MSG_GLOBAL), use_xyz=self.use_xyz))
+        self.pointnet_modules = nn.ModuleList(levels)
+        self.fc_layer = _fc_head(self.n_classes)

@@ -10,10 +10,13 @@ MLP + max (x3 SA levels) -> FC head -> label-smoothed CE -> backward -> SGD(mome
 
 One JSON line on rank 0 (see the keys below).  `value` = points/sec with the batch resident in
 HBM; `e2e` = the same step driven from pinned HOST buffers (H2D of xyz/normals/labels and D2H of
-the loss inside the timed region).  `roofline` is quoted on the ball-query+group kernel (the
-kernel BASELINE.json's metric names), timed live with CUDA events on its launch stream inside
-the timed region; `cpu_baseline` is the CPU restatement of the reference path (oracle/) timed on
-this box's host cores on a bounded sample.
+the loss inside the timed region).  Both timed regions replay ONE CUDA graph per step (zero-grad +
+forward + loss + backward; the all-reduce and the SGD kernel follow it).  `roofline` is quoted on the
+dominant own kernel by total time, measured with a CUDA-event pair around every own launch in an
+eager pass of the same step run right after the timed region (events cannot subdivide a graph
+replay); `roofline.ballquery_group` is the stand-alone ball-query+group kernel BASELINE.json's
+metric names, on the config's six shapes; `cpu_baseline` is the CPU restatement of the reference
+path (oracle/) timed on this box's host cores on a bounded sample.
 """
 from __future__ import annotations
 

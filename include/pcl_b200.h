@@ -158,6 +158,11 @@ int pcl_compute_density(const float *xyz, int B, int N, float bandwidth, float *
  *                          (the sparse form of PCL_PRO_G3_A2's one-hot block; tcgen05 cores only,
  *                          ns a power of two <= 128, P % ns == 0)
  */
+/* Field notes: c0 / c1 are the widths of x0 / x1 for PCL_PRO_PLAIN2 only.  For every other prologue
+ * c0 carries opt-in switches of the tcgen05 kernels and must be 0 in production: bit 15 routes the
+ * PCL_EPI_BWD_Y / PCL_EPI_BWD_GATHER epilogues to the warp-specialised kernel too (slower today, kept
+ * for parity testing), bits 16.. are profiling knobs (skip MMA / loads / epilogue; wrong results).
+ * `reserved`, `reserved_f` and, for the fetch epilogues, c1 are overwritten by the library. */
 typedef struct PclRowGemm {
     const float *W, *x0, *x1, *U, *V, *scale, *shift, *mean, *rstd, *bscale, *m1, *m2, *g3s;
     const int32_t *src, *selpos;

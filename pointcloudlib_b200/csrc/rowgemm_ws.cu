@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
                                 if (pb >= a.P) break;
                                 float v[16];
                                 tc_ld16(tbase + blk * 16, v);
-                                if (ns >= 16) {
+                                {   // ns is 16, 32, 64 or 128 (rowgemm_ws_supported)
                                     const int l0 = (int)(pb & (ns - 1));   // offset of this block inside its group
 #pragma unroll
                                     for (int i = 0; i < 16; ++i) {
@@ -398,25 +398,6 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
                                             a.gmax[o] = mx; a.gmin[o] = mn; a.amax[o] = imx; a.amin[o] = imn;
                                         }
                                         mx = -3.402823466e38f; mn = 3.402823466e38f; imx = 0; imn = 0;
-                                    }
-                                } else {   // ns = 8: two groups per block
-#pragma unroll
-                                    for (int gq = 0; gq < 2; ++gq) {
-                                        if (pb + gq * 8 < a.P) {
-                                            mx = -3.402823466e38f; mn = 3.402823466e38f; imx = 0; imn = 0;
-#pragma unroll
-                                            for (int i = 0; i < 8; ++i) {
-                                                const float x = v[gq * 8 + i];
-                                                fs += x;
-                                                fq = fmaf(x, x, fq);
-                                                if (x > mx) { mx = x; imx = i; }
-                                                if (x < mn) { mn = x; imn = i; }
-                                            }
-                                            if (act) {
-                                                const long long o = ((pb + gq * 8) >> sh) * a.N + n;
-                                                a.gmax[o] = mx; a.gmin[o] = mn; a.amax[o] = imx; a.amin[o] = imn;
-                                            }
-                                        }
                                     }
                                 }
                             }
@@ -687,7 +668,7 @@ bool rowgemm_ws_supported(const PclRowGemm &a, int pro, int epi) {
     // gathered epilogue operand: the V term is hoisted per 16-row block
     if (epi == PCL_EPI_BWD_GATHER && a.V != nullptr && (a.reserved < 4 || a.P % a.ns != 0)) return false;
     if (epi == PCL_EPI_MAXMIN_STATS) {
-        if (!(a.ns == 8 || a.ns == 16 || a.ns == 32 || a.ns == 64 || a.ns == 128)) return false;
+        if (!(a.ns == 16 || a.ns == 32 || a.ns == 64 || a.ns == 128)) return false;   // whole 16-row blocks
         if (a.P % a.ns != 0 || a.reserved < 0) return false;
     }
     return a.P >= 1;

@@ -75,6 +75,8 @@ def test_var_reproduces_the_jittor_semantics_the_networks_rely_on(ref_path):
     ("networks.cls.pointconv", "PointConvDensityClsSsg", {"n_classes": 40},
      "pointcloudlib_b200.networks.cls.pointconv"),
     ("networks.cls.pointcnn", "PointCNNcls", {"n_classes": 40}, "pointcloudlib_b200.networks.cls.pointcnn"),
+    ("networks.seg.pointconv_partseg", "PointConvDensity_partseg", {"part_num": 50},
+     "pointcloudlib_b200.networks.seg.pointconv_partseg"),
 ])
 def test_reference_network_files_construct_on_the_shim(ref_path, mod, cls, kwargs, mirror):
     """Same parameter inventory (sorted shapes) as the mirror in pointcloudlib_b200.networks, and the

@@ -68,3 +68,16 @@ def test_flat_bucket_allreduce_world2(tmp_path):
     soft_cross_entropy_loss(model(torch.cat(xs)), torch.cat(ys)).backward()
     flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
     torch.testing.assert_close(avg, flat, rtol=1e-5, atol=1e-6)
+
+
+def test_graph_trainer_never_captures_on_cpu():
+    """Trainer(graph=True) only captures CUDA steps: CPU tensors take the eager path, which stops at the
+    optimizer because the SGD kernel has no CPU fallback (the gradients are already in the bucket)."""
+    from pointcloudlib_b200.train import Trainer
+    model = _make_model()
+    tr = Trainer(model, lr=0.1, graph=True, distributed=False)
+    x, y = _rank_data(0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tr.step(x, labels=y)
+    assert tr._graph is None and tr.graph_error is None
+    assert float(tr.opt.grads.abs().sum()) > 0

@@ -1,6 +1,8 @@
 // rowgemm_ws.cu — warp-specialised, software-pipelined version of the fused row-GEMM
-// (tcgen05 + TMEM, 3xTF32).  Same contract as rowgemm_tc_kernel (rowgemm_tc.cu) for the four hot
-// (prologue, epilogue) pairs of the fused set-abstraction stage; selected with x3 == 3.
+// (tcgen05 + TMEM, 3xTF32).  Same contract as rowgemm_tc_kernel (rowgemm_tc.cu) for the hot
+// (prologue, epilogue) pairs of the fused set-abstraction stage; selected with x3 == 3 where
+// rowgemm_ws_supported() says so (today: the forward layer-2 / layer-3 GEMMs; the two backward
+// epilogues that need an extra operand are opt-in, see the end of this file).
 //
 // Why: rowgemm_tc_kernel runs load -> transform -> MMA -> epilogue in sequence inside a CTA, with
 // the activation loads held in registers one chunk ahead.  A knob decomposition on B200
@@ -8,10 +10,12 @@
 // Here every phase overlaps every other:
 //   * 1 persistent CTA per SM, 17 warps in three roles:
 //       warps 0-7   TRANSFORM: cp.async the raw activation chunk (and the pre-split weights)
-//                   S-1 chunks ahead, straight into the UMMA operand slot it will occupy; when it
+//                   S-2 chunks ahead, straight into the UMMA operand slot it will occupy; when it
 //                   has landed, read it back, apply the prologue math (BatchNorm+ReLU, gather - V,
 //                   BatchNorm backward, routed one-hot), split into TF32 hi/lo and overwrite the
 //                   slot IN PLACE (hi) / fill its twin (lo); fence.proxy.async + mbarrier arrive.
+//                   The stage refilled is the one of chunk c-2 (kLag), never the one just handed
+//                   to the tensor core, so the transform is not tied to the MMA's pace.
 //       warp 16     MMA: one thread issues tcgen05.mma.kind::tf32, commits to the stage-free and
 //                   accumulator-full mbarriers.
 //       warps 8-15  EPILOGUE: tcgen05.ld the finished accumulator and run the epilogue while the
@@ -22,8 +26,10 @@
 //     and in TMEM a LANE is an output channel and a COLUMN is a row: per-channel statistics,
 //     max / min over a group of rows and BatchNorm-backward sums are thread-local scans with no
 //     shared memory, shuffles or barriers, and global stores are 128 B per warp and row.
-//   * K chunks of 16 floats (64-byte rows, UMMA SWIZZLE_64B K-major atoms), 4 stages of 48 KB:
-//     [act hi 256x64B | act lo | W hi 128x64B | W lo]; accumulators 2 x 256 TMEM columns.
+//   * K chunks of 16 floats (64-byte rows, UMMA SWIZZLE_64B K-major atoms), 4 stages of
+//     [act hi 256x64B | act lo | W hi BNx64B | W lo] (32 KB + 2*BN*64 B); the weight rows >= BN are
+//     not staged: the 128-lane read runs into whatever follows and only feeds accumulator lanes that
+//     nobody reads.  Accumulators: 2 x 256 TMEM columns.
 #include "ws_common.cuh"
 
 namespace pcl {

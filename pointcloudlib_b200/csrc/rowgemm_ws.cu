@@ -21,7 +21,7 @@
 //       warps 8-15  EPILOGUE: tcgen05.ld the finished accumulator and run the epilogue while the
 //                   next tile's MMAs fill the other TMEM buffer.
 //   * operand roles are SWAPPED with respect to rowgemm_tc: the weights are the 128-lane A operand
-//     (M = output channels, zero padded to 128), a macro tile of 256 activation rows is the N
+//     (M = output channels, up to 128 lanes), a macro tile of 256 activation rows is the N
 //     dimension.  One staged weight chunk serves 256 rows, one instruction covers 128 x 256 x 8,
 //     and in TMEM a LANE is an output channel and a COLUMN is a row: per-channel statistics,
 //     max / min over a group of rows and BatchNorm-backward sums are thread-local scans with no

@@ -90,3 +90,23 @@ def test_reference_network_files_construct_on_the_shim(ref_path, mod, cls, kwarg
     assert ours, "no compat/misc module found inside the reference network"
     for m in ours:
         assert any(b.__module__.startswith("pointcloudlib_b200.misc") for b in type(m).__mro__)
+
+
+def test_reference_dgcnn_topk_and_knn_run_on_the_shim_and_match_the_mirror(ref_path):
+    """networks/cls/dgcnn.py:11-26 (`topk`: transpose + jt.argsort -> (index, values)) and :52-57 (`knn`,
+    matmul-form distances + topk) are framework-op code: run from the reference file on the CPU through
+    the shim, they must give what the mirror's torch implementation gives."""
+    import jittor as jt
+    jt.flags.use_cuda = 0
+    ref = importlib.import_module("networks.cls.dgcnn")
+    from pointcloudlib_b200.misc import ops as mirror
+    x = torch.from_numpy(np.random.RandomState(3).randn(2, 5, 40).astype(np.float32))
+    for largest in (True, False):
+        v_ref, i_ref = ref.topk(jt.array(x), k=7, dim=2, largest=largest)
+        v_mir, i_mir = mirror.topk(x, k=7, dim=2, largest=largest)
+        assert torch.equal(v_ref.as_subclass(torch.Tensor), v_mir)
+        assert torch.equal(i_ref.as_subclass(torch.Tensor), i_mir)
+    idx_ref = ref.knn(jt.array(x), 6)
+    idx_mir = mirror.knn(x, 6)
+    assert torch.equal(idx_ref.as_subclass(torch.Tensor), idx_mir)
+    assert (idx_mir[:, :, 0] == torch.arange(40)).all()            # every point is its own nearest neighbour

@@ -100,7 +100,7 @@ class _GroupFn(torch.autograd.Function, _GroupBackwardMixin):
                               int(use_xyz), ptr(out), stream(xyz)), "pcl_group")
         ctx.save_for_backward(idx)
         ctx.dims = (B, N, S, ns, C, use_xyz)
-        ctx.needs_feat_grad = feat is not None and feat.requires_grad
+        ctx.needs_feat_grad = feat is not None and ctx.needs_input_grad[2]
         return out
 
     @staticmethod
@@ -129,7 +129,7 @@ class _BallQueryGroupFn(torch.autograd.Function, _GroupBackwardMixin):
                   key=(B, N, S, int(nsample), C, int(use_xyz)))
         ctx.save_for_backward(idx)
         ctx.dims = (B, N, S, nsample, C, use_xyz)
-        ctx.needs_feat_grad = feat is not None and feat.requires_grad
+        ctx.needs_feat_grad = feat is not None and ctx.needs_input_grad[2]
         ctx.mark_non_differentiable(idx, cnt)
         return out, idx, cnt
 

@@ -111,7 +111,7 @@ def pack_weight(w: torch.Tensor, sign: float = 1.0) -> torch.Tensor:
     out = torch.empty((3, N, ld), dtype=torch.float32, device=w.device)
     if not w.is_cuda:
         raise RuntimeError("libpcl_b200 operators need CUDA tensors: there is no CPU fallback")
-    _lib.call("pcl_pack_weight", w.data_ptr(), N, K, w.stride(0), float(sign), ptr(out), stream())
+    _lib.call("pcl_pack_weight", w.data_ptr(), N, K, w.stride(0), float(sign), ptr(out), stream(out))
     return out
 
 
@@ -124,7 +124,7 @@ def rowgemm(pro: int, epi: int, name: str, **kw):
     a, keep = _args(**kw)
     if pro != PRO_PLAIN2:
         a.c0 = (WS_DBG << 16) | (WS_FETCH_EPI << 15)
-    _lib.call("pcl_rowgemm", ctypes.byref(a), pro, epi, int(MODE), stream(), key=(name, pro, epi, a.P, a.K, a.N))
+    _lib.call("pcl_rowgemm", ctypes.byref(a), pro, epi, int(MODE), stream(keep[0]), key=(name, pro, epi, a.P, a.K, a.N))
     return keep
 
 
@@ -135,7 +135,7 @@ def wgrad(pro_l, kw_l, pro_r, kw_r, P, M, N, out, name="wgrad"):
     if WS_DBG and pro_l != PRO_PLAIN2:
         al.c0 = WS_DBG << 16
     _lib.call("pcl_wgrad", ctypes.byref(al), pro_l, ctypes.byref(ar), pro_r, P, M, N, ptr(out),
-              out.stride(0), int(MODE), stream(), key=(name, P, M, N))
+              out.stride(0), int(MODE), stream(out), key=(name, P, M, N))
 
 
 def bn_param(stats, P, bn, C):
@@ -170,6 +170,8 @@ class FusedSAFn(torch.autograd.Function):
     def forward(ctx, xyz, new_xyz, feat, idx, W1, W2, W3, g1, b1, g2, b2, g3, b3, bns, slope):
         _bind()
         dev = xyz.device
+        xyz, new_xyz, idx = _lib.f32(xyz), _lib.f32(new_xyz), _lib.i32(idx)
+        feat = _lib.f32(feat) if feat is not None else None
         B, N, _ = xyz.shape
         S, ns = idx.shape[1], idx.shape[2]
         G, P = B * S, B * S * ns
@@ -348,6 +350,7 @@ class FusedEdgeConvFn(torch.autograd.Function):
     def forward(ctx, x, idx_kmajor, W, gamma, beta, bn, slope):
         _bind()
         dev = x.device
+        x, idx_kmajor = _lib.f32(x), _lib.i32(idx_kmajor)
         B, C, N = x.shape
         k = idx_kmajor.shape[1]
         Co = W.shape[0]

@@ -58,6 +58,13 @@ class PointNetFeaturePropagation(Module):
 
         if S == 1:
             interpolated_points = points2.repeat(1, N, 1)
+        elif S < 3:
+            # ops.py:86-93 with S == 2: `dists[:, :, :3]` keeps the 2 neighbours there are and the weights
+            # renormalise over them (the 3-NN kernel needs S >= 3)
+            dists, idx = torch.sort(square_distance(xyz1, xyz2), dim=-1, stable=True)
+            dist_recip = 1.0 / (dists + 1e-8)
+            weight = dist_recip / dist_recip.sum(dim=2, keepdim=True)
+            interpolated_points = (index_points(points2, idx.int()) * weight.unsqueeze(-1)).sum(dim=2)
         else:
             idx, _dists, weight = F.three_nn(xyz1, xyz2)
             interpolated_points = F.three_interpolate(points2, idx, weight)

@@ -41,8 +41,8 @@ def shared_mlp_rows(h: torch.Tensor, seq: nn.Sequential) -> torch.Tensor:
         w = conv.weight.reshape(conv.weight.shape[0], -1)
         h = TF.linear(h, w, conv.bias)
         if bn is not None:
-            h = TF.batch_norm(h, bn.running_mean, bn.running_var, bn.weight, bn.bias,
-                              bn.training, bn.momentum, bn.eps)
+            # the module itself (running statistics, num_batches_tracked, momentum=None) on (P, C, 1[, 1])
+            h = bn(h.view(h.shape + (1,) * (2 if isinstance(bn, nn.BatchNorm2d) else 1))).view(h.shape)
         if isinstance(act, nn.LeakyReLU):
             h = TF.leaky_relu(h, act.negative_slope)
         elif act is not None:

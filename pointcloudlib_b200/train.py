@@ -75,6 +75,11 @@ class Trainer:
         self.world = dist.get_world_size() if self.distributed else 1
         self.use_graph = bool(graph)
         self.graph_warmup = int(graph_warmup)
+        if self.world > 1:
+            # replicas must start identical whatever the caller seeded: rank 0's parameters and buffers win
+            dist.broadcast(self.opt.params, 0)
+            for b in model.buffers():
+                dist.broadcast(b, 0)
         self._eager_steps = 0
         self._graph = None
         self._static = None
@@ -131,6 +136,10 @@ class Trainer:
                 self._graph = None
                 torch.cuda.synchronize()
                 return self._eager_step(*inputs, labels=labels)
+        if (any(s.shape != t.shape or s.dtype != t.dtype for s, t in zip(self._static[0], inputs))
+                or self._static[1].shape != labels.shape or len(inputs) != len(self._static[0])):
+            # a batch the graph was not captured for (e.g. the last partial batch of an epoch)
+            return self._eager_step(*inputs, labels=labels)
         for s, t in zip(self._static[0], inputs):
             s.copy_(t, non_blocking=True)
         self._static[1].copy_(labels, non_blocking=True)

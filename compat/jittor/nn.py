@@ -55,6 +55,10 @@ class Sequential(Module):
         return self
 
     def __getitem__(self, i):
+        # Jittor: `idx not in self.layers` -> positional, else by key (pointnet2_partseg.py:60-64 indexes
+        # self.mlps with the KEYS of self.groupers.layers)
+        if isinstance(i, str):
+            return self._modules[i]
         return list(self._modules.values())[i]
 
     def __len__(self):
@@ -64,6 +68,14 @@ class Sequential(Module):
         return iter(self._modules.values())
 
     def execute(self, x, *args):
+        from pointcloudlib_b200.lazy import LazyGrouped
+        if isinstance(x, LazyGrouped):
+            # a deferred BallQueryGrouper result: a [Conv1x1 -> BatchNorm -> ReLU] x 3 stack the fused
+            # kernels cover stays deferred (networks/cls/pointnet2.py:54); anything else runs eagerly
+            y = x.apply_mlp(self)
+            if y is not None:
+                return y
+            x = x.materialize()
         for m in self._modules.values():
             x = m(x)
         return x

@@ -79,5 +79,42 @@ def build(force: bool = False) -> str | None:
     return OUT_SO
 
 
+REF_ROOT = "/root/reference"
+SNAPSHOT_DIR = os.path.join(os.path.dirname(_HERE), "baseline", "_ref", "PointCloudLib")
+_SNAPSHOT_FILES = ("misc/layers.py", "misc/ops.py", "misc/pointconv_utils.py", "misc/utils.py",
+                   "networks/cls/pointnet.py", "networks/cls/pointnet2.py", "networks/cls/dgcnn.py",
+                   "networks/cls/pointconv.py", "networks/cls/pointcnn.py",
+                   "networks/seg/pointnet_partseg.py", "networks/seg/pointnet2_partseg.py",
+                   "networks/seg/dgcnn_partseg.py", "networks/seg/pointconv_partseg.py",
+                   "networks/seg/pointcnn_partseg.py")
+
+
+def snapshot() -> str | None:
+    """Place the UNMODIFIED reference network / misc files (a dozen .py files) under the git-ignored
+    baseline/_ref/PointCloudLib/ so they travel to the GPU box with the repo snapshot: the GPU tests
+    import them from there through compat/ (``PCL_REFERENCE``) and check that the reference's own
+    ``networks/**`` run on libpcl_b200.  Nothing is committed; a no-op where /root/reference is absent."""
+    import shutil
+    if not os.path.isdir(os.path.join(REF_ROOT, "networks")):
+        return SNAPSHOT_DIR if os.path.isdir(os.path.join(SNAPSHOT_DIR, "networks")) else None
+    for rel in _SNAPSHOT_FILES:
+        src = os.path.join(REF_ROOT, rel)
+        dst = os.path.join(SNAPSHOT_DIR, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        if os.path.exists(src):
+            shutil.copyfile(src, dst)
+    return SNAPSHOT_DIR
+
+
+def reference_checkout() -> str | None:
+    """Where the reference's python files can be imported from: $PCL_REFERENCE, the build container's
+    /root/reference, or the snapshot made by snapshot()."""
+    for cand in (os.environ.get("PCL_REFERENCE"), REF_ROOT, SNAPSHOT_DIR):
+        if cand and os.path.isdir(os.path.join(cand, "networks")):
+            return cand
+    return None
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
+    print(snapshot())

@@ -216,6 +216,56 @@ def pointconv_sa(mod, xyz, points):
     return new_xyz.permute(0, 2, 1), new_points
 
 
+def _density_conv_tail(mod, B, S, new_points, grouped_xyz_norm, grouped_density):
+    """misc/pointconv_utils.py:384-397 == :307-321 (the two modules share this tail)."""
+    new_points = new_points.permute(0, 3, 2, 1)
+    for i in range(len(mod.mlp_convs)):
+        new_points = mod.relu(mod.mlp_bns[i](mod.mlp_convs[i](new_points)))
+    weights = mod.weightnet(grouped_xyz_norm.permute(0, 3, 2, 1))
+    new_points = new_points * grouped_density.permute(0, 3, 2, 1)
+    new_points = torch.matmul(new_points.permute(0, 3, 1, 2),
+                              weights.permute(0, 3, 2, 1)).reshape(B, S, -1)
+    new_points = mod.linear(new_points)
+    return mod.relu(mod.bn_linear(new_points.permute(0, 2, 1)))
+
+
+def pointconv_interp(mod, xyz1, xyz2, points1, points2):
+    """misc/pointconv_utils.py:274-321 (PointConvDensitySetInterpolation.execute): 3-NN inverse-distance
+    interpolation of points2 onto xyz1 (points1 is permuted at :289 and never used), KDE density ->
+    DensityNet, sample_and_group with npoint = N (FPS over ALL points: a permutation from a random
+    start), shared MLP, weight net, density-weighted (C x ns).(ns x 16) product, Linear + BN + ReLU."""
+    xyz1 = xyz1.permute(0, 2, 1)
+    xyz2 = xyz2.permute(0, 2, 1)
+    points2 = points2.permute(0, 2, 1)
+    B, N, _ = xyz1.shape
+    idx, dist, _w = oracle.three_nn(xyz1.detach().numpy(), xyz2.detach().numpy())
+    idx, dists = _t(idx), _t(dist).to(xyz1.dtype)
+    dist_recip = 1.0 / (dists + 1e-8)
+    weight = dist_recip / torch.sum(dist_recip, dim=2, keepdim=True)
+    interpolated = torch.sum(index_points_t(points2, idx) * weight.view(B, N, 3, 1), dim=2)
+    sq = square_distance_t(xyz1, xyz1)
+    xyz_density = (torch.exp(-sq / (2.0 * mod.bandwidth * mod.bandwidth)) / (2.5 * mod.bandwidth)).mean(dim=-1)
+    density_scale = mod.densitynet(xyz_density)
+    _new_xyz, new_points, grouped_xyz_norm, _, grouped_density = pointconv_sample_and_group(
+        N, mod.nsample, xyz1, interpolated, density_scale.reshape(B, N, 1))
+    return _density_conv_tail(mod, B, N, new_points, grouped_xyz_norm, grouped_density)
+
+
+def pointconv_partseg(model, xyz, cls_label=None):
+    """networks/seg/pointconv_partseg.py:42-63 (cls_label is accepted and ignored there)."""
+    xyz = xyz.permute(0, 2, 1)
+    l1_xyz, l1_points = pointconv_sa(model.sa0, xyz, None)
+    l2_xyz, l2_points = pointconv_sa(model.sa1, l1_xyz, l1_points)
+    l3_xyz, l3_points = pointconv_sa(model.sa2, l2_xyz, l2_points)
+    l4_xyz, l4_points = pointconv_sa(model.sa3, l3_xyz, l3_points)
+    l3_points = pointconv_interp(model.in0, l3_xyz, l4_xyz, l3_points, l4_points)
+    l2_points = pointconv_interp(model.in1, l2_xyz, l3_xyz, l2_points, l3_points)
+    l1_points = pointconv_interp(model.in2, l1_xyz, l2_xyz, l1_points, l2_points)
+    l0_points = pointconv_interp(model.in3, xyz, l1_xyz, xyz, l1_points)
+    x = model.drop1(model.relu(model.bn1(model.fc1(l0_points))))
+    return model.fc3(x).permute(0, 2, 1)
+
+
 def pointconv_cls(model, xyz):
     """networks/cls/pointconv.py:23-34."""
     xyz = xyz.permute(0, 2, 1)

@@ -115,6 +115,7 @@ _in_call = False  # set while call() itself is timing (avoids double records)
 
 
 LAUNCHES = 0          # C-ABI calls that enqueued a kernel (bench.py reads the delta)
+LAUNCH_TAGS = __import__("collections").Counter()   # per entry point and per call-site tag ("sa_l3", ...)
 _timer = None         # active KernelTimer or None
 
 
@@ -148,6 +149,9 @@ def call(name: str, *args, key=None) -> None:
     """Invoke a C-ABI entry point, raise on a non-zero return, time it if a KernelTimer is active."""
     global _in_call
     fn = getattr(lib(), name)
+    LAUNCH_TAGS[name] += 1
+    if key and isinstance(key[0], str):
+        LAUNCH_TAGS[key[0]] += 1
     t = _timer
     if t is not None and (t.only is None or name in t.only):
         e0 = torch.cuda.Event(enable_timing=True)

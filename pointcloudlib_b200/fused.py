@@ -332,7 +332,7 @@ class FusedSAFn(torch.autograd.Function):
 def fused_sa_branch(xyz, new_xyz, feat, idx, seq, slope: float = 0.0):
     """Apply one radius branch's shared MLP + max to the neighbourhoods given by idx (B,S,ns)."""
     convs = [m for m in seq if isinstance(m, (torch.nn.Conv2d, torch.nn.Conv1d))]
-    bns = [m for m in seq if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm1d))]
+    bns = [m for m in seq if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)]
     assert len(convs) == 3 and len(bns) == 3 and all(c.bias is None for c in convs)
     return FusedSAFn.apply(xyz, new_xyz, feat, idx, convs[0].weight, convs[1].weight, convs[2].weight,
                            bns[0].weight, bns[0].bias, bns[1].weight, bns[1].bias, bns[2].weight,

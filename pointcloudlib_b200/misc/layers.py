@@ -3,12 +3,12 @@
 Same class names, constructor arguments and layouts as the reference: the PointNet T-Nets
 (``STN3d`` / ``STNkd``, layers.py:11-92), the channel-last wrappers and dense blocks
 (``EndChannels``, ``EndChannels1d``, ``SepConv``, ``Conv``, ``Dense_Conv1d``, ``Dense_Conv2d``,
-:97-270) and the PointCNN stack (``RandPointCNN_Decoder``, ``RandPointCNN``, ``PointCNN``,
-``XConv``, :273-517).  PointCNN is a CONSUMER of the hot path: its sampling is
-``FurthestPointSampler`` (pcl_fps), its neighbourhoods come from ``KNN(K*D)`` with the dilation
-slice ``[:, 0::D, :]`` (pcl_knn), and ``select_region`` — a per-sample Python loop of fancy-index
-gathers + ``jt.stack`` in the reference (:381-388) — is one pcl_index_points launch whose backward
-is the scatter-add kernel.  The X-conv math itself is plain dense layers (out of scope for kernels).
+:97-270).  The PointCNN stack (``RandPointCNN``, ``PointCNN``, ``XConv``, :273-517) is a CONSUMER of
+the hot path made of plain dense layers: it is NOT re-written here.  compat/
+serves the reference's own misc/layers.py through the jittor shim, with its sampling on
+``FurthestPointSampler`` (pcl_fps), its neighbourhoods on ``KNN(K*D)`` + the dilation slice (pcl_knn),
+and only ``select_region`` — a per-sample Python loop of fancy-index gathers + ``jt.stack`` in the
+reference (:381-388) — replaced by :func:`select_region` below (one gather kernel).
 
 Jittor conventions kept: modules are called as ``m(x)`` -> ``execute(x)``; ``nn.Conv`` is a 2-D
 convolution; ``nn.BatchNorm(momentum=0.9)`` uses Jittor's update ``running += (batch - running) *
@@ -16,14 +16,11 @@ momentum``, which is torch's convention with the same number.
 """
 from __future__ import annotations
 
-import math
-
-import numpy as np
 import torch
 from torch import nn
 
 from .. import functional as F
-from .ops import KNN, FurthestPointSampler, Module
+from .ops import Module
 
 
 class _TNet(Module):
@@ -164,127 +161,10 @@ class Dense_Conv2d(_Dense):
         self._finish(out_features, drop_rate, with_bn, activation, nn.BatchNorm2d)
 
 
-class RandPointCNN_Decoder(Module):
-    """layers.py:273-303: PointCNN onto given representative points, fused with skip features."""
-
-    def __init__(self, C_in, C_out, C_last, dims, K, D, P):
-        super().__init__()
-        self.pointcnn = PointCNN(C_in, C_out, dims, K, D, P)
-        self.P = P
-        self.conv_fuse = EndChannels1d(Dense_Conv1d(C_out + C_last, C_out))
-
-    def execute(self, x_l, x_h):
-        pts_l, fts_l = x_l
-        pts_h, fts_h = x_h
-        rep_pts_fts = self.pointcnn((pts_h, pts_l, fts_l))
-        concat_feature = torch.cat((rep_pts_fts, fts_h), dim=2)
-        rep_pts_fts = self.conv_fuse(concat_feature)
-        return pts_h, rep_pts_fts
-
-
-class RandPointCNN(Module):
-    """layers.py:306-337: representative points by furthest-point sampling (P > 0), then PointCNN."""
-
-    def __init__(self, C_in, C_out, dims, K, D, P):
-        super().__init__()
-        self.pointcnn = PointCNN(C_in, C_out, dims, K, D, P)
-        self.P = P
-        if self.P > 0:
-            self.sampler = FurthestPointSampler(self.P)
-
-    def execute(self, x):
-        pts, fts = x
-        if 0 < self.P < pts.size()[1]:
-            rep_pts = self.sampler(pts)
-        else:
-            rep_pts = pts
-        rep_pts_fts = self.pointcnn((rep_pts, pts, fts))
-        return rep_pts, rep_pts_fts
-
-
-class PointCNN(Module):
-    """layers.py:341-407: KNN(K*D) with dilation D -> regional gather -> XConv."""
-
-    def __init__(self, C_in, C_out, dims, K, D, P):
-        super().__init__()
-        C_mid = C_out // 2 if C_in == 0 else C_out // 4
-        if C_in == 0:
-            depth_multiplier = 4
-        else:
-            depth_multiplier = int(np.ceil(C_out / C_in))
-        self.knn = KNN(K * D)
-        self.dense = EndChannels1d(Dense_Conv1d(C_in, C_out // 2)) if C_in != 0 else None
-        self.x_conv = XConv(C_out // 2 if C_in != 0 else C_in, C_out, dims, K, P, C_mid, depth_multiplier)
-        self.D = D
-        self.K = K
-
-    def select_region(self, pts, pts_idx):
-        """layers.py:381-388: pts (N,x,C), pts_idx (N,P,K) -> (N,P,K,C).  One gather kernel (the
-        reference loops over the batch in Python and stacks)."""
-        return F.index_points(pts.contiguous(), pts_idx.contiguous())
-
-    def execute(self, x):
-        rep_pts, pts, fts = x
-        fts = self.dense(fts) if fts is not None else fts
-        tmp_rep_pts = rep_pts.permute(0, 2, 1).contiguous()
-        tmp_pts = pts.permute(0, 2, 1).contiguous()
-        pts_idx = self.knn(tmp_rep_pts, tmp_pts)          # (N, K*D, P), nearest first
-        pts_idx = pts_idx[:, 0::self.D, :]
-        pts_idx = pts_idx.permute(0, 2, 1)                # (N, P, K)
-        pts_regional = self.select_region(pts, pts_idx)
-        fts_regional = self.select_region(fts, pts_idx) if fts is not None else fts
-        return self.x_conv((rep_pts, pts_regional, fts_regional))
-
-
-class XConv(Module):
-    """layers.py:411-517: convolution over a representative point and its K neighbours."""
-
-    def __init__(self, C_in, C_out, dims, K, P, C_mid, depth_multiplier):
-        super().__init__()
-        self.C_in = C_in
-        self.C_mid = C_mid
-        self.dims = dims
-        self.K = K
-        self.P = P
-        self.dense1 = Dense_Conv2d(dims, C_mid)
-        self.dense2 = Dense_Conv2d(C_mid, C_mid)
-        self.x_trans_0 = Conv(in_channels=dims, out_channels=K * K, kernel_size=(1, K), with_bn=True)
-        self.x_trans_1 = Dense_Conv2d(K * K, K * K, with_bn=True, groups=1)
-        self.x_trans_2 = Dense_Conv2d(K * K, K * K, with_bn=False, activation=None, groups=1)
-        self.end_conv = EndChannels(SepConv(in_channels=C_mid + C_in, out_channels=C_out,
-                                            kernel_size=(1, K), depth_multiplier=depth_multiplier))
-
-    def execute(self, x):
-        rep_pt, pts, fts = x          # (N,P,dims), (N,P,K,dims), (N,P,K,C_in)
-        if fts is not None:
-            assert rep_pt.size()[0] == pts.size()[0] == fts.size()[0]
-            assert rep_pt.size()[1] == pts.size()[1] == fts.size()[1]
-            assert pts.size()[2] == fts.size()[2] == self.K
-            assert fts.size()[3] == self.C_in
-        else:
-            assert rep_pt.size()[0] == pts.size()[0]
-            assert rep_pt.size()[1] == pts.size()[1]
-            assert pts.size()[2] == self.K
-        assert rep_pt.size()[2] == pts.size()[3] == self.dims
-
-        N = pts.size()[0]
-        P = rep_pt.size()[1]
-        p_center = torch.unsqueeze(rep_pt, dim=2)
-        pts_local = pts - p_center.repeat(1, 1, self.K, 1)
-        pts_local = pts_local.permute(0, 3, 1, 2)            # (N, dims, P, K)
-        fts_lifted0 = self.dense1(pts_local)
-        fts_lifted = self.dense2(fts_lifted0)                # (N, C_mid, P, K)
-        fts = fts.permute(0, 3, 1, 2)                        # (layers.py:495 precedes the None test)
-        if fts is None:
-            fts_cat = fts_lifted
-        else:
-            fts_cat = torch.cat((fts_lifted, fts), 1)        # (N, C_mid + C_in, P, K)
-        X_shape = (N, P, self.K, self.K)
-        x = self.x_trans_0(pts_local)
-        x = self.x_trans_1(x)
-        X = self.x_trans_2(x)
-        X = X.permute(0, 2, 3, 1)
-        X = X.reshape(X_shape)
-        fts_cat = fts_cat.permute(0, 2, 3, 1)
-        fts_X = torch.matmul(X, fts_cat)
-        return self.end_conv(fts_X).squeeze(dim=2)
+def select_region(pts, pts_idx):
+    """PointCNN.select_region (layers.py:381-388): pts (N,x,C), pts_idx (N,P,K) -> (N,P,K,C).  The
+    reference loops over the batch in Python (`pts[n][idx,:]` per sample + jt.stack); here it is ONE
+    pcl_index_points launch whose backward is the scatter-add kernel.  compat/misc/layers.py installs it
+    over the reference's method: the PointCNN / XConv stack itself is served by the reference's OWN
+    misc/layers.py (plain dense layers, out of scope for kernels, SURVEY 2.1 #3) through the shim."""
+    return F.index_points(pts.contiguous(), pts_idx.contiguous())

@@ -24,7 +24,7 @@ def _triples(seq: nn.Sequential):
         conv = mods[i]
         i += 1
         bn = None
-        if i < len(mods) and isinstance(mods[i], (nn.BatchNorm1d, nn.BatchNorm2d)):
+        if i < len(mods) and isinstance(mods[i], nn.modules.batchnorm._BatchNorm):
             bn = mods[i]
             i += 1
         act = None
@@ -42,7 +42,7 @@ def shared_mlp_rows(h: torch.Tensor, seq: nn.Sequential) -> torch.Tensor:
         h = TF.linear(h, w, conv.bias)
         if bn is not None:
             # the module itself (running statistics, num_batches_tracked, momentum=None) on (P, C, 1[, 1])
-            h = bn(h.view(h.shape + (1,) * (2 if isinstance(bn, nn.BatchNorm2d) else 1))).view(h.shape)
+            h = bn(h.view(h.shape + ((1,) if isinstance(bn, nn.BatchNorm1d) else (1, 1)))).view(h.shape)
         if isinstance(act, nn.LeakyReLU):
             h = TF.leaky_relu(h, act.negative_slope)
         elif act is not None:
@@ -71,11 +71,12 @@ def sa_branch(grouper, seq: nn.Sequential, new_xyz, xyz, feature) -> torch.Tenso
         if plain and fused.supported(grouper.n_samples, chans, len(tr)):
             idx, _cnt = F.ball_query(new_xyz, xyz, float(str(grouper.radius)), grouper.n_samples)
             return fused.fused_sa_branch(xyz, new_xyz, feature, idx, seq, slope=0.0)
-    return mlp_max(grouper(new_xyz, xyz, feature), seq)
+    # .execute, not __call__: compat's grouper __call__ returns a deferred handle (pointcloudlib_b200.lazy)
+    return mlp_max(grouper.execute(new_xyz, xyz, feature), seq)
 
 
 def mlp_max(grouped: torch.Tensor, seq: nn.Sequential) -> torch.Tensor:
     """grouped (B,S,ns,Cin) -> (B,S,Cout): shared MLP then max over the ns neighbours."""
     B, S, ns, Cin = grouped.shape
     h = shared_mlp_rows(grouped.reshape(B * S * ns, Cin), seq)
-    return h.view(B, S, ns, -1).max(dim=2).values
+    return torch.max(h.view(B, S, ns, -1), dim=2)[0]

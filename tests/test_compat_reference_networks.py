@@ -4,7 +4,8 @@ dense layers only — run on the CPU through the shim; the models that need the 
 with the same parameter inventory as this repo's mirrors (their forward needs libpcl_b200 on a GPU:
 tests/test_models_gpu.py exercises the same modules through the mirrors).
 
-The reference tree exists only in the build container (/root/reference): skipped elsewhere."""
+The checkout is $PCL_REFERENCE, /root/reference (build container) or the git-ignored snapshot
+baseline/_ref/PointCloudLib; tests/test_reference_networks_run.py RUNS the same files end to end."""
 import importlib
 import os
 import sys
@@ -14,9 +15,10 @@ import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF = os.environ.get("PCL_REFERENCE", "/root/reference")
-pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "networks")),
-                                reason="reference checkout not present")
+from oracle import build_ref
+
+REF = build_ref.reference_checkout()
+pytestmark = pytest.mark.skipif(REF is None, reason="reference checkout not present")
 
 
 @pytest.fixture()
@@ -74,7 +76,6 @@ def test_var_reproduces_the_jittor_semantics_the_networks_rely_on(ref_path):
     ("networks.seg.dgcnn_partseg", "DGCNN_partseg", {"part_num": 50}, "pointcloudlib_b200.networks.seg.dgcnn_partseg"),
     ("networks.cls.pointconv", "PointConvDensityClsSsg", {"n_classes": 40},
      "pointcloudlib_b200.networks.cls.pointconv"),
-    ("networks.cls.pointcnn", "PointCNNcls", {"n_classes": 40}, "pointcloudlib_b200.networks.cls.pointcnn"),
     ("networks.seg.pointconv_partseg", "PointConvDensity_partseg", {"part_num": 50},
      "pointcloudlib_b200.networks.seg.pointconv_partseg"),
 ])

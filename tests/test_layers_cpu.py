@@ -1,5 +1,5 @@
-"""misc/layers.py mirror: the dense building blocks (no custom kernels) run on the CPU; the PointCNN
-stack needs the CUDA ops and is covered by tests/test_models_gpu.py."""
+"""misc/layers.py mirror: the dense building blocks (no custom kernels) run on the CPU.  The PointCNN
+stack is the reference's own misc/layers.py served through compat/ (tests/test_reference_networks_run.py)."""
 import torch
 
 from pointcloudlib_b200.misc import layers as L
@@ -32,10 +32,3 @@ def test_dense_blocks_shapes_and_order():
     assert sep(torch.randn(2, 5, 4, 6)).shape == (2, 5, 1, 12)
     e1 = L.EndChannels1d(L.Dense_Conv1d(6, 4)).train()
     assert e1(torch.randn(2, 9, 6)).shape == (2, 9, 4)
-
-
-def test_pointcnn_constructor_matches_reference_channel_rules():
-    m = L.PointCNN(48, 96, 3, 12, 2, 384)                     # C_mid = C_out // 4, depth = ceil(96/48)
-    assert m.x_conv.C_mid == 24 and m.x_conv.C_in == 48 and m.knn.k == 24 and m.D == 2
-    sep = m.x_conv.end_conv.f
-    assert sep.conv[0].out_channels == (24 + 48) * 2

@@ -1,26 +1,32 @@
 #!/usr/bin/env python
-"""bench.py — PointNet++ MSG classification, forward + backward + SGD, points/sec on B200.
+"""bench.py — forward + backward + SGD points/sec of the set-abstraction / EdgeConv hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--workload pointnet2_msg|dgcnn|partseg|pointconv]
 
-Workload = BASELINE.json configs[1]: PointNet++ MSG cls, B=32 clouds x N=4096 points, xyz+normal,
-per GPU (weak scaling: every rank gets its own batch; one flat-bucket NCCL all-reduce per step).
-A step = one pass of the hot path over one synthetic batch: FPS -> ball query + group -> shared
-MLP + max (x3 SA levels) -> FC head -> label-smoothed CE -> backward -> SGD(momentum).
+Default workload = BASELINE.json configs[1]: PointNet++ MSG cls, B=32 clouds x N=4096 points, xyz+normal,
+per GPU (weak scaling: every rank gets its own batch; one flat-bucket NCCL all-reduce per step).  The other
+workloads are configs[2..4] with the same line schema (DGCNN B=32 N=1024 k=20; PointNet++ part-seg B=16
+N=2048; PointConv cls B=32 N=1024).  A step = one pass of the hot path over one synthetic batch: sampling ->
+grouping / kNN -> shared MLP + max -> head -> loss -> backward -> SGD(momentum).
 
-One JSON line on rank 0 (see the keys below).  `value` = points/sec with the batch resident in
-HBM; `e2e` = the same step driven from pinned HOST buffers (H2D of xyz/normals/labels and D2H of
-the loss inside the timed region).  Both timed regions replay ONE CUDA graph per step (zero-grad +
-forward + loss + backward; the all-reduce and the SGD kernel follow it).  `roofline` is quoted on the
-dominant own kernel by total time, measured with a CUDA-event pair around every own launch in an
-eager pass of the same step run right after the timed region (events cannot subdivide a graph
-replay); `roofline.ballquery_group` is the stand-alone ball-query+group kernel BASELINE.json's
-metric names, on the config's six shapes; `cpu_baseline` is the CPU restatement of the reference
-path (oracle/) timed on this box's host cores on a bounded sample.
+One JSON line on rank 0.  `value` = points/sec with the batch resident in HBM; `e2e` = the same step driven
+from pinned HOST buffers (H2D of the inputs and D2H of the loss inside the timed region).  Both timed regions
+replay ONE CUDA graph per step where the workload captures (zero-grad + forward + loss + backward; the
+all-reduce and the SGD kernel follow it).  `roofline` is quoted on the dominant own kernel by total time,
+measured with a CUDA-event pair around every own launch in an eager pass of the same step run right after the
+timed region (events cannot subdivide a graph replay); each kernel is quoted against BOTH ceilings (measured
+HBM copy bandwidth from MEASURED_PEAKS.json; TF32 tensor throughput measured here with a cuBLAS TF32 GEMM)
+and `bound` names the nearer one.  `roofline.ballquery_group` is the stand-alone ball-query+group kernel that
+BASELINE.json's metric names; `reference_kernels_b200` times the reference's OWN CUDA kernels
+(oracle/_ref, compiled from the reference's kernel strings, reference launch configuration) next to the
+replacements at the config's shapes; `cpu_baseline` is the CPU restatement of the reference path (oracle/)
+on this box's host cores at the FULL batch.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -32,12 +38,81 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-B_PER_GPU = 32
-N_POINTS = 4096
-N_CLASSES = 40
-METRIC = "pointnet2_msg_cls_fwd_bwd_points_per_sec"
 UNIT = "points/s"
-WORKLOAD = "PointNet++ MSG cls B=32 N=4096 xyz+normal (BASELINE configs[1]), fwd+bwd+SGD, weak scaling"
+N_CLASSES = 40
+
+
+# --------------------------------------------------------------------------------------------
+# workloads (BASELINE.json configs[1..4])
+# --------------------------------------------------------------------------------------------
+class Workload:
+    def __init__(self, name):
+        self.name = name
+        spec = {
+            "pointnet2_msg": (32, 4096, "pointnet2_msg_cls_fwd_bwd_points_per_sec",
+                              "PointNet++ MSG cls B=32 N=4096 xyz+normal (BASELINE configs[1]), fwd+bwd+SGD, weak scaling"),
+            "dgcnn": (32, 1024, "dgcnn_cls_fwd_bwd_points_per_sec",
+                      "DGCNN cls EdgeConv k=20 B=32 N=1024 (BASELINE configs[2]), fwd+bwd+SGD, weak scaling"),
+            "partseg": (16, 2048, "pointnet2_partseg_fwd_bwd_points_per_sec",
+                        "PointNet++ SSG part-seg B=16 N=2048, 3-NN upsample decoder (BASELINE configs[3]), fwd+bwd+SGD"),
+            "pointconv": (32, 1024, "pointconv_cls_fwd_bwd_points_per_sec",
+                          "PointConv cls B=32 N=1024 density-weighted conv (BASELINE configs[4]), fwd+bwd+SGD"),
+        }[name]
+        self.B, self.N, self.metric, self.desc = spec
+
+    def build_model(self):
+        if self.name == "pointnet2_msg":
+            from pointcloudlib_b200.networks.cls.pointnet2 import PointNetMSG
+            return PointNetMSG(n_classes=N_CLASSES)
+        if self.name == "dgcnn":
+            from pointcloudlib_b200.networks.cls.dgcnn import DGCNN
+            return DGCNN(n_classes=N_CLASSES)
+        if self.name == "partseg":
+            from pointcloudlib_b200.networks.seg.pointnet2_partseg import PointNet2_partseg
+            return PointNet2_partseg(part_num=50)
+        from pointcloudlib_b200.networks.cls.pointconv import PointConvDensityClsSsg
+        return PointConvDensityClsSsg(n_classes=N_CLASSES)
+
+    def batch(self, seed, B=None):
+        """-> (inputs, labels): CPU tensors of one synthetic batch (ModelNet40 / ShapeNetPart shaped)."""
+        import torch
+        from pointcloudlib_b200.synthetic import modelnet_batch
+        B = self.B if B is None else B
+        xyz, nrm, lab = modelnet_batch(B, self.N, seed=seed)
+        if self.name == "pointnet2_msg":
+            return (xyz, nrm), lab
+        if self.name == "dgcnn":
+            return (xyz.permute(0, 2, 1).contiguous(),), lab
+        if self.name == "partseg":
+            g = torch.Generator().manual_seed(seed + 7)
+            onehot = torch.nn.functional.one_hot(torch.randint(0, 16, (B,), generator=g), 16).float()
+            seg = torch.randint(0, 50, (B, self.N), generator=g)
+            return (xyz, xyz.clone(), onehot), seg          # train_partseg.py:110 model(data, data, onehot)
+        return (xyz,), lab
+
+    def loss_fn(self):
+        from pointcloudlib_b200 import train
+        return train.partseg_cross_entropy_loss if self.name == "partseg" else train.soft_cross_entropy_loss
+
+    def oracle_step_fn(self, model, opt, inputs, labels):
+        """CPU restatement of the reference step (oracle/model_oracle.py graphs + torch SGD)."""
+        import torch
+        from oracle import model_oracle as MO
+        graph = {"pointnet2_msg": MO.pointnet2_cls, "dgcnn": MO.dgcnn, "partseg": MO.pointnet2_partseg,
+                 "pointconv": MO.pointconv_cls}[self.name]
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            out = graph(model, *inputs)
+            if self.name == "partseg":
+                loss = torch.nn.functional.cross_entropy(out.permute(0, 2, 1).reshape(-1, out.shape[1]),
+                                                         labels.reshape(-1))
+            else:
+                loss = MO.soft_cross_entropy_loss(out, labels)
+            loss.backward()
+            opt.step()
+            return float(loss.detach())
+        return step
 
 
 def peaks():
@@ -46,6 +121,35 @@ def peaks():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def measure_compute_peaks(dev):
+    """TF32 tensor-core and FP32 FFMA throughput of this GPU, measured the way MEASURED_PEAKS.json measures
+    bf16: torch.matmul 8192^3 (2*N^3 flops), best of 5 after warm-up, CUDA events.  cuBLAS here is the
+    measuring instrument for the ceiling, not part of the product path."""
+    import torch
+    n = 8192
+    a = torch.randn(n, n, device=dev)
+    b = torch.randn(n, n, device=dev)
+    out = {}
+    old = torch.backends.cuda.matmul.allow_tf32
+    try:
+        for key, tf32, reps in (("tf32_tflops", True, 5), ("fp32_tflops", False, 2)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.matmul(a, b)
+            best = float("inf")
+            for _ in range(reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                torch.matmul(a, b)
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            out[key] = 2 * n ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    out["how"] = "torch.matmul fp32 8192^3 with allow_tf32 on / off, best of 5 / 2, CUDA events (burst)"
+    return out
 
 
 class ClockSampler:
@@ -106,58 +210,63 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # CPU restatement of the reference path (oracle/): the cpu_baseline leg and the reference arm
 # --------------------------------------------------------------------------------------------
-def cpu_reference_step_factory(sample_clouds: int):
-    """Returns (step_fn, cores, description).  One step = fwd+loss+bwd+SGD of PointNet++ MSG on
-    `sample_clouds` clouds of N=4096 through oracle/model_oracle.py (C index ops + torch-CPU
-    dense layers in the reference's op order)."""
-    import torch
-    from oracle import model_oracle
-    import oracle as orc
-    from pointcloudlib_b200.networks.cls.pointnet2 import PointNetMSG
-    from pointcloudlib_b200.synthetic import modelnet_batch
+def host_threads() -> int:
+    try:
+        return max(len(os.sched_getaffinity(0)), 1)
+    except Exception:
+        return max(os.cpu_count() or 1, 1)
 
+
+def cpu_reference_step_factory(wl: Workload):
+    """Returns (step_fn, cores, description, clouds).  One step = fwd+loss+bwd+SGD of the workload's network
+    on the FULL per-GPU batch through oracle/model_oracle.py (C index ops with OpenMP + torch-CPU dense layers
+    in the reference's op order).  Thread counts are set explicitly: torchrun exports OMP_NUM_THREADS=1."""
+    import psutil
+    import torch
+    import oracle as orc
+
+    cores = host_threads()
+    torch.set_num_threads(cores)
+    orc.lib()  # build/load outside the timed region
+    orc.set_num_threads(cores)
+    # the reference op order materialises every activation: ~0.6 GB per cloud (fp32, with autograd) at config 2
+    need_gb = {"pointnet2_msg": 0.75, "dgcnn": 0.35, "partseg": 0.3, "pointconv": 0.5}[wl.name] * wl.B
+    clouds = wl.B
+    avail = psutil.virtual_memory().available / 2 ** 30
+    while clouds > 2 and need_gb * clouds / wl.B > 0.5 * avail:
+        clouds //= 2
     torch.manual_seed(0)
-    model = PointNetMSG(n_classes=N_CLASSES)
+    model = wl.build_model()
     model.train()
     opt = torch.optim.SGD(model.parameters(), lr=0.02, momentum=0.9)
-    xyz, normals, labels = modelnet_batch(sample_clouds, N_POINTS, seed=123)
-    orc.lib()  # build/load outside the timed region
-
-    def step():
-        opt.zero_grad(set_to_none=True)
-        logits = model_oracle.pointnet2_cls(model, xyz, normals)
-        loss = model_oracle.soft_cross_entropy_loss(logits, labels)
-        loss.backward()
-        opt.step()
-        return float(loss.detach())
-
-    cores = max(torch.get_num_threads(), orc.num_threads())
-    desc = (f"{sample_clouds} clouds x {N_POINTS} points per step (1/{B_PER_GPU // sample_clouds} of "
-            f"the B=32 batch), CPU restatement of the reference path: oracle C index ops (OpenMP) + "
-            f"torch-CPU Conv/BN/ReLU/max in the reference's op order; Jittor is not installable "
-            f"and its custom ops have no CPU source")
-    return step, cores, desc
+    inputs, labels = wl.batch(seed=123, B=clouds)
+    step = wl.oracle_step_fn(model, opt, inputs, labels)
+    frac = "the full per-GPU batch" if clouds == wl.B else f"{clouds}/{wl.B} of the batch (host memory {avail:.0f} GB)"
+    desc = (f"{clouds} clouds x {wl.N} points per step ({frac}), CPU restatement of the reference path: oracle C "
+            f"index ops (OpenMP, {orc.num_threads()} threads) + torch-CPU Conv/BN/ReLU/max ({torch.get_num_threads()} "
+            f"threads) in the reference's op order; Jittor is not installable and its custom ops have no CPU source")
+    return step, cores, desc, clouds
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, wl: Workload):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sample = 2
-    step, cores, desc = cpu_reference_step_factory(sample)
-    for _ in range(max(args.warmup, 1)):
+    step, cores, desc, clouds = cpu_reference_step_factory(wl)
+    for _ in range(max(min(args.warmup, 2), 1)):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
-    value = sample * N_POINTS * args.steps / dt
+    value = clouds * wl.N * args.steps / dt
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "impl": "reference", "metric": wl.metric, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": desc},
+        "config": {"workload": wl.desc, "sample": desc, "same_config": clouds == wl.B,
+                   "per_gpu_batch": wl.B, "points": wl.N},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -167,34 +276,24 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------------------------
-# the product arm
+# algorithmic cost model of the own kernels
 # --------------------------------------------------------------------------------------------
 def bq_group_bytes(key):
     """ALGORITHMIC bytes of one ball-query+group launch: read xyz+feat once, read the
     centroids, write idx, write the grouped tensor."""
-    B, N, S, ns, C, use_xyz = key
+    B, N, S, ns, C, use_xyz = key[:6]
     W = (3 if use_xyz else 0) + C
     return 4 * (B * N * (3 + C) + 3 * B * S + B * S * ns + B * S * ns * W)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch, from profiles/ws_r01_ncu_full.txt (ncu --set
-# full captures of the same kernels at the same shapes: the P = 2,097,152-row branch of SA1).
-NCU_TRAFFIC = {
-    ("pcl_rowgemm", ("sa_b3", "1", "5", "2097152", "96", "96")): 1033961000 + 765846784,
-    ("pcl_rowgemm", ("sa_b2", "3", "4", "2097152", "96", "64")): 1656425000 + 507462144,
-    ("pcl_rowgemm", ("sa_l3", "1", "2", "2097152", "96", "128")): 805442000 + 33350912,
-    ("pcl_rowgemm", ("sa_l2", "2", "1", "2097152", "64", "96")): 43436000 + 747486976,
-    ("pcl_wgrad", ("sa_gram", "2097152", "96", "97")): 805384000 + 4113920,
-    ("pcl_wgrad", ("sa_dw2", "2097152", "96", "64")): 1860347000 + 4392448,
-}
-
-
 def algorithmic_cost(name, key):
-    """(ALGORITHMIC bytes, flops) of one launch of an own kernel.  Bytes count
-    each HBM-resident operand once (tensors of a few MB that stay in L2 — weights, U/V, per-channel
-    vectors — are left out); flops = 2*P*K*N for the GEMM-shaped kernels."""
+    """(ALGORITHMIC bytes, logical fp32 flops, tensor-issued flops) of one launch of an own kernel.  Bytes
+    count each HBM-resident operand once (tensors of a few MB that stay in L2 — weights, U/V, per-channel
+    vectors — are left out); flops = 2*P*K*N for the GEMM-shaped kernels, issued x3 by the 3xTF32 split."""
+    if not key:
+        return 0, 0, 0
     if name == "pcl_ball_query_group":
-        return bq_group_bytes(key), 0
+        return bq_group_bytes(key), 0, 0
     if name == "pcl_rowgemm":
         tag, pro, epi, P, K, N = key
         by = {"sa_l2": 4 * (P * N + P),                    # write y2, read src
@@ -202,24 +301,119 @@ def algorithmic_cost(name, key):
               "sa_b3": 4 * (P * N + P * N),                # read y2, write dyhat2
               "sa_b2": 4 * (2 * P * K + P * N + P),        # read dyhat2 + y2, write dyhat1, read src
               }.get(tag, 4 * P * (K + N))
-        return by, 2 * P * K * N
+        fl = 2 * P * K * N
+        return by, fl, 3 * fl
     if name == "pcl_wgrad":
         tag, P, M, N = key
         by = {"sa_gram": 4 * P * M, "sa_dw2": 4 * (2 * P * M + P)}.get(tag, 4 * P * (M + N))
-        return by, 2 * P * M * N
+        fl = 2 * P * M * N
+        return by, fl, 3 * fl
     if name == "pcl_sel_outer":
         tag, G, C3, C2 = key
-        return 4 * G * C3 * (C2 + 2), 2 * G * C3 * C2
-    if name == "pcl_gather_bn_backward":
+        return 4 * G * C3 * (C2 + 2), 2 * G * C3 * C2, 0
+    if name in ("pcl_gather_bn_backward", "pcl_gather_bn_backward_routed"):
         tag, P, C1 = key
-        return 4 * (P * C1 + P), 0
-    if name == "pcl_gather_stats":
+        return (4 * (P * C1 + P) if name == "pcl_gather_bn_backward" else 4 * P), 0, 0
+    if name in ("pcl_gather_stats", "pcl_gather_maxmin"):
         tag, P, C1 = key
-        return 4 * P, 0
-    return 0, 0
+        return 4 * P, 0, 0
+    if name == "pcl_knn" and len(key) >= 5:
+        B, C, Nr, Nq, k = key[:5]
+        return 4 * (B * C * (Nq + Nr) + B * k * Nq), 3 * B * Nq * Nr * C, 0
+    if name == "pcl_three_interpolate" and len(key) >= 4:
+        B, N, S, D = key[:4]
+        return 4 * (B * S * D + B * N * D + 6 * B * N), 0, 0
+    if name == "pcl_index_points" and len(key) >= 4:
+        B, N, S, C = key[:4]
+        return 4 * (B * N * C + B * S + B * S * C), 0, 0
+    return 0, 0, 0
 
 
-def run_product_arm(args):
+def load_ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of
+    THIS round (profiles/ncu_traffic_r02.json, written by profiles/tools/ncu_traffic.py from the .ncu-rep);
+    {} when absent — `traffic` is then null rather than a stale number."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def reference_kernels_block(dev, peak):
+    """The reference's OWN CUDA kernels (misc/ops.py:124-234, :291-330, :429-552, compiled unmodified into
+    oracle/_ref/libref_kernels.so, launched with the reference's configuration: grid = B, block =
+    optimal_block(B) threads) timed on this GPU next to the replacements, at the C2 / C3 shapes.  Checker
+    leg: runs after, and outside, every timed product region."""
+    import torch
+    from oracle import build_ref
+    from pointcloudlib_b200 import functional as PF
+    from pointcloudlib_b200.synthetic import modelnet_batch
+    so = build_ref.build()
+    if so is None or not os.path.exists(so):
+        return {"unavailable": "oracle/_ref/libref_kernels.so not built (reference tree absent at build time)"}
+    lib = ctypes.CDLL(so)
+    P, I, Fl = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    lib.ref_fps.argtypes = [P, I, I, I, I, P, P, P]
+    lib.ref_ball_query.argtypes = [P, P, I, I, I, Fl, I, I, P, P, P]
+    lib.ref_knn.argtypes = [P, P, I, I, I, I, I, P, P]
+    st = torch.cuda.current_stream().cuda_stream
+
+    def timeit(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return 1e3 * e0.elapsed_time(e1) / reps
+
+    rows = []
+    xyz = modelnet_batch(32, 4096, seed=1000)[0].to(dev)
+    bs = int(PF.optimal_block(32))
+    temp = torch.empty(32, 4096, device=dev)
+    idx = torch.empty(32, 512, dtype=torch.int32, device=dev)
+    t_ref = timeit(lambda: lib.ref_fps(xyz.data_ptr(), 32, 4096, 512, bs, temp.data_ptr(), idx.data_ptr(), st), 2)
+    t_own = timeit(lambda: PF.furthest_point_sample(xyz, 512), 10)
+    same = bool(torch.equal(idx, PF.furthest_point_sample(xyz, 512)))
+    rows.append({"op": "furthest_point_sample", "shape": "B=32 N=4096 M=512 (C2 SA1)", "reference_us": t_ref,
+                 "own_us": t_own, "speedup": t_ref / t_own, "idx_equal": same, "reference_block": bs})
+    cen1 = PF.gather_xyz(xyz, idx)
+    cen2 = PF.gather_xyz(cen1, PF.furthest_point_sample(cen1, 128))
+    for cen, pts, r, ns, tag in ((cen1, xyz, 0.1, 16, "SA1"), (cen1, xyz, 0.2, 32, "SA1"), (cen1, xyz, 0.4, 128, "SA1"),
+                                 (cen2, cen1, 0.2, 32, "SA2"), (cen2, cen1, 0.4, 64, "SA2"), (cen2, cen1, 0.8, 128, "SA2")):
+        B, S, N = cen.shape[0], cen.shape[1], pts.shape[1]
+        ridx = torch.zeros(B, S, ns, dtype=torch.int32, device=dev)
+        rcnt = torch.zeros(B, S, dtype=torch.int32, device=dev)
+        t_ref = timeit(lambda: lib.ref_ball_query(cen.data_ptr(), pts.data_ptr(), B, N, S, float(r), ns, bs,
+                                                  ridx.data_ptr(), rcnt.data_ptr(), st), 2)
+        t_own = timeit(lambda: PF.ball_query(cen, pts, r, ns), 10)
+        oidx, ocnt = PF.ball_query(cen, pts, r, ns)
+        rows.append({"op": "ball_query", "shape": f"B={B} N={N} S={S} r={r} ns={ns} (C2 {tag})", "reference_us": t_ref,
+                     "own_us": t_own, "speedup": t_ref / t_own,
+                     "idx_equal": bool(torch.equal(ridx, oidx) and torch.equal(rcnt, ocnt)), "reference_block": bs})
+    g = torch.Generator().manual_seed(3)
+    for C in (3, 64, 128):
+        x = (xyz[:, :1024].permute(0, 2, 1).contiguous() if C == 3
+             else torch.randn(32, C, 1024, generator=g).to(dev))
+        tmp = torch.empty(32, 1024, 1024, device=dev)
+        kidx = torch.empty(32, 20, 1024, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        t_ref = timeit(lambda: lib.ref_knn(x.data_ptr(), x.data_ptr(), 32, C, 1024, 1024, 20, tmp.data_ptr(),
+                                           kidx.data_ptr()), 3)
+        t_own = timeit(lambda: PF.knn(x, x, 20), 10)
+        rows.append({"op": "knn", "shape": f"B=32 C={C} N=1024 k=20 (C3)", "reference_us": t_ref, "own_us": t_own,
+                     "speedup": t_ref / t_own, "idx_equal": bool(torch.equal(kidx, PF.knn(x, x, 20)))})
+    return {"what": "the reference's own kernels compiled for sm_100a (oracle/_ref) vs libpcl_b200, CUDA events, "
+                    "same inputs; ball_query rows time the QUERY only on both sides", "rows": rows}
+
+
+# --------------------------------------------------------------------------------------------
+# the product arm
+# --------------------------------------------------------------------------------------------
+def run_product_arm(args, wl: Workload):
     import torch
     import torch.distributed as dist
 
@@ -234,26 +428,23 @@ def run_product_arm(args):
         dist.init_process_group("nccl", device_id=dev)
 
     from pointcloudlib_b200 import _lib
-    from pointcloudlib_b200.networks.cls.pointnet2 import PointNetMSG
-    from pointcloudlib_b200.synthetic import modelnet_batch
     from pointcloudlib_b200.train import Trainer
 
     _lib.lib()
-    torch.manual_seed(0)  # identical initial weights on every rank
-    model = PointNetMSG(n_classes=N_CLASSES).to(dev)
+    torch.manual_seed(0)  # identical initial weights on every rank (Trainer also broadcasts rank 0's)
+    model = wl.build_model().to(dev)
     model.train()
-    # zero-grad + forward + loss + backward replay as ONE CUDA graph; the NCCL all-reduce and the SGD kernel
-    # are launched after it (capturing the all-reduce hung the 2-GPU run on this image, round 1)
-    trainer = Trainer(model, lr=0.02, momentum=0.9, graph=not args.no_graph)
+    trainer = Trainer(model, lr=0.02, momentum=0.9, graph=not args.no_graph, loss_fn=wl.loss_fn(),
+                      overlap_allreduce=not args.no_overlap)
 
     # distinct synthetic batches per rank and per step slot (rotated), resident in HBM
     n_slots = 4
     host, resident = [], []
     for s in range(n_slots):
-        xyz, nrm, lab = modelnet_batch(B_PER_GPU, N_POINTS, seed=1000 * rank + s)
-        host.append((xyz.pin_memory(), nrm.pin_memory(), lab.pin_memory()))
-        resident.append((xyz.to(dev), nrm.to(dev), lab.to(dev)))
-    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+        inputs, lab = wl.batch(seed=1000 * rank + s)
+        host.append((tuple(t.pin_memory() for t in inputs), lab.pin_memory()))
+        resident.append((tuple(t.to(dev) for t in inputs), lab.to(dev)))
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0][0]) + host[0][1].numel() * host[0][1].element_size()
 
     def sync_all():
         torch.cuda.synchronize()
@@ -270,8 +461,8 @@ def run_product_arm(args):
 
     # ---- warm-up (the first 3 steps run eagerly, the 4th captures the CUDA graph) ---------------
     for i in range(max(args.warmup, 3) + (2 if trainer.use_graph else 0)):
-        x, n, l = resident[i % n_slots]
-        trainer.step(x, n, labels=l)
+        x, l = resident[i % n_slots]
+        trainer.step(*x, labels=l)
     sync_all()
     graphed = trainer.use_graph and trainer._graph is not None
 
@@ -281,13 +472,11 @@ def run_product_arm(args):
         sampler.start()
     launches0 = _lib.LAUNCHES
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    timed = ["pcl_rowgemm", "pcl_wgrad", "pcl_sel_outer", "pcl_gather_stats", "pcl_gather_bn_backward",
-             "pcl_ball_query", "pcl_ball_query_group", "pcl_fps", "pcl_group_backward"]
     sync_all()
     ev0.record()
     for i in range(args.steps):
-        x, n, l = resident[i % n_slots]
-        loss = trainer.step(x, n, labels=l)
+        x, l = resident[i % n_slots]
+        loss = trainer.step(*x, labels=l)
     ev1.record()
     sync_all()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
@@ -302,14 +491,14 @@ def run_product_arm(args):
     trainer.use_graph = False
     pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i in range(2):   # the eager path re-grows its allocator pool after the graph capture
-        x, n, l = resident[i % n_slots]
-        trainer.step(x, n, labels=l)
-    with _lib.KernelTimer(only=timed) as kt:
+        x, l = resident[i % n_slots]
+        trainer.step(*x, labels=l)
+    with _lib.KernelTimer() as kt:
         sync_all()
         pe0.record()
         for i in range(prof_steps):
-            x, n, l = resident[i % n_slots]
-            trainer.step(x, n, labels=l)
+            x, l = resident[i % n_slots]
+            trainer.step(*x, labels=l)
         pe1.record()
         sync_all()
     ms_prof = pe0.elapsed_time(pe1)
@@ -321,17 +510,16 @@ def run_product_arm(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        hx, hn, hl = host[i % n_slots]
-        x = hx.to(dev, non_blocking=True)
-        n = hn.to(dev, non_blocking=True)
+        hx, hl = host[i % n_slots]
+        x = tuple(t.to(dev, non_blocking=True) for t in hx)
         l = hl.to(dev, non_blocking=True)
-        loss = trainer.step(x, n, labels=l)
+        loss = trainer.step(*x, labels=l)
         _ = loss.item()  # D2H of the step's result, every step
     e1.record()
     sync_all()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
 
-    points_per_step = world * B_PER_GPU * N_POINTS
+    points_per_step = world * wl.B * wl.N
     value = points_per_step * args.steps / (ms_total * 1e-3)
     e2e_value = points_per_step * args.steps / (ms_e2e * 1e-3)
 
@@ -340,12 +528,15 @@ def run_product_arm(args):
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the ball-query+group kernel (HBM-bound) ---------------------------------
+    # ---- roofline of the own kernels ---------------------------------------------------------
     peak, peak_src = peaks()
+    cpeaks = measure_compute_peaks(dev)
+    tf32_peak = cpeaks["tf32_tflops"]
+    traffic_db = load_ncu_traffic()
     step_us = 1e3 * ms_prof / prof_steps      # the eager, event-instrumented pass
     kernels = []
     for (name, key), (n, mean_ms, tot_ms) in sorted(kernel_stats.items(), key=lambda kv: -kv[1][2]):
-        by, fl = algorithmic_cost(name, key)
+        by, fl, fl_issued = algorithmic_cost(name, key)
         k = {"call": name, "key": [str(x) for x in key] if key else None,
              "launches_per_step": n / prof_steps, "mean_us": 1e3 * mean_ms,
              "share_of_step": 1e3 * tot_ms / prof_steps / step_us}
@@ -353,88 +544,119 @@ def run_product_arm(args):
             k.update({"algorithmic_MB": by / 1e6, "GBps": by / (mean_ms * 1e-3) / 1e9,
                       "hbm_frac": by / (mean_ms * 1e-3) / 1e9 / peak})
         if fl:
-            k["TFLOPs"] = fl / (mean_ms * 1e-3) / 1e12   # logical fp32 flops; the 3xTF32 split issues 3x
-        tr = NCU_TRAFFIC.get((name, tuple(str(x) for x in key) if key else ()))
+            k["TFLOPs"] = fl / (mean_ms * 1e-3) / 1e12          # logical fp32 flops
+        if fl_issued:
+            k["tf32_issued_TFLOPs"] = fl_issued / (mean_ms * 1e-3) / 1e12   # the 3xTF32 split issues 3x
+            k["tensor_frac"] = k["tf32_issued_TFLOPs"] / tf32_peak
+        if by:
+            k["bound"] = "tensor" if k.get("tensor_frac", 0.0) > k["hbm_frac"] else "hbm"
+        tr = traffic_db.get("|".join([name] + (k["key"] or [])))
         if tr:
             k["ncu_dram_traffic_MB"] = tr / 1e6
         kernels.append(k)
-    top = next((k for k in kernels if "GBps" in k), kernels[0])
-    traffic = NCU_TRAFFIC.get((top["call"], tuple(top["key"] or ())))
-    roofline = {"kernel": f"{top['call']} {top['key']}", "bound": "hbm",
-                "achieved": top.get("GBps"), "peak": peak, "unit": "GB/s", "frac": top.get("hbm_frac"),
-                "traffic": traffic, "peak_source": peak_src,
+    top = next((k for k in kernels if "GBps" in k), kernels[0] if kernels else {"call": None, "key": None,
+               "mean_us": None, "share_of_step": None})
+    tensor_bound = top.get("bound") == "tensor"
+    roofline = {"kernel": f"{top['call']} {top['key']}", "bound": "tensor" if tensor_bound else "hbm",
+                "achieved": top.get("tf32_issued_TFLOPs") if tensor_bound else top.get("GBps"),
+                "peak": tf32_peak if tensor_bound else peak, "unit": "TFLOP/s" if tensor_bound else "GB/s",
+                "frac": top.get("tensor_frac") if tensor_bound else top.get("hbm_frac"),
+                "traffic": traffic_db.get("|".join([str(top["call"])] + (top["key"] or []))),
+                "peak_source": peak_src, "hbm_frac": top.get("hbm_frac"), "tensor_frac": top.get("tensor_frac"),
+                "compute_peaks": cpeaks,
                 "algorithmic_bytes_per_launch": int(top.get("algorithmic_MB", 0) * 1e6),
                 "mean_launch_us": top["mean_us"], "share_of_step": top["share_of_step"],
                 "own_kernels_share_of_step": sum(k["share_of_step"] for k in kernels),
                 "instrumented_step_us": step_us,
-                "note": "dominant own kernel by total time; CUDA events on the launch stream around every "
-                        "own launch, in an eager pass of the same step run right after the timed region "
-                        "(the timed region replays one CUDA graph per step, which events cannot "
-                        "subdivide); tcgen05 3xTF32 row-GEMM with fused prologue/epilogue; traffic = "
-                        "dram read+write of the same kernel/shape from the committed ncu --set full "
-                        "capture (profiles/), when one exists for that key",
-                "kernels": kernels[:24]}
+                "note": "dominant own kernel by total time; CUDA events on the launch stream around every own "
+                        "launch, in an eager pass of the same step run right after the timed region (the timed "
+                        "region replays one CUDA graph per step, which events cannot subdivide); every kernel is "
+                        "quoted against the measured HBM copy peak and, for the tcgen05 3xTF32 GEMMs, the TF32 "
+                        "throughput measured here (issued flops = 3x logical); bound = the nearer ceiling; "
+                        "traffic = dram read+write per launch from this round's ncu --set full capture "
+                        "(profiles/ncu_traffic_r02.json) or null",
+                "kernels": kernels[:32]}
 
     # ---- second half of the metric: ball-query+group (unfused BallQueryGrouper kernel) GB/s -----
     # The training step above never materialises the grouped tensor; the reference-facing
-    # BallQueryGrouper module does, through pcl_ball_query_group.  Timed here on the config's own
-    # shapes (SA1: N=4096,S=512,C=3; SA2: N=512,S=128,C=320), CUDA events, 10 launches each,
-    # output tensors (6-700 MB) far larger than L2 for the big cases.
+    # BallQueryGrouper module does, through pcl_ball_query_group.  Timed on config 2's own shapes
+    # (SA1: N=4096,S=512,C=3; SA2: N=512,S=128,C=320), CUDA events, 10 launches each; the three radii of a
+    # level are also timed as ONE multi-radius launch (pcl_ball_query_group_msg: one scan for nested balls).
     from pointcloudlib_b200 import functional as PF
+    from pointcloudlib_b200.synthetic import modelnet_batch
     bq = []
-    xyz0, nrm0, _ = resident[0]
+    xyz0, nrm0, _ = (t.to(dev) for t in modelnet_batch(32, 4096, seed=1000))
     cen1 = PF.gather_xyz(xyz0, PF.furthest_point_sample(xyz0, 512))
     cen2 = PF.gather_xyz(cen1, PF.furthest_point_sample(cen1, 128))
-    feat2 = torch.randn(B_PER_GPU, 512, 320, device=dev)
-    for (cen, pts, feat, r, ns) in [(cen1, xyz0, nrm0, 0.1, 16), (cen1, xyz0, nrm0, 0.2, 32),
-                                    (cen1, xyz0, nrm0, 0.4, 128), (cen2, cen1, feat2, 0.2, 32),
-                                    (cen2, cen1, feat2, 0.4, 64), (cen2, cen1, feat2, 0.8, 128)]:
+    feat2 = torch.randn(32, 512, 320, device=dev)
+
+    def timeit(fn, reps=10):
         for _ in range(3):
-            PF.ball_query_group(cen, pts, feat, r, ns)
+            fn()
         b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         b0.record()
-        for _ in range(10):
-            PF.ball_query_group(cen, pts, feat, r, ns)
+        for _ in range(reps):
+            fn()
         b1.record()
         torch.cuda.synchronize()
-        us = 1e3 * b0.elapsed_time(b1) / 10
-        key = (B_PER_GPU, pts.shape[1], cen.shape[1], ns, feat.shape[2], 1)
-        by = bq_group_bytes(key)
-        bq.append({"B,N,S,ns,C,use_xyz": list(key), "radius": r, "mean_us": us,
-                   "algorithmic_MB": by / 1e6, "GBps": by / us / 1e3, "hbm_frac": by / us / 1e3 / peak})
+        return 1e3 * b0.elapsed_time(b1) / reps
+
+    levels = [(cen1, xyz0, nrm0, (0.1, 0.2, 0.4), (16, 32, 128)), (cen2, cen1, feat2, (0.2, 0.4, 0.8), (32, 64, 128))]
+    for cen, pts, feat, radii, nss in levels:
+        level_bytes = 0
+        for r, ns in zip(radii, nss):
+            us = timeit(lambda: PF.ball_query_group(cen, pts, feat, r, ns))
+            key = (32, pts.shape[1], cen.shape[1], ns, feat.shape[2], 1)
+            by = bq_group_bytes(key)
+            level_bytes += by
+            bq.append({"B,N,S,ns,C,use_xyz": list(key), "radius": r, "mean_us": us,
+                       "algorithmic_MB": by / 1e6, "GBps": by / us / 1e3, "hbm_frac": by / us / 1e3 / peak})
+        if hasattr(PF, "ball_query_group_msg"):
+            us = timeit(lambda: PF.ball_query_group_msg(cen, pts, feat, radii, nss))
+            bq.append({"B,N,S,ns,C,use_xyz": [32, pts.shape[1], cen.shape[1], list(nss), feat.shape[2], 1],
+                       "radius": list(radii), "multi_radius_one_launch": True, "mean_us": us,
+                       "algorithmic_MB": level_bytes / 1e6, "GBps": level_bytes / us / 1e3,
+                       "hbm_frac": level_bytes / us / 1e3 / peak})
     roofline["ballquery_group"] = bq
 
-    # ---- CPU baseline (bounded sample, rank 0, N=1 only) ----------------------------------------
+    ref_kernels = None
     cpu_baseline = None
+    if world == 1:
+        try:
+            ref_kernels = reference_kernels_block(dev, peak)
+        except Exception as e:  # the checker leg must never take the bench line down
+            ref_kernels = {"unavailable": repr(e)}
+    # ---- CPU baseline (bounded sample, rank 0, N=1 only) ----------------------------------------
     if world == 1 and not args.no_cpu_baseline:
-        sample = 2
-        step, cores, desc = cpu_reference_step_factory(sample)
+        step, cores, desc, clouds = cpu_reference_step_factory(wl)
         step()
         t0 = time.perf_counter()
         n_cpu = 0
-        while n_cpu < 2 or (time.perf_counter() - t0 < 10.0 and n_cpu < 20):
+        while n_cpu < 2 or (time.perf_counter() - t0 < 15.0 and n_cpu < 20):
             step()
             n_cpu += 1
         dt = time.perf_counter() - t0
-        cpu_baseline = {"value": sample * N_POINTS * n_cpu / dt, "unit": UNIT, "cores": cores,
-                        "kind": "port", "sample": f"{n_cpu} steps of {desc}"}
+        cpu_baseline = {"value": clouds * wl.N * n_cpu / dt, "unit": UNIT, "cores": cores,
+                        "kind": "port", "sample": f"{n_cpu} steps of {desc}", "same_config": clouds == wl.B}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": wl.metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "per_gpu_batch": B_PER_GPU, "points": N_POINTS,
-                   "global_batch": world * B_PER_GPU, "parallelism": f"dp{world}",
-                   "l2_policy": "per-step working set (>2 GB of activations) exceeds the 126 MB L2; "
+        "config": {"workload": wl.desc, "per_gpu_batch": wl.B, "points": wl.N,
+                   "global_batch": world * wl.B, "parallelism": f"dp{world}",
+                   "l2_policy": "per-step working set (GBs of activations) exceeds the 126 MB L2; "
                                 f"{n_slots} distinct input batches rotated",
                    "optimizer": "SGD momentum 0.9 (one flat-bucket kernel)", "final_loss": final_loss,
-                   "cuda_graph": bool(graphed), "cuda_graph_error": trainer.graph_error},
+                   "cuda_graph": bool(graphed), "cuda_graph_error": trainer.graph_error,
+                   "allreduce": trainer.allreduce_mode},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "roofline": roofline,
+        "reference_kernels_b200": ref_kernels,
         "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line), flush=True)
@@ -449,18 +671,21 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--workload", default="pointnet2_msg", choices=["pointnet2_msg", "dgcnn", "partseg", "pointconv"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly (no CUDA graph)")
+    ap.add_argument("--no-overlap", action="store_true", help="blocking all-reduce after the whole backward")
     args = ap.parse_args()
+    wl = Workload(args.workload)
     if args.impl == "reference":
-        return run_reference_arm(args)
+        return run_reference_arm(args, wl)
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # convenience: re-launch under torchrun (the driver launches torchrun itself)
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port", "29511",
                os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
-    return run_product_arm(args)
+    return run_product_arm(args, wl)
 
 
 if __name__ == "__main__":

@@ -75,6 +75,19 @@ int pcl_group(const float *new_xyz, const float *xyz, const float *feat, const i
 int pcl_ball_query_group(const float *new_xyz, const float *xyz, const float *feat, int B, int N,
                          int S, float radius, int nsample, int C, int use_xyz, int32_t *idx,
                          int32_t *cnt, float *out, void *stream);
+/* pcl_ball_query_msg / pcl_ball_query_group_msg: R (<= 3) calls of BallQueryGrouper that share centroids
+ * and points — the multi-scale levels of networks/cls/pointnet2.py:165-190 call the grouper once per radius
+ * on the same (new_xyz, pointset), ops.py:345-407 — in ONE scan: balls are nested, the squared distance of
+ * ops.py:317 is computed once and compared against the ASCENDING radii; each radius r keeps its own list
+ * idx[r] (B,S,nsamples[r]), cnt[r] (B,S) and, for the group variant, out[r] (B,S,nsamples[r],3+C) with
+ * exactly the contents R separate pcl_ball_query(_group) calls produce.  radii / nsamples are HOST arrays of
+ * R entries; idx / cnt / out are HOST arrays of R device pointers (cnt, and idx in the group variant, may be
+ * NULL or hold NULLs). */
+int pcl_ball_query_msg(const float *new_xyz, const float *xyz, int B, int N, int S, int R, const float *radii,
+                       const int *nsamples, int32_t *const *idx, int32_t *const *cnt, void *stream);
+int pcl_ball_query_group_msg(const float *new_xyz, const float *xyz, const float *feat, int B, int N, int S,
+                             int C, int use_xyz, int R, const float *radii, const int *nsamples,
+                             int32_t *const *idx, int32_t *const *cnt, float *const *out, void *stream);
 /* backward of pcl_group w.r.t. feat: dfeat[b, idx[b,s,l], c] += dout[b,s,l,off+c] (dfeat must be
  * zeroed by the caller); off = use_xyz?3:0. */
 int pcl_group_backward(const float *dout, const int32_t *idx, int B, int N, int S, int ns, int C,

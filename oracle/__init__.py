@@ -61,6 +61,10 @@ def num_threads() -> int:
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n: int) -> None:
+    lib().orc_set_num_threads(int(n))
+
+
 def optimal_block(batch_size: int) -> int:
     return int(lib().orc_optimal_block(int(batch_size)))
 

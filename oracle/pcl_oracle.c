@@ -43,6 +43,15 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* bench.py: torchrun exports OMP_NUM_THREADS=1; the timed CPU arm sets its thread count explicitly */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 static inline float sqdist3(float ax, float ay, float az, float bx, float by, float bz) {
     /* (a-b)^2 summed as nvcc contracts it: mul, fma, fma */
     float dx = ax - bx, dy = ay - by, dz = az - bz;

@@ -32,6 +32,8 @@ _SIGNATURES = {
     "pcl_group": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P],
     "pcl_ball_query_group": [P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, c_int, P, P, P, P],
     "pcl_group_backward": [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P],
+    "pcl_ball_query_msg": [P, P, c_int, c_int, c_int, c_int, P, P, P, P, P],
+    "pcl_ball_query_group_msg": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P],
     "pcl_index_points": [P, P, c_int, c_int, c_int, c_int, P, P],
     "pcl_index_points_backward": [P, P, c_int, c_int, c_int, c_int, P, P],
     "pcl_knn": [P, P, c_int, c_int, c_int, c_int, c_int, P, P],

@@ -13,6 +13,8 @@
 // same warp immediately writes the centroid's ns*(3+C) contiguous output floats with fully
 // coalesced 128 B stores (flat element index -> (row, channel) tracked incrementally, no divides).
 // HBM traffic = read xyz/feat once (L2-resident per cloud), write idx + grouped tensor once.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pcl {
@@ -240,6 +242,18 @@ __global__ void group_backward_kernel(const float *__restrict__ dout,
 
 }  // namespace pcl
 
+namespace pcl {
+// ball_query_msg.cu: the one-scan multi-radius kernel with the CTA-cooperative float4 writer
+bool bq_msg_supported(int B, int N, int S, int C, int use_xyz, int R, const float *radii, const int *ns, bool group);
+int launch_bq_msg(const float *new_xyz, const float *xyz, const float *feat, int B, int N, int S, int C, int use_xyz,
+                  int R, const float *radii, const int *ns, int32_t *const *idx, int32_t *const *cnt,
+                  float *const *out, cudaStream_t st, const char *what);
+static bool legacy_bq() {
+    const char *v = getenv("PCL_BQ_LEGACY");   // A/B timing knob: 1 = the round-1 warp-per-centroid writer
+    return v && v[0] == '1';
+}
+}  // namespace pcl
+
 using namespace pcl;
 
 static int bq_validate(const char *what, const float *new_xyz, const float *xyz, int B, int N,
@@ -256,6 +270,9 @@ extern "C" int pcl_ball_query(const float *new_xyz, const float *xyz, int B, int
     if (int r = bq_validate("pcl_ball_query", new_xyz, xyz, B, N, S, nsample)) return r;
     PCL_REQUIRE(idx, "pcl_ball_query: null idx");
     if (B == 0 || S == 0) return PCL_OK;
+    if (!legacy_bq() && bq_msg_supported(B, N, S, 0, 1, 1, &radius, &nsample, false))
+        return launch_bq_msg(new_xyz, xyz, nullptr, B, N, S, 0, 1, 1, &radius, &nsample, &idx, &cnt, nullptr,
+                             (cudaStream_t)stream, "pcl_ball_query");
     BQArgs a{new_xyz, xyz, nullptr, nullptr, idx, cnt, nullptr, B, N, S, nsample, 0, 1, 0,
              radius * radius};
     return launch_bq<true, false>(a, (cudaStream_t)stream, "pcl_ball_query");
@@ -284,6 +301,9 @@ extern "C" int pcl_ball_query_group(const float *new_xyz, const float *xyz, cons
     PCL_REQUIRE(use_xyz || (feat && C > 0),
                 "pcl_ball_query_group: nothing to group (use_xyz=0, no feature)");
     if (B == 0 || S == 0) return PCL_OK;
+    if (!legacy_bq() && bq_msg_supported(B, N, S, C, use_xyz, 1, &radius, &nsample, true))
+        return launch_bq_msg(new_xyz, xyz, feat, B, N, S, C, use_xyz, 1, &radius, &nsample, &idx, &cnt, &out,
+                             (cudaStream_t)stream, "pcl_ball_query_group");
     BQArgs a{new_xyz, xyz, C > 0 ? feat : nullptr, nullptr, idx, cnt, out, B, N, S, nsample, C,
              use_xyz ? 1 : 0, 0, radius * radius};
     return launch_bq<true, true>(a, (cudaStream_t)stream, "pcl_ball_query_group");

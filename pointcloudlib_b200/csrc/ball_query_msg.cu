@@ -1,0 +1,337 @@
+// ball_query_msg.cu — multi-radius ball query (+ group) in ONE scan, with a CTA-cooperative writer.
+//
+// Replaces R calls of misc/ops.py:289-407 (BallQueryGrouper) that share centroids and points: the
+// multi-scale-grouping levels of networks/cls/pointnet2.py:165-190 call the grouper three times per level
+// (radii .1/.2/.4 and .2/.4/.8) on the same (new_xyz, pointset); the reference scans the N points once per
+// radius per centroid.  Balls around one centroid are NESTED, so one pass over the points serves every
+// radius: the squared distance is computed once (same mul/fma/fma sequence as ops.py:317 -> bit-identical
+// hit sets), compared against the ascending radii, and each radius keeps its own "first nsample hits in
+// index order, padded with the first hit" list.
+//
+// B200 design.
+//   * Points staged once per CTA as float4 (x, y, z, -) in shared memory: ONE 16-byte LDS per point test.
+//   * One WARP per centroid, 128 points per iteration; the ballot of the LARGEST radius gates the others
+//     (a 32-point chunk with no hit in the big ball has none in the small ones), hit slots come from
+//     popc-prefix, no serial loop; the scan stops when every list is full.
+//   * Writer: after the CTA's lists are in shared memory, ALL 256 threads write the CTA's grouped rows as
+//     one flat, 16-byte-aligned float4 stream per radius (a centroid's ns*(3+C) floats are contiguous and
+//     ns % 4 == 0 makes them a whole number of float4s): 16-byte coalesced stores, kU float4s (4*kU
+//     gathers) per thread in flight before the first store — the round-1 writer had one warp per centroid
+//     and 12 loads per lane in flight, i.e. ~6 MB in flight chip-wide, right at Little's law for HBM3e,
+//     and every warp wrote its 165 KB alone (load imbalance across the single wave of CTAs).
+//     (row, channel) of a flat index come from two multiply-high divisions.
+// HBM traffic = read xyz/feat once (L2-resident per cloud), write idx + grouped tensors once.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace pcl {
+
+constexpr int kMR = 3;            // radii per launch
+constexpr int kMThreads = 256, kMWarps = 8;
+
+struct BQMArgs {
+    const float *new_xyz, *xyz, *feat;
+    int32_t *idx[kMR];
+    int32_t *cnt[kMR];
+    float *out[kMR];
+    float r2[kMR];
+    int ns[kMR];
+    unsigned m_per4[kMR];         // ceil(2^32 / (ns*W/4))
+    unsigned m_w;                 // ceil(2^32 / W)
+    int R, B, N, S, C, use_xyz, cpb;
+};
+
+__device__ __forceinline__ float4 lds_f4(const float4 *p) { return *p; }
+
+template <int U>
+__device__ __forceinline__ void write_rows(const BQMArgs &a, int r, int b, int s0, int n_c, const float4 *s_pts,
+                                           const float4 *s_ctr, const int *s_idx) {
+    const int off = a.use_xyz ? 3 : 0;
+    const int W = off + (a.feat ? a.C : 0);
+    const int ns = a.ns[r];
+    const int per4 = ns * W / 4;
+    const int total4 = n_c * per4;
+    float4 *o4 = reinterpret_cast<float4 *>(a.out[r] + ((long long)b * a.S + s0) * ns * W);
+    const float *fb = a.feat ? a.feat + (long long)b * a.N * a.C - off : nullptr;
+    const float *s_pts_f = reinterpret_cast<const float *>(s_pts);
+    const float *s_ctr_f = reinterpret_cast<const float *>(s_ctr);
+    for (int e0 = threadIdx.x; e0 < total4; e0 += kMThreads * U) {
+        float v[U][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + kMThreads * u;
+            if (e < total4) {
+                const int cen = (int)__umulhi((unsigned)e, a.m_per4[r]);
+                const int f = 4 * (e - cen * per4);
+                const int l = (int)__umulhi((unsigned)f, a.m_w);
+                const int c = f - l * W;
+                const int *si = s_idx + cen * ns;
+                const int k0 = si[l], k1 = si[l + 1 < ns ? l + 1 : l];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int cj = c + j, kk = k0;
+                    if (cj >= W) {
+                        cj -= W;
+                        kk = k1;
+                    }
+                    if (cj < off)   // ops.py:401 local_xyz = grouped_xyz - new_xyz
+                        v[u][j] = __fsub_rn(s_pts_f[4 * kk + cj], s_ctr_f[4 * cen + cj]);
+                    else
+                        v[u][j] = __ldg(fb + (long long)kk * a.C + cj);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + kMThreads * u;
+            if (e < total4) o4[e] = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+        }
+    }
+}
+
+// Dynamic smem: float4 pts[N] | float4 ctr[cpb] | int idx[R][cpb*ns_r]
+template <int R, bool GROUP, int U>
+__global__ void __launch_bounds__(kMThreads) ball_query_msg_kernel(const BQMArgs a) {
+    extern __shared__ float4 smem4[];
+    float4 *s_pts = smem4;
+    float4 *s_ctr = smem4 + a.N;
+    int *s_idx[R];
+    {
+        int *p = reinterpret_cast<int *>(s_ctr + a.cpb);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            s_idx[r] = p;
+            p += a.cpb * a.ns[r];
+        }
+    }
+    const int blocks_per_cloud = (a.S + a.cpb - 1) / a.cpb;
+    const int b = blockIdx.x / blocks_per_cloud;
+    const int s0 = (blockIdx.x % blocks_per_cloud) * a.cpb;
+    const int n_c = min(a.cpb, a.S - s0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *pb = a.xyz + (long long)b * a.N * 3;
+    {
+        float *s_pts_f = reinterpret_cast<float *>(s_pts);
+        for (int i = tid; i < 3 * a.N; i += kMThreads) {
+            const int k = i / 3, c = i - 3 * k;
+            s_pts_f[4 * k + c] = __ldg(pb + i);
+        }
+    }
+    __syncthreads();
+
+    for (int cl = warp; cl < n_c; cl += kMWarps) {
+        const long long bs = (long long)b * a.S + s0 + cl;
+        const float cx = __ldg(a.new_xyz + bs * 3 + 0), cy = __ldg(a.new_xyz + bs * 3 + 1),
+                    cz = __ldg(a.new_xyz + bs * 3 + 2);
+        if (lane == 0) s_ctr[cl] = make_float4(cx, cy, cz, 0.f);
+        int cnt[R], first[R];
+        int *sidx[R];
+        bool open = false;   // some list still has room
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            cnt[r] = 0;
+            first[r] = 0;
+            sidx[r] = s_idx[r] + cl * a.ns[r];
+            open = true;
+        }
+        for (int base = 0; base < a.N && open; base += 128) {
+            float d[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = base + 32 * j + lane;
+                d[j] = 3.0e38f;
+                if (k < a.N) {
+                    const float4 p = lds_f4(s_pts + k);
+                    d[j] = sqdist3(cx, cy, cz, p.x, p.y, p.z);   // ops.py:317-320
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                unsigned m = __ballot_sync(0xffffffffu, d[j] < a.r2[R - 1]);   // largest ball gates the rest
+                if (m == 0) continue;
+#pragma unroll
+                for (int r = R - 1; r >= 0; --r) {
+                    const bool hit = d[j] < a.r2[r];                            // strict <, ops.py:320
+                    if (r != R - 1) m = __ballot_sync(0xffffffffu, hit);
+                    if (m == 0) break;                                          // nested: none in the smaller balls
+                    if (cnt[r] < a.ns[r]) {                                     // ops.py:313 loop condition
+                        if (cnt[r] == 0) first[r] = base + 32 * j + __ffs(m) - 1;
+                        const int pos = cnt[r] + __popc(m & ((1u << lane) - 1u));
+                        if (hit && pos < a.ns[r]) sidx[r][pos] = base + 32 * j + lane;
+                        cnt[r] += __popc(m);
+                    }
+                }
+            }
+            open = false;
+#pragma unroll
+            for (int r = 0; r < R; ++r) open |= cnt[r] < a.ns[r];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int ns = a.ns[r];
+            const int c = min(cnt[r], ns);
+            // ops.py:321-324: the first hit pre-fills every slot.  No hit at all: zeros.
+            for (int l = c + lane; l < ns; l += 32) sidx[r][l] = first[r];
+            __syncwarp();
+            if (a.idx[r])
+                for (int l = lane; l < ns; l += 32) a.idx[r][bs * ns + l] = sidx[r][l];
+            if (a.cnt[r] && lane == 0) a.cnt[r][bs] = c;
+        }
+    }
+    if (GROUP) {
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < R; ++r) write_rows<U>(a, r, b, s0, n_c, s_pts, s_ctr, s_idx[r]);
+    }
+}
+
+static unsigned magic_u32(unsigned d) { return (unsigned)((0x100000000ull + d - 1) / d); }
+
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+// Shapes the one-scan kernel covers (else the caller falls back to ball_query.cu, one radius at a time).
+bool bq_msg_supported(int B, int N, int S, int C, int use_xyz, int R, const float *radii, const int *ns, bool group) {
+    if (R < 1 || R > kMR || B < 1 || S < 1 || N < 1) return false;
+    int sum_ns = 0;
+    for (int r = 0; r < R; ++r) {
+        if (ns[r] < 1 || ns[r] > 1024) return false;
+        if (r > 0 && !(radii[r] >= radii[r - 1])) return false;   // ascending radii = nested balls
+        sum_ns += ns[r];
+    }
+    if ((size_t)N * 16 + 8 * (16 + 4 * sum_ns) > 200 * 1024) return false;
+    if (group) {
+        const int W = (use_xyz ? 3 : 0) + C;
+        if (W < 3) return false;                         // one row wrap per float4
+        for (int r = 0; r < R; ++r)
+            if ((ns[r] * W) % 4 != 0) return false;      // whole float4s per centroid
+    }
+    return true;
+}
+
+template <int R, bool GROUP>
+static int launch_msg_r(BQMArgs a, cudaStream_t st, const char *what) {
+    const int W = (a.use_xyz ? 3 : 0) + (a.feat ? a.C : 0);
+    int sum_ns = 0, max_per4 = 1;
+    for (int r = 0; r < R; ++r) {
+        sum_ns += a.ns[r];
+        const int per4 = GROUP ? a.ns[r] * W / 4 : 1;
+        a.m_per4[r] = magic_u32((unsigned)per4);
+        max_per4 = per4 > max_per4 ? per4 : max_per4;
+    }
+    a.m_w = magic_u32((unsigned)(W > 0 ? W : 1));
+    // centroids per CTA: wide rows -> few (the writer is the work, many resident CTAs = many loads in
+    // flight); narrow rows -> 16 (amortise the cloud staging; the scan is the work)
+    int cpb = GROUP ? (W >= 64 ? 4 : 16) : 32;
+    cpb = env_int("PCL_BQ_CPB", cpb);
+    while (cpb > 1 && (long long)a.B * ceil_div(a.S, cpb) < 2 * kNumSMs) cpb >>= 1;
+    // multiply-high division is exact while n < 2^32 / d
+    while (cpb > 1 && (long long)cpb * max_per4 * max_per4 >= (1ll << 32)) cpb >>= 1;
+    auto smem_for = [&](int c) { return (size_t)a.N * 16 + (size_t)c * (16 + 4 * sum_ns); };
+    while (cpb > 1 && smem_for(cpb) > 200 * 1024) cpb >>= 1;
+    if (smem_for(cpb) > 227 * 1024 || (long long)cpb * max_per4 * max_per4 >= (1ll << 32) ||
+        (GROUP && (long long)max_per4 * 4 * W >= (1ll << 32))) {
+        set_error("%s: shape not covered by the one-scan kernel", what);
+        return PCL_ERR_UNSUPPORTED;
+    }
+    a.cpb = cpb;
+    const size_t smem = smem_for(cpb);
+    const int grid = a.B * ceil_div(a.S, cpb);
+    const int U = env_int("PCL_BQ_UNROLL", W >= 64 ? 8 : 4);
+    auto kern = U >= 8 ? ball_query_msg_kernel<R, GROUP, 8> : (U >= 4 ? ball_query_msg_kernel<R, GROUP, 4> : ball_query_msg_kernel<R, GROUP, 2>);
+    if (smem > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+            return (int)e;
+        }
+    }
+    kern<<<grid, kMThreads, smem, st>>>(a);
+    return check_launch(what);
+}
+
+int launch_bq_msg(const float *new_xyz, const float *xyz, const float *feat, int B, int N, int S, int C, int use_xyz,
+                  int R, const float *radii, const int *ns, int32_t *const *idx, int32_t *const *cnt,
+                  float *const *out, cudaStream_t st, const char *what) {
+    BQMArgs a{};
+    a.new_xyz = new_xyz;
+    a.xyz = xyz;
+    a.feat = C > 0 ? feat : nullptr;
+    a.R = R;
+    a.B = B;
+    a.N = N;
+    a.S = S;
+    a.C = C;
+    a.use_xyz = use_xyz ? 1 : 0;
+    for (int r = 0; r < R; ++r) {
+        a.idx[r] = idx ? idx[r] : nullptr;
+        a.cnt[r] = cnt ? cnt[r] : nullptr;
+        a.out[r] = out ? out[r] : nullptr;
+        a.r2[r] = radii[r] * radii[r];   // fp32 product, as the reference's `radius * radius` (ops.py:309)
+        a.ns[r] = ns[r];
+    }
+    const bool group = out != nullptr;
+    switch (R) {
+        case 1: return group ? launch_msg_r<1, true>(a, st, what) : launch_msg_r<1, false>(a, st, what);
+        case 2: return group ? launch_msg_r<2, true>(a, st, what) : launch_msg_r<2, false>(a, st, what);
+        default: return group ? launch_msg_r<3, true>(a, st, what) : launch_msg_r<3, false>(a, st, what);
+    }
+}
+
+}  // namespace pcl
+
+using namespace pcl;
+
+static int msg_validate(const char *what, const float *new_xyz, const float *xyz, int B, int N, int S, int R,
+                        const float *radii, const int *ns) {
+    PCL_REQUIRE(new_xyz && xyz && radii && ns, "%s: null pointer", what);
+    PCL_REQUIRE(R >= 1 && R <= kMR, "%s: %d radii (1..%d supported per launch)", what, R, kMR);
+    PCL_REQUIRE(B >= 0 && N >= 1 && S >= 0, "%s: bad shape B=%d N=%d S=%d", what, B, N, S);
+    for (int r = 0; r < R; ++r) {
+        PCL_REQUIRE(ns[r] >= 1, "%s: nsample[%d]=%d", what, r, ns[r]);
+        PCL_REQUIRE(r == 0 || radii[r] >= radii[r - 1], "%s: radii must be ascending (nested balls)", what);
+    }
+    return PCL_OK;
+}
+
+extern "C" int pcl_ball_query_msg(const float *new_xyz, const float *xyz, int B, int N, int S, int R,
+                                  const float *radii, const int *nsamples, int32_t *const *idx,
+                                  int32_t *const *cnt, void *stream) {
+    if (int rc = msg_validate("pcl_ball_query_msg", new_xyz, xyz, B, N, S, R, radii, nsamples)) return rc;
+    PCL_REQUIRE(idx, "pcl_ball_query_msg: null idx");
+    for (int r = 0; r < R; ++r) PCL_REQUIRE(idx[r], "pcl_ball_query_msg: null idx[%d]", r);
+    if (B == 0 || S == 0) return PCL_OK;
+    if (!bq_msg_supported(B, N, S, 0, 1, R, radii, nsamples, false)) {
+        for (int r = 0; r < R; ++r)   // shapes beyond the one-scan kernel: one radius at a time
+            if (int rc = pcl_ball_query(new_xyz, xyz, B, N, S, radii[r], nsamples[r], idx[r], cnt ? cnt[r] : nullptr, stream))
+                return rc;
+        return PCL_OK;
+    }
+    return launch_bq_msg(new_xyz, xyz, nullptr, B, N, S, 0, 1, R, radii, nsamples, idx, cnt, nullptr,
+                         (cudaStream_t)stream, "pcl_ball_query_msg");
+}
+
+extern "C" int pcl_ball_query_group_msg(const float *new_xyz, const float *xyz, const float *feat, int B, int N,
+                                        int S, int C, int use_xyz, int R, const float *radii, const int *nsamples,
+                                        int32_t *const *idx, int32_t *const *cnt, float *const *out,
+                                        void *stream) {
+    if (int rc = msg_validate("pcl_ball_query_group_msg", new_xyz, xyz, B, N, S, R, radii, nsamples)) return rc;
+    PCL_REQUIRE(out, "pcl_ball_query_group_msg: null out");
+    for (int r = 0; r < R; ++r) PCL_REQUIRE(out[r], "pcl_ball_query_group_msg: null out[%d]", r);
+    PCL_REQUIRE(C >= 0 && (feat || C == 0), "pcl_ball_query_group_msg: feat is null but C=%d", C);
+    PCL_REQUIRE(use_xyz || (feat && C > 0), "pcl_ball_query_group_msg: nothing to group (use_xyz=0, no feature)");
+    if (B == 0 || S == 0) return PCL_OK;
+    if (!bq_msg_supported(B, N, S, C, use_xyz, R, radii, nsamples, true)) {
+        for (int r = 0; r < R; ++r)
+            if (int rc = pcl_ball_query_group(new_xyz, xyz, feat, B, N, S, radii[r], nsamples[r], C, use_xyz,
+                                              idx ? idx[r] : nullptr, cnt ? cnt[r] : nullptr, out[r], stream))
+                return rc;
+        return PCL_OK;
+    }
+    return launch_bq_msg(new_xyz, xyz, feat, B, N, S, C, use_xyz, R, radii, nsamples, idx, cnt, out,
+                         (cudaStream_t)stream, "pcl_ball_query_group_msg");
+}

@@ -138,6 +138,93 @@ class _BallQueryGroupFn(torch.autograd.Function, _GroupBackwardMixin):
         return None, None, _GroupBackwardMixin._backward(ctx, dout), None, None, None
 
 
+def _msg_host_arrays(radii, nsamples):
+    """Ascending-radius order (nested balls) + the host arrays the multi-radius entry points take."""
+    import ctypes
+    order = sorted(range(len(radii)), key=lambda i: float(radii[i]))
+    R = len(order)
+    rad = (ctypes.c_float * R)(*[float(radii[i]) for i in order])
+    nss = (ctypes.c_int * R)(*[int(nsamples[i]) for i in order])
+    return order, R, rad, nss
+
+
+def _ptr_array(tensors):
+    import ctypes
+    return (ctypes.c_void_p * len(tensors))(*[ptr(t) for t in tensors])
+
+
+def ball_query_msg(new_xyz, xyz, radii, nsamples):
+    """R ball queries (misc/ops.py:291-330) sharing centroids and points in ONE scan — the multi-scale
+    levels of networks/cls/pointnet2.py:165-190.  -> [(idx (B,S,ns_r) int32, cnt (B,S) int32)] in the
+    order of `radii`, identical to R separate ball_query calls."""
+    new_xyz, xyz = f32(new_xyz), f32(xyz)
+    B, S, _ = new_xyz.shape
+    N = xyz.shape[1]
+    order, R, rad, nss = _msg_host_arrays(radii, nsamples)
+    idx = [torch.empty((B, S, int(nsamples[i])), dtype=torch.int32, device=xyz.device) for i in order]
+    cnt = [torch.empty((B, S), dtype=torch.int32, device=xyz.device) for _ in order]
+    _lib.call("pcl_ball_query_msg", ptr(new_xyz), ptr(xyz), B, N, S, R, rad, nss, _ptr_array(idx),
+              _ptr_array(cnt), stream(xyz), key=("bq_msg", B, N, S, R))
+    out = [None] * R
+    for j, i in enumerate(order):
+        out[i] = (idx[j], cnt[j])
+    return out
+
+
+class _BallQueryGroupMsgFn(torch.autograd.Function):
+    """R BallQueryGrouper calls (misc/ops.py:345-407) on the same (new_xyz, pointset, feature) in one launch."""
+
+    @staticmethod
+    def forward(ctx, new_xyz, xyz, feat, radii, nsamples, use_xyz):
+        new_xyz, xyz = f32(new_xyz), f32(xyz)
+        B, S, _ = new_xyz.shape
+        N = xyz.shape[1]
+        C = 0
+        if feat is not None:
+            feat = f32(feat)
+            C = feat.shape[2]
+        W = (3 if use_xyz else 0) + C
+        order, R, rad, nss = _msg_host_arrays(radii, nsamples)
+        dev = xyz.device
+        idx = [torch.empty((B, S, int(nsamples[i])), dtype=torch.int32, device=dev) for i in order]
+        cnt = [torch.empty((B, S), dtype=torch.int32, device=dev) for _ in order]
+        out = [torch.empty((B, S, int(nsamples[i]), W), dtype=torch.float32, device=dev) for i in order]
+        _lib.call("pcl_ball_query_group_msg", ptr(new_xyz), ptr(xyz), ptr(feat), B, N, S, C, int(use_xyz), R,
+                  rad, nss, _ptr_array(idx), _ptr_array(cnt), _ptr_array(out), stream(xyz),
+                  key=("bq_group_msg", B, N, S, C, R))
+        inv = [0] * R
+        for j, i in enumerate(order):
+            inv[i] = j
+        idx, out = [idx[inv[i]] for i in range(R)], [out[inv[i]] for i in range(R)]
+        ctx.save_for_backward(*idx)
+        ctx.dims = (B, N, S, [int(n) for n in nsamples], C, use_xyz)
+        ctx.needs_feat_grad = feat is not None and ctx.needs_input_grad[2]
+        ctx.mark_non_differentiable(*idx)
+        return tuple(out) + tuple(idx)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        idx = ctx.saved_tensors
+        B, N, S, nss, C, use_xyz = ctx.dims
+        dfeat = None
+        if C > 0 and ctx.needs_feat_grad:
+            dfeat = torch.zeros((B, N, C), dtype=torch.float32, device=idx[0].device)
+            for r, ix in enumerate(idx):
+                if grads[r] is None:
+                    continue
+                dout = f32(grads[r])
+                check(lib().pcl_group_backward(ptr(dout), ptr(ix), B, N, S, nss[r], C, int(use_xyz),
+                                               ptr(dfeat), stream(dout)), "pcl_group_backward")
+        return None, None, dfeat, None, None, None
+
+
+def ball_query_group_msg(new_xyz, xyz, feat, radii, nsamples, use_xyz: bool = True, return_idx: bool = False):
+    """-> [grouped (B,S,ns_r,3+C)] (and the idx tensors) for every radius, from one scan of the points."""
+    R = len(radii)
+    res = _BallQueryGroupMsgFn.apply(new_xyz, xyz, feat, tuple(radii), tuple(nsamples), bool(use_xyz))
+    return (list(res[:R]), list(res[R:])) if return_idx else list(res[:R])
+
+
 def group(new_xyz, xyz, feat, idx, use_xyz: bool = True):
     return _GroupFn.apply(new_xyz, xyz, feat, idx, bool(use_xyz))
 

@@ -115,6 +115,7 @@ def pack_weight(w: torch.Tensor, sign: float = 1.0) -> torch.Tensor:
     return out
 
 
+DEBUG = None   # tests: a dict that FusedSAFn.forward fills with its routing state (selpos, y2, U, V, src, BN vectors)
 WS_DBG = 0   # profiling knobs of rowgemm_ws.cu (scratch/ws_branch_knobs.py); 0 in production
 WS_FETCH_EPI = 0   # 1: also route the BWD_Y / BWD_GATHER epilogues to rowgemm_ws.cu (slower today)
 
@@ -222,6 +223,8 @@ class FusedSAFn(torch.autograd.Function):
         _lib.call("pcl_maxpool_finalize", ptr(gmax), ptr(gmin), ptr(amax), ptr(amin), ptr(sc3), ptr(sh3),
                   float(slope), G, C3, ptr(out), ptr(ysel), ptr(selpos), stream())
 
+        if DEBUG is not None:
+            DEBUG.update(selpos=selpos, y2=y2, U=U, V=V, src=src, sc1=sc1, sh1=sh1, sc2=sc2, sh2=sh2, out=out)
         ctx.save_for_backward(xyz_r, feat_r if feat_r is not None else xyz_r, nxyz_r, src, U, V, y2,
                               W1m, W2m, W3m, sc1, sh1, mu1, rs1, sc2, sh2, mu2, rs2, sc3, mu3, rs3,
                               out, ysel, selpos)

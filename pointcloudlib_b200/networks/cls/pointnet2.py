@@ -13,7 +13,7 @@ import torch
 from torch import nn
 
 from ...misc.ops import BallQueryGrouper, FurthestPointSampler, GroupAll, Module
-from ...sa import sa_branch
+from ...sa import sa_branches
 
 
 class PointNetModuleBase(Module):
@@ -48,10 +48,8 @@ class PointNetModuleBase(Module):
         else:
             new_xyz = None
 
-        new_feature_list = []
-        for i, grouper in enumerate(self.groupers):
-            # grouper -> transpose -> mlps -> transpose -> argmax(dim=2)[1]  (pointnet2.py:51-57)
-            new_feature_list.append(sa_branch(grouper, self.mlps[i], new_xyz, xyz, feature))
+        # per grouper: grouper -> transpose -> mlps -> transpose -> argmax(dim=2)[1]  (pointnet2.py:51-57)
+        new_feature_list = sa_branches(self.groupers, self.mlps, new_xyz, xyz, feature)
         new_feature = torch.cat(new_feature_list, dim=-1)
         return new_xyz, new_feature
 

@@ -53,6 +53,39 @@ def shared_mlp_rows(h: torch.Tensor, seq: nn.Sequential) -> torch.Tensor:
 FUSED = os.environ.get("PCL_FUSED", "1") != "0"
 
 
+def _fusable(grouper, seq, xyz):
+    from . import fused
+    from .misc.ops import BallQueryGrouper
+    if not (FUSED and isinstance(grouper, BallQueryGrouper) and grouper.use_xyz and xyz.is_cuda):
+        return False
+    tr = _triples(seq)
+    plain = all(c.bias is None and b is not None and b.training and isinstance(a, nn.ReLU) for c, b, a in tr)
+    return plain and fused.supported(grouper.n_samples, [c.weight.shape[0] for c, _, _ in tr], len(tr))
+
+
+def sa_branches(groupers, mlps, new_xyz, xyz, feature):
+    """Every (grouper, shared MLP) branch of one set-abstraction module -> [(B, S, Cout_i)].  The radius
+    branches of a multi-scale level share centroids and points (networks/cls/pointnet2.py:165-190): their
+    ball queries run as ONE scan of the points (pcl_ball_query_msg, nested balls), three at a time."""
+    from . import functional as F
+    from . import fused
+    groupers, mlps = list(groupers), list(mlps)
+    outs = [None] * len(groupers)
+    fus = [i for i, (g, m) in enumerate(zip(groupers, mlps)) if _fusable(g, m, xyz)]
+    for j in range(0, len(fus), 3):
+        chunk = fus[j:j + 3]
+        if len(chunk) == 1:
+            continue                                  # a single radius: sa_branch below
+        res = F.ball_query_msg(new_xyz, xyz, [float(str(groupers[i].radius)) for i in chunk],
+                               [groupers[i].n_samples for i in chunk])
+        for i, (idx, _cnt) in zip(chunk, res):
+            outs[i] = fused.fused_sa_branch(xyz, new_xyz, feature, idx, mlps[i], slope=0.0)
+    for i, (g, m) in enumerate(zip(groupers, mlps)):
+        if outs[i] is None:
+            outs[i] = sa_branch(g, m, new_xyz, xyz, feature)
+    return outs
+
+
 def sa_branch(grouper, seq: nn.Sequential, new_xyz, xyz, feature) -> torch.Tensor:
     """One (grouper, shared MLP) branch of a set-abstraction module -> (B, S, Cout).
 
@@ -61,16 +94,10 @@ def sa_branch(grouper, seq: nn.Sequential, new_xyz, xyz, feature) -> torch.Tenso
     materialised); anything else goes grouper -> mlp_max, the reference's own sequence."""
     from . import functional as F
     from . import fused
-    from .misc.ops import BallQueryGrouper
 
-    if FUSED and isinstance(grouper, BallQueryGrouper) and grouper.use_xyz and xyz.is_cuda:
-        tr = _triples(seq)
-        chans = [c.weight.shape[0] for c, _, _ in tr]
-        plain = all(c.bias is None and b is not None and b.training and isinstance(a, nn.ReLU)
-                    for c, b, a in tr)
-        if plain and fused.supported(grouper.n_samples, chans, len(tr)):
-            idx, _cnt = F.ball_query(new_xyz, xyz, float(str(grouper.radius)), grouper.n_samples)
-            return fused.fused_sa_branch(xyz, new_xyz, feature, idx, seq, slope=0.0)
+    if _fusable(grouper, seq, xyz):
+        idx, _cnt = F.ball_query(new_xyz, xyz, float(str(grouper.radius)), grouper.n_samples)
+        return fused.fused_sa_branch(xyz, new_xyz, feature, idx, seq, slope=0.0)
     # .execute, not __call__: compat's grouper __call__ returns a deferred handle (pointcloudlib_b200.lazy)
     return mlp_max(grouper.execute(new_xyz, xyz, feature), seq)
 

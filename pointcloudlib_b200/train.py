@@ -15,6 +15,12 @@ import torch.nn.functional as TF
 from . import functional as F
 
 
+def partseg_cross_entropy_loss(seg_pred, seg):
+    """train_partseg.py:111-114: seg_pred (B, part_num, N) -> permute -> cross entropy over B*N points."""
+    n_part = seg_pred.shape[1]
+    return TF.cross_entropy(seg_pred.permute(0, 2, 1).reshape(-1, n_part), seg.reshape(-1).long())
+
+
 def soft_cross_entropy_loss(output, target, smoothing: bool = True):
     """train_cls.py:31-51 without the per-sample host loop: label smoothing eps = 0.2."""
     target = target.view(-1).long()
@@ -58,18 +64,28 @@ class FlatSGD:
 
 
 class Trainer:
-    """One fwd + loss + bwd + (all-reduce) + SGD step of a classification network.
+    """One fwd + loss + bwd + (all-reduce) + SGD step of a classification / segmentation network.
 
     graph=True captures zero-grad + forward + loss + backward (about a thousand kernel launches, ours
     and torch's) in ONE CUDA graph after `graph_warmup` eager steps and replays it from then on: inputs
     are copied into static buffers, gradients land in the flat bucket, BatchNorm running statistics are
-    updated in place by the replay.  The gradient all-reduce and the SGD kernel are launched after the
-    replay, outside the graph (a captured NCCL all-reduce hung the 2-GPU run on this image).  The
-    returned loss tensor is a static buffer, overwritten by the next step."""
+    updated in place by the replay.  The SGD kernel is launched after the replay.
+
+    Data-parallel exchange (world > 1).  The flat gradient bucket is split into two contiguous regions in
+    parameter order: the HEAD region (the first ~5 % of the parameters: the first set-abstraction / EdgeConv
+    level, whose gradients are the LAST to be produced by backward) and the TAIL region (everything else,
+    ~95 % of the bytes, complete as soon as the second level's backward has run).  With
+    overlap_allreduce=True a post-accumulate-grad hook on the tail's parameters records a CUDA event when
+    the last of them has its gradient — inside a captured graph that is an EXTERNAL event-record node — and
+    the step launches the tail's NCCL all-reduce on a side stream gated on that event, so it runs over NVLink
+    while the first level's backward (the largest part of the step) is still executing; only the head
+    region's all-reduce (tens of KB: launch latency) follows the backward.  NCCL itself stays outside the
+    graph: eager collectives on a side stream need no capture support and cannot deadlock the replay."""
 
     def __init__(self, model, lr=0.02, momentum=0.9, weight_decay=0.0, distributed=None, graph=False,
-                 graph_warmup=3):
+                 graph_warmup=3, loss_fn=None, overlap_allreduce=True, head_fraction=0.05):
         self.model = model
+        self.loss_fn = loss_fn if loss_fn is not None else soft_cross_entropy_loss
         self.opt = FlatSGD(model, lr, momentum, weight_decay)
         self.distributed = dist.is_initialized() if distributed is None else distributed
         self.world = dist.get_world_size() if self.distributed else 1
@@ -85,19 +101,84 @@ class Trainer:
         self._static = None
         self.graph_launches = 0     # own C-ABI launches captured in the graph (per step)
         self.graph_error = None
-
-    def reduce_gradients(self) -> float:
-        """Data-parallel exchange: ONE all-reduce (SUM) of the flat gradient bucket; returns the
-        scale (1/world) the optimizer applies.  The operators are per-cloud, so this is the only
-        collective of a step (NCCL over NVLink / NVSwitch on GPUs, gloo in the CPU tests)."""
+        self.allreduce_mode = "none (1 rank)"
+        self._split = 0             # element offset between the head and tail regions of the bucket
+        self._tail_pending = 0
         if self.world > 1:
-            dist.all_reduce(self.opt.grads)
+            self.allreduce_mode = "one blocking all-reduce of the flat bucket after backward"
+            if overlap_allreduce:
+                self._setup_overlap(head_fraction)
+
+    # ---- bucketed, overlapped all-reduce -------------------------------------------------------
+    def _setup_overlap(self, head_fraction):
+        ps = [p for p in self.model.parameters() if p.requires_grad]
+        cum, k = 0, 0
+        while k < len(ps) - 1 and cum + ps[k].numel() <= head_fraction * self.opt.numel:
+            cum += ps[k].numel()
+            k += 1
+        if k == 0 or k == len(ps):
+            return
+        self._split = cum
+        self._tail_params = ps[k:]
+        self._tail_total = len(self._tail_params)
+        cuda = self.opt.params.is_cuda
+        self._side = torch.cuda.Stream() if cuda else None
+        self._ev_eager = torch.cuda.Event() if cuda else None
+        self._ev_graph = torch.cuda.Event(external=True) if cuda else None
+        self._tail_fired = False
+        for p in self._tail_params:
+            p.register_post_accumulate_grad_hook(self._tail_hook)
+        self.allreduce_mode = (f"2 buckets: tail {self.opt.numel - cum} floats all-reduced on a side stream as soon as "
+                               f"its last gradient lands (event-gated, overlaps the first level's backward), "
+                               f"head {cum} floats after backward")
+
+    def _tail_hook(self, _p):
+        self._tail_pending -= 1
+        if self._tail_pending == 0:
+            self._record_tail_ready()
+
+    def _record_tail_ready(self):
+        self._tail_fired = True
+        if self._ev_eager is None:
+            return
+        if torch.cuda.is_current_stream_capturing():
+            self._ev_graph.record()        # external event-record node inside the captured backward
+        else:
+            self._ev_eager.record()
+
+    def _arm(self):
+        self._tail_pending = getattr(self, "_tail_total", 0)
+        self._tail_fired = False
+
+    def reduce_gradients(self, replayed: bool = False) -> float:
+        """Data-parallel exchange of the flat gradient bucket (SUM); returns the scale (1/world) the
+        optimizer applies.  The operators are per-cloud, so this is the only collective of a step (NCCL
+        over NVLink / NVSwitch on GPUs, gloo in the CPU tests)."""
+        if self.world == 1:
+            return 1.0
+        g = self.opt.grads
+        if self._split == 0:
+            dist.all_reduce(g)
+            return 1.0 / self.world
+        head, tail = g[:self._split], g[self._split:]
+        if self._side is not None:
+            if not replayed and not self._tail_fired:      # a tail parameter took no part in this step
+                self._ev_eager.record()
+            self._side.wait_event(self._ev_graph if replayed else self._ev_eager)
+            with torch.cuda.stream(self._side):
+                w_tail = dist.all_reduce(tail, async_op=True)
+        else:
+            w_tail = dist.all_reduce(tail, async_op=True)
+        w_head = dist.all_reduce(head, async_op=True)
+        w_tail.wait()
+        w_head.wait()
         return 1.0 / self.world
 
     def _fwd_bwd(self, *inputs, labels):
         self.opt.zero_grad()
+        self._arm()
         logits = self.model(*inputs)
-        loss = soft_cross_entropy_loss(logits, labels)
+        loss = self.loss_fn(logits, labels)
         loss.backward()
         return loss.detach()
 
@@ -118,6 +199,8 @@ class Trainer:
         # thread_local: other threads (NCCL watchdog, clock sampler) may touch CUDA during the capture
         with torch.cuda.graph(g, capture_error_mode="thread_local"):
             self._static_loss = self._fwd_bwd(*self._static[0], labels=self._static[1])
+            if self._split and not self._tail_fired:
+                self._ev_graph.record()
         self.graph_launches = _lib.LAUNCHES - n0
         self._graph = g
 
@@ -144,5 +227,5 @@ class Trainer:
             s.copy_(t, non_blocking=True)
         self._static[1].copy_(labels, non_blocking=True)
         self._graph.replay()
-        self.opt.step(grad_scale=self.reduce_gradients())
+        self.opt.step(grad_scale=self.reduce_gradients(replayed=True))
         return self._static_loss

@@ -31,13 +31,19 @@ def _rank_data(rank):
     return torch.randn(8, 6, generator=g), torch.randint(0, 5, (8,), generator=g)
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, head_fraction=0.05):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from pointcloudlib_b200.train import Trainer, soft_cross_entropy_loss
     model = _make_model()
-    tr = Trainer(model, lr=0.1)
+    if rank == 1:          # a replica seeded differently: Trainer must broadcast rank 0's parameters
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(1.0)
+    tr = Trainer(model, lr=0.1, head_fraction=head_fraction)
     assert tr.world == world and tr.distributed
+    assert (tr._split > 0) == (head_fraction > 0.5), tr.allreduce_mode
+    torch.testing.assert_close(tr.opt.params, torch.cat([p.reshape(-1) for p in _make_model().parameters()]))
     # every parameter and gradient is a view of the flat buckets
     for p in model.parameters():
         lo, hi = tr.opt.params.data_ptr(), tr.opt.params.data_ptr() + 4 * tr.opt.numel
@@ -45,7 +51,9 @@ def _worker(rank, world, port, out_dir):
         assert tr.opt.grads.data_ptr() <= p.grad.data_ptr() < tr.opt.grads.data_ptr() + 4 * tr.opt.numel
     x, y = _rank_data(rank)
     tr.opt.zero_grad()
+    tr._arm()
     soft_cross_entropy_loss(model(x), y).backward()
+    assert tr._split == 0 or tr._tail_fired          # the tail region's last gradient hook ran during backward
     local = tr.opt.grads.clone()
     scale = tr.reduce_gradients()
     torch.save({"local": local, "reduced": tr.opt.grads.clone() * scale}, f"{out_dir}/r{rank}.pt")
@@ -54,9 +62,10 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_flat_bucket_allreduce_world2(tmp_path):
+@pytest.mark.parametrize("head_fraction", [0.05, 0.6])     # one blocking all-reduce | head + tail buckets
+def test_flat_bucket_allreduce_world2(tmp_path, head_fraction):
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), head_fraction), nprocs=world, join=True)
     r = [torch.load(f"{tmp_path}/r{i}.pt") for i in range(world)]
     avg = (r[0]["local"] + r[1]["local"]) / 2
     for i in range(world):

@@ -159,3 +159,141 @@ def test_fused_edgeconv_matches_reference_sequence(B, C, N, k, Co):
     for (n, p), (_, q) in zip(seq_d.named_parameters(), ref_seq.named_parameters()):
         assert _rel(p.grad, q.grad) <= 5e-3, f"{n}: rel-L2 {_rel(p.grad, q.grad):.3e}"
     assert _rel(xd.grad, x64.grad) <= 5e-3
+
+
+def _graph64(x, Ws, gammas, betas, G, ns, masks=None, sel=None, mask_out=None, eps=1e-5):
+    """The reference stage in float64 row form (Conv1x1 -> BatchNorm(train, biased variance) -> ReLU, x3,
+    max over the ns rows of a group).  With masks / sel / mask_out given, every DISCRETE decision (the two
+    hidden ReLU masks, the row each (group, channel) maximum is routed to, the output ReLU mask) is forced
+    to the given one instead of being taken from the float64 activations."""
+    h, zs = x, []
+    for l in range(3):
+        y = h @ Ws[l].t()
+        mu, var = y.mean(0), y.var(0, unbiased=False)
+        z = (y - mu) / torch.sqrt(var + eps) * gammas[l] + betas[l]
+        zs.append(z)
+        if l < 2:
+            h = z * masks[l] if masks is not None else torch.relu(z)
+    z3 = zs[2].view(G, ns, -1)
+    if sel is None:
+        return torch.relu(z3).max(dim=1).values, zs
+    return z3.gather(1, sel.view(G, 1, -1)).squeeze(1) * mask_out, zs
+
+
+def test_routing_flips_account_for_the_gradient_gap():
+    """Why model-level gradient tolerances are 2e-2 and not north_star's 1e-3: ReLU and max route
+    gradients DISCRETELY, and fp32 vs float64 activations disagree on a handful of near-tied routes.
+    This test (i) counts the routes on which the fused fp32 path and the float64 reference graph
+    disagree and checks each is a genuine near-tie in float64; (ii) re-evaluates the float64 graph with
+    the discrete decisions forced to the GPU path's and requires every gradient to agree to 1e-3
+    relative L2 — i.e. with the routing held equal the float arithmetic meets the north_star bound, and
+    the whole residual of the free comparison is routing."""
+    B, N, S, r, ns, C, chans = 8, 2048, 256, 0.3, 64, 3, (64, 96, 128)
+    xyz, nrm, _ = modelnet_batch(B, N, seed=77)
+    seq = _mlp(chans, 3 + C).train()
+    grouper = BallQueryGrouper(r, ns, True)
+    fidx = oracle.fps(xyz.numpy(), S)
+    new_xyz = torch.from_numpy(oracle.index_points(xyz.numpy(), fidx))
+    ridx, _ = oracle.ball_query(new_xyz.numpy(), xyz.numpy(), float(str(r)), ns)
+    G, P = B * S, B * S * ns
+
+    seq_d = copy.deepcopy(seq).to(DEV)
+    fd = nrm.to(DEV).requires_grad_(True)
+    fused.DEBUG = {}
+    try:
+        out = sa.sa_branch(grouper, seq_d, new_xyz.to(DEV), xyz.to(DEV), fd)
+        dbg = {k: v.detach().cpu() for k, v in fused.DEBUG.items()}
+    finally:
+        fused.DEBUG = None
+    gen = torch.Generator().manual_seed(9)
+    gout = torch.randn(out.shape, generator=gen)
+    out.backward(gout.to(DEV))
+
+    # the GPU path's discrete decisions, from its own saved state
+    y1 = dbg["U"][dbg["src"].long()] - dbg["V"].repeat_interleave(ns, dim=0)
+    mask1 = (dbg["sc1"] * y1 + dbg["sh1"] > 0).double()
+    mask2 = (dbg["sc2"] * dbg["y2"] + dbg["sh2"] > 0).double()
+    sel = dbg["selpos"].long()
+    mask_out = (dbg["out"] > 0).double()
+
+    def leaves():
+        Ws = [m.weight.detach().double().reshape(m.weight.shape[0], -1).requires_grad_(True)
+              for m in seq if isinstance(m, nn.Conv2d)]
+        gs = [m.weight.detach().double().requires_grad_(True) for m in seq if isinstance(m, nn.BatchNorm2d)]
+        bs = [m.bias.detach().double().requires_grad_(True) for m in seq if isinstance(m, nn.BatchNorm2d)]
+        f = nrm.double().requires_grad_(True)
+        grouped = torch.from_numpy(oracle.group(new_xyz.numpy(), xyz.numpy(), nrm.numpy(), ridx)).double()
+        bi = torch.arange(B).view(B, 1, 1).expand(B, S, ns)
+        x = torch.cat([grouped[..., :3], f[bi, torch.from_numpy(ridx).long()]], dim=-1).reshape(P, 3 + C)
+        return x, Ws, gs, bs, f
+
+    # (a) the free float64 graph: its own routing
+    x, Ws, gs, bs, f = leaves()
+    ref, zs = _graph64(x, Ws, gs, bs, G, ns)
+    ref.backward(gout.double().reshape(G, -1))
+    free = [t.grad.clone() for t in Ws + gs + bs + [f]]
+    flips1 = ((zs[0].detach() > 0).double() != mask1)
+    flips2 = ((zs[1].detach() > 0).double() != mask2)
+    z3 = zs[2].detach().view(G, ns, -1)
+    ref_max = torch.relu(z3).max(dim=1)
+    routed = ref_max.values > 0
+    flips3 = (ref_max.indices != sel) & routed
+    # every disagreement is a near-tie of the float64 activations (relative to the activation scale)
+    for z, fl in ((zs[0].detach(), flips1), (zs[1].detach(), flips2)):
+        assert fl.double().mean().item() <= 1e-4
+        if fl.any():
+            assert z[fl].abs().max().item() <= 1e-4 * z.abs().max().item()
+    gap = ref_max.values - torch.relu(z3.gather(1, sel.view(G, 1, -1)).squeeze(1))
+    assert flips3.double().mean().item() <= 2e-3
+    if flips3.any():
+        assert gap[flips3].abs().max().item() <= 1e-4 * ref_max.values.max().item()
+
+    # (b) the same graph with the GPU path's routing forced: pure float arithmetic remains
+    x, Ws, gs, bs, f = leaves()
+    forced, _ = _graph64(x, Ws, gs, bs, G, ns, masks=[mask1, mask2], sel=sel, mask_out=mask_out)
+    forced.backward(gout.double().reshape(G, -1))
+    ours = ([m.weight.grad.reshape(m.weight.shape[0], -1) for m in seq_d if isinstance(m, nn.Conv2d)]
+            + [m.weight.grad for m in seq_d if isinstance(m, nn.BatchNorm2d)]
+            + [m.bias.grad for m in seq_d if isinstance(m, nn.BatchNorm2d)] + [fd.grad])
+    names = ["W1", "W2", "W3", "g1", "g2", "g3", "b1", "b2", "b3", "dfeat"]
+    assert (out.detach().cpu().double().reshape(G, -1) - forced.detach()).abs().max().item() \
+        <= 1e-4 * forced.detach().abs().max().item()
+    worst_forced = worst_free = 0.0
+    for n, o, t, fr in zip(names, ours, Ws + gs + bs + [f], free):
+        # (a BN shift feeding another BatchNorm has a vanishing true gradient: bound it by the global scale)
+        scale = max(t.grad.norm().item(), 1e-3 * max(q.grad.norm().item() for q in Ws))
+        e_forced = (o.cpu().double() - t.grad).norm().item() / scale
+        e_free = (o.cpu().double() - fr).norm().item() / scale
+        worst_forced, worst_free = max(worst_forced, e_forced), max(worst_free, e_free)
+        assert e_forced <= 1e-3, f"{n}: forced-routing rel-L2 {e_forced:.3e} (free {e_free:.3e})"
+        assert e_free <= 2e-2, f"{n}: free rel-L2 {e_free:.3e}"
+    print(f"routing flips: relu1 {int(flips1.sum())}/{flips1.numel()}, relu2 {int(flips2.sum())}/{flips2.numel()}, "
+          f"max {int(flips3.sum())}/{flips3.numel()}; worst grad rel-L2 forced {worst_forced:.2e}, free {worst_free:.2e}")
+
+
+def test_fused_sa_branch_at_the_bench_shape():
+    """The shape bench.py's roofline is quoted on — BASELINE config 2, SA1 radius 0.4: B=32, N=4096, S=512,
+    ns=128, 6 -> 64 -> 96 -> 128, P = 2,097,152 rows — against the float64 reference sequence."""
+    import psutil
+    if psutil.virtual_memory().available < 64 * 2 ** 30:
+        pytest.skip("needs ~40 GB of host memory for the float64 reference graph")
+    B, N, S, r, ns, C, chans = 32, 4096, 512, 0.4, 128, 3, (64, 96, 128)
+    xyz, nrm, _ = modelnet_batch(B, N, seed=1)
+    seq = _mlp(chans, 3 + C).train()
+    ref_seq = copy.deepcopy(seq).double()
+    fidx = oracle.fps(xyz.numpy(), S)
+    new_xyz = torch.from_numpy(oracle.index_points(xyz.numpy(), fidx))
+    ridx, _ = oracle.ball_query(new_xyz.numpy(), xyz.numpy(), float(str(r)), ns)
+    grouped = torch.from_numpy(oracle.group(new_xyz.numpy(), xyz.numpy(), nrm.numpy(), ridx)).double()
+    ref = _ref64(ref_seq, grouped)
+    gen = torch.Generator().manual_seed(5)
+    gout = torch.randn(ref.shape, generator=gen)
+    ref.backward(gout.double())
+    seq_d = copy.deepcopy(seq).to(DEV)
+    out = sa.sa_branch(BallQueryGrouper(r, ns, True), seq_d, new_xyz.to(DEV), xyz.to(DEV), nrm.to(DEV))
+    assert out.shape == (B, S, chans[-1])
+    out.backward(gout.to(DEV))
+    scale = ref.abs().max().item()
+    assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= 1e-3 * scale
+    for (n, p), (_, q) in zip(seq_d.named_parameters(), ref_seq.named_parameters()):
+        assert _rel(p.grad, q.grad) <= 2e-3, f"{n}: rel-L2 {_rel(p.grad, q.grad):.3e}"

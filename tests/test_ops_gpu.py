@@ -284,3 +284,58 @@ def test_pack_weight_is_the_3xtf32_split():
     lo = rna(ref0 - hi)
     assert torch.equal(out[0], ref0) and torch.equal(out[1], hi) and torch.equal(out[2], lo)
     assert ((out[1] + out[2] - ref0).abs() <= 2.0 ** -21 * ref0.abs()).all()
+
+
+# ------------------------------------------------- multi-radius ball query (+ group) in one scan (a3, MSG levels)
+@pytest.mark.parametrize("B,N,S,C,radii,nss", [
+    (32, 4096, 512, 3, (0.1, 0.2, 0.4), (16, 32, 128)),        # config 2, SA1 (networks/cls/pointnet2.py:165-176)
+    (32, 512, 128, 320, (0.2, 0.4, 0.8), (32, 64, 128)),       # config 2, SA2 (:178-190)
+    (4, 1024, 100, 5, (0.4, 0.1), (12, 20)),                   # radii given in DESCENDING order, two of them
+    (3, 300, 37, 0, (0.3, 0.3, 0.5), (8, 4, 16)),              # equal radii, no feature (W = 3)
+    (2, 257, 9, 7, (0.05, 0.2, 0.9), (5, 7, 3)),               # ns*W not a multiple of 4: per-radius fallback
+    (1, 20000, 64, 2, (0.3,), (64,)),                          # cloud too large for shared memory: fallback
+])
+def test_ball_query_msg_equals_separate_queries(B, N, S, C, radii, nss):
+    xyz, nrm, _ = modelnet_batch(B, N, seed=N + S)
+    g = torch.Generator().manual_seed(13)
+    feat = nrm if C == 3 else (torch.randn(B, N, C, generator=g) if C else None)
+    fidx = oracle.fps(xyz.numpy(), S)
+    new_xyz = torch.from_numpy(oracle.index_points(xyz.numpy(), fidx))
+    xd, nd = xyz.to(DEV), new_xyz.to(DEV)
+    fd = None if feat is None else feat.to(DEV).requires_grad_(True)
+    res = F.ball_query_msg(nd, xd, [float(str(r)) for r in radii], nss)
+    grouped, idxs = F.ball_query_group_msg(nd, xd, fd, [float(str(r)) for r in radii], nss, return_idx=True)
+    assert len(res) == len(grouped) == len(radii)
+    for (idx, cnt), grp, idx2, r, ns in zip(res, grouped, idxs, radii, nss):
+        ridx, rcnt = oracle.ball_query(new_xyz.numpy(), xyz.numpy(), float(str(r)), ns)
+        np.testing.assert_array_equal(_np(idx), ridx)
+        np.testing.assert_array_equal(_np(cnt), rcnt)
+        np.testing.assert_array_equal(_np(idx2), ridx)
+        rgrp = oracle.group(new_xyz.numpy(), xyz.numpy(), None if feat is None else feat.numpy(), ridx)
+        np.testing.assert_array_equal(_np(grp), rgrp)
+    if fd is not None:      # backward: every radius scatters into the same feature gradient
+        gens = [torch.randn(gr.shape, generator=g) for gr in grouped]
+        torch.autograd.backward(grouped, [t.to(DEV) for t in gens])
+        dref = torch.zeros(B, N, C, dtype=torch.float64)
+        for (idx, _), t in zip(res, gens):
+            flat = idx.cpu().long().view(B, -1)
+            for b in range(B):
+                dref[b].index_add_(0, flat[b], t[b].reshape(-1, C + 3)[:, 3:].double())
+        np.testing.assert_allclose(_np(fd.grad), dref.numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_group_backward_reaches_a_permuted_feature():
+    """a non-contiguous feature (channels-first .permute) is copied inside forward; its gradient
+    must still arrive (ctx.needs_input_grad, not the copy's requires_grad)."""
+    B, N, S, ns, C = 2, 128, 16, 8, 6
+    xyz, _, _ = modelnet_batch(B, N, seed=3)
+    base = torch.randn(B, C, N, generator=torch.Generator().manual_seed(1)).to(DEV).requires_grad_(True)
+    new_xyz = xyz[:, :S].contiguous().to(DEV)
+    out = F.ball_query_group(new_xyz, xyz.to(DEV), base.permute(0, 2, 1), 0.5, ns)
+    out.sum().backward()
+    assert base.grad is not None and float(base.grad.abs().sum()) > 0
+    idx, _ = F.ball_query(new_xyz, xyz.to(DEV), 0.5, ns)
+    out2 = F.group(new_xyz, xyz.to(DEV), base.permute(0, 2, 1).double(), idx)     # fp64 input: converted copy
+    base.grad = None
+    out2.sum().backward()
+    assert base.grad is not None and float(base.grad.abs().sum()) > 0

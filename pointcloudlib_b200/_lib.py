@@ -53,7 +53,8 @@ _SIGNATURES = {
 # entry points bound in pointcloudlib_b200/fused.py (struct-taking signatures)
 FUSED_SYMBOLS = ("pcl_rowgemm", "pcl_wgrad", "pcl_gather_stats", "pcl_bn_param",
                  "pcl_maxpool_finalize", "pcl_maxpool_backward", "pcl_sel_outer",
-                 "pcl_gather_bn_backward", "pcl_gather_maxmin", "pcl_gather_bn_backward_routed")
+                 "pcl_gather_bn_backward", "pcl_gather_maxmin", "pcl_gather_bn_backward_routed",
+                 "pcl_routed_csr", "pcl_sel_outer_csr")
 
 
 def declared_symbols(header: str = HEADER_PATH):
@@ -98,6 +99,8 @@ class _TimedLib:
         w = self._cache.get(name)
         if w is None:
             def w(*args, _fn=fn, _name=name):
+                if not _in_call:
+                    LAUNCH_TAGS[_name] += 1
                 t = _timer
                 if t is None or _in_call or (t.only is not None and _name not in t.only):
                     return _fn(*args)
@@ -155,19 +158,21 @@ def call(name: str, *args, key=None) -> None:
     if key and isinstance(key[0], str):
         LAUNCH_TAGS[key[0]] += 1
     t = _timer
-    if t is not None and (t.only is None or name in t.only):
+    timed = t is not None and (t.only is None or name in t.only)
+    if timed:
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
-        _in_call = True
-        try:
+    _in_call = True
+    try:
+        if timed:
             e0.record()
-            rc = fn(*args)
-            e1.record()
-        finally:
-            _in_call = False
-        t.records.append((name, key, e0, e1))
-    else:
         rc = fn(*args)
+        if timed:
+            e1.record()
+    finally:
+        _in_call = False
+    if timed:
+        t.records.append((name, key, e0, e1))
     check(rc, name)
 
 

@@ -9,7 +9,11 @@
 // index order, padded with the first hit" list.
 //
 // B200 design.
-//   * Points staged once per CTA as float4 (x, y, z, -) in shared memory: ONE 16-byte LDS per point test.
+//   * The cloud (N*12 bytes, contiguous in global memory) is staged once per CTA by the TMA engine: one thread
+//     issues 1-D bulk copies (cp.async.bulk.shared.global, completion on an mbarrier), the layout in shared
+//     memory stays the global AoS (x,y,z per point; stride-3 word accesses are bank-conflict free).  The
+//     round-1 staging loop (one dependent load -> transposing store per thread and iteration, 48 iterations)
+//     cost ~18 us per CTA at N = 4096 and dominated every SA1-shaped launch.
 //   * One WARP per centroid, 128 points per iteration; the ballot of the LARGEST radius gates the others
 //     (a 32-point chunk with no hit in the big ball has none in the small ones), hit slots come from
 //     popc-prefix, no serial loop; the scan stops when every list is full.
@@ -42,10 +46,10 @@ struct BQMArgs {
     int R, B, N, S, C, use_xyz, cpb;
 };
 
-__device__ __forceinline__ float4 lds_f4(const float4 *p) { return *p; }
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <int U>
-__device__ __forceinline__ void write_rows(const BQMArgs &a, int r, int b, int s0, int n_c, const float4 *s_pts,
+__device__ __forceinline__ void write_rows(const BQMArgs &a, int r, int b, int s0, int n_c, const float *s_pts_f,
                                            const float4 *s_ctr, const int *s_idx) {
     const int off = a.use_xyz ? 3 : 0;
     const int W = off + (a.feat ? a.C : 0);
@@ -54,7 +58,6 @@ __device__ __forceinline__ void write_rows(const BQMArgs &a, int r, int b, int s
     const int total4 = n_c * per4;
     float4 *o4 = reinterpret_cast<float4 *>(a.out[r] + ((long long)b * a.S + s0) * ns * W);
     const float *fb = a.feat ? a.feat + (long long)b * a.N * a.C - off : nullptr;
-    const float *s_pts_f = reinterpret_cast<const float *>(s_pts);
     const float *s_ctr_f = reinterpret_cast<const float *>(s_ctr);
     for (int e0 = threadIdx.x; e0 < total4; e0 += kMThreads * U) {
         float v[U][4];
@@ -76,7 +79,7 @@ __device__ __forceinline__ void write_rows(const BQMArgs &a, int r, int b, int s
                         kk = k1;
                     }
                     if (cj < off)   // ops.py:401 local_xyz = grouped_xyz - new_xyz
-                        v[u][j] = __fsub_rn(s_pts_f[4 * kk + cj], s_ctr_f[4 * cen + cj]);
+                        v[u][j] = __fsub_rn(s_pts_f[3 * kk + cj], s_ctr_f[4 * cen + cj]);
                     else
                         v[u][j] = __ldg(fb + (long long)kk * a.C + cj);
                 }
@@ -90,15 +93,16 @@ __device__ __forceinline__ void write_rows(const BQMArgs &a, int r, int b, int s
     }
 }
 
-// Dynamic smem: float4 pts[N] | float4 ctr[cpb] | int idx[R][cpb*ns_r]
+// Dynamic smem: float ctr4[cpb][4] | float pts[3*N (padded to 16 B)] | int idx[R][cpb*ns_r]
 template <int R, bool GROUP, int U>
 __global__ void __launch_bounds__(kMThreads) ball_query_msg_kernel(const BQMArgs a) {
     extern __shared__ float4 smem4[];
-    float4 *s_pts = smem4;
-    float4 *s_ctr = smem4 + a.N;
+    __shared__ __align__(8) uint64_t s_bar;
+    float4 *s_ctr = smem4;
+    float *s_pts = reinterpret_cast<float *>(smem4 + a.cpb);
     int *s_idx[R];
     {
-        int *p = reinterpret_cast<int *>(s_ctr + a.cpb);
+        int *p = reinterpret_cast<int *>(s_pts + ((3 * a.N + 3) & ~3));
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             s_idx[r] = p;
@@ -111,14 +115,35 @@ __global__ void __launch_bounds__(kMThreads) ball_query_msg_kernel(const BQMArgs
     const int n_c = min(a.cpb, a.S - s0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *pb = a.xyz + (long long)b * a.N * 3;
-    {
-        float *s_pts_f = reinterpret_cast<float *>(s_pts);
-        for (int i = tid; i < 3 * a.N; i += kMThreads) {
-            const int k = i / 3, c = i - 3 * k;
-            s_pts_f[4 * k + c] = __ldg(pb + i);
+    const uint32_t bytes = (uint32_t)a.N * 12u;
+    const bool bulk = (bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(pb) & 15u) == 0;   // TMA: 16-byte granules
+    if (bulk) {
+        const uint32_t bar = smem_addr(&s_bar);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            for (uint32_t o = 0; o < bytes; o += 16384u) {
+                const uint32_t n = bytes - o < 16384u ? bytes - o : 16384u;
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                        smem_addr(s_pts) + o),
+                    "l"(reinterpret_cast<const char *>(pb) + o), "r"(n), "r"(bar)
+                    : "memory");
+            }
         }
+        __syncthreads();   // the barrier is initialised before anyone polls it
+        uint32_t ok = 0;
+        while (!ok)
+            asm volatile(
+                "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                : "=r"(ok)
+                : "r"(bar)
+                : "memory");
+    } else {
+        for (int i = tid; i < 3 * a.N; i += kMThreads) s_pts[i] = __ldg(pb + i);
+        __syncthreads();
     }
-    __syncthreads();
 
     for (int cl = warp; cl < n_c; cl += kMWarps) {
         const long long bs = (long long)b * a.S + s0 + cl;
@@ -141,10 +166,7 @@ __global__ void __launch_bounds__(kMThreads) ball_query_msg_kernel(const BQMArgs
             for (int j = 0; j < 4; ++j) {
                 const int k = base + 32 * j + lane;
                 d[j] = 3.0e38f;
-                if (k < a.N) {
-                    const float4 p = lds_f4(s_pts + k);
-                    d[j] = sqdist3(cx, cy, cz, p.x, p.y, p.z);   // ops.py:317-320
-                }
+                if (k < a.N) d[j] = sqdist3(cx, cy, cz, s_pts[3 * k], s_pts[3 * k + 1], s_pts[3 * k + 2]);   // ops.py:317-320
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -203,7 +225,7 @@ bool bq_msg_supported(int B, int N, int S, int C, int use_xyz, int R, const floa
         if (r > 0 && !(radii[r] >= radii[r - 1])) return false;   // ascending radii = nested balls
         sum_ns += ns[r];
     }
-    if ((size_t)N * 16 + 8 * (16 + 4 * sum_ns) > 200 * 1024) return false;
+    if ((size_t)N * 12 + 16 + 8 * (16 + 4 * sum_ns) > 200 * 1024) return false;
     if (group) {
         const int W = (use_xyz ? 3 : 0) + C;
         if (W < 3) return false;                         // one row wrap per float4
@@ -231,7 +253,7 @@ static int launch_msg_r(BQMArgs a, cudaStream_t st, const char *what) {
     while (cpb > 1 && (long long)a.B * ceil_div(a.S, cpb) < 2 * kNumSMs) cpb >>= 1;
     // multiply-high division is exact while n < 2^32 / d
     while (cpb > 1 && (long long)cpb * max_per4 * max_per4 >= (1ll << 32)) cpb >>= 1;
-    auto smem_for = [&](int c) { return (size_t)a.N * 16 + (size_t)c * (16 + 4 * sum_ns); };
+    auto smem_for = [&](int c) { return (((size_t)a.N * 12 + 15) & ~(size_t)15) + (size_t)c * (16 + 4 * sum_ns); };
     while (cpb > 1 && smem_for(cpb) > 200 * 1024) cpb >>= 1;
     if (smem_for(cpb) > 227 * 1024 || (long long)cpb * max_per4 * max_per4 >= (1ll << 32) ||
         (GROUP && (long long)max_per4 * 4 * W >= (1ll << 32))) {

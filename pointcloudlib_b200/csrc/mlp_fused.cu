@@ -740,6 +740,11 @@ extern "C" int pcl_rowgemm(const PclRowGemm *args, int prologue, int epilogue, i
     if (epilogue == PCL_EPI_BWD_Y_ROUTED)
         PCL_REQUIRE(x3 >= 2 && a.reserved >= 0 && a.ns <= BM && a.P % a.ns == 0 && a.x1 && a.g3s && a.selpos && a.C3 >= 1,
                     "pcl_rowgemm: routed epilogue needs a tcgen05 core, ns = 2^j <= 128, P %% ns == 0, x1/g3s/selpos");
+    if (epilogue == PCL_EPI_BWD_Y_CSR && !(x3 == 3 && rowgemm_ws_supported(a, prologue, epilogue))) {
+        set_error("pcl_rowgemm: PCL_EPI_BWD_Y_CSR needs x3 == 3, PCL_PRO_BN_ACT, K == N <= 128, N %% 32 == 0, ReLU, "
+                  "ns = 2^j >= 16 (K=%d N=%d ns=%d)", a.K, a.N, a.ns);
+        return PCL_ERR_UNSUPPORTED;
+    }
     if (a.P == 0) return PCL_OK;
     cudaStream_t st = (cudaStream_t)stream;
     // x3: 0 = mma.sync TF32, 1 = mma.sync 3xTF32, 2 = tcgen05 3xTF32 (W = [raw | hi | lo] stacked)

@@ -92,6 +92,24 @@ struct WEpiBwdGather {
     static __device__ __forceinline__ void apply(const PclRowGemm &a, const Par &e, float &v, float &q, float y) { bwd_act1(a, e, v, q, y); }
 };
 
+// Last-layer backward with NO per-element epilogue operand in global memory (PCL_EPI_BWD_Y_CSR):
+//   v = relu'(z2) * (acc + routed + ebias),  out = v,  stats[n] += sum v
+// K == N (the dense part is -a2.Q with a2 = relu(bn2(y2)) staged by THIS kernel's transform warps), so the
+// ReLU mask of output element (p, n) is the sign of the A-operand element (p, k = n) the transform warps just
+// produced: they drop one byte per element into a shared-memory stash (256 x N bytes per tile, two tiles),
+// the epilogue reads it back.  The routed term arrives as a per-group CSR by row (routed.cu): thread = channel n
+// adds g3s[g,c3] * W3[c3, n] for the entries of each of its 16 rows (warp-uniform trip counts, W3 rows read
+// coalesced from L1/L2).  The second BatchNorm-backward sum (sum v * xhat) needs no pass at all: with
+// a2 = mask*(gamma*xhat + beta) it equals (sum_p dA2*a2 - beta*sum v)/gamma, and sum_p dA2*a2 follows from the
+// Gram matrix, the column sums and the routed outer product the step computes anyway (fused.py).
+struct WEpiBwdYCsr {
+    static constexpr bool kMaxMin = false, kFetch = false, kStats = true, kSrc = false;
+    using Par = int;
+    static __device__ __forceinline__ Par params(const PclRowGemm &, int, bool) { return 0; }
+};
+template <class Epi> struct EpiTraits { static constexpr bool kCsr = false; };
+template <> struct EpiTraits<WEpiBwdYCsr> { static constexpr bool kCsr = true; };
+
 constexpr int kTransformWarps = 8, kEpilogueWarps = 8;
 constexpr int kThreadsWS = (kTransformWarps + kEpilogueWarps + 1) * 32;   // 544
 constexpr int TILE_ROWS = 256;    // activation rows per macro tile = MMA N
@@ -118,10 +136,11 @@ template <int KC, class Epi>
 constexpr int stages() { return KC == 16 ? 4 : 2; }
 constexpr int kLag = 2;   // the transform refills the stage of chunk c - kLag (never blocks on the MMAs just issued)
 
-template <int KC, class Pro, class Epi>
+template <int KC, class Pro, class Epi, int S = stages<KC, Epi>()>
 __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowGemm a) {
     using C = Cfg<KC>;
-    constexpr int S = stages<KC, Epi>(), CPR = C::CPR;
+    constexpr int CPR = C::CPR;
+    constexpr bool kCsr = EpiTraits<Epi>::kCsr;
     // instruction descriptor: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), both K-major, N>>3, M>>4
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TILE_ROWS >> 3) << 17) |
                                ((uint32_t)(MMA_M >> 4) << 24);
@@ -170,6 +189,9 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
     // loads, 16 no transform math
     const int dbg = a.c0 >> 16;
     const float *Whi = a.W + (long long)a.N * a.ldw;   // W = [raw | hi | lo]; lo = hi + N*ldw
+    // kCsr: ReLU-mask stash, one byte per (row, channel), [2 tiles][256 rows][N], right after the operand ring
+    const uint32_t mstash = sbase + S * stage_bytes;
+    const uint32_t mstash_tile = (uint32_t)(TILE_ROWS * a.N);
 
     if (warp < kTransformWarps) {
         // ============================ TRANSFORM warps ============================
@@ -315,6 +337,8 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
             } else {
                 const int kcol = k0 - kbase + a_c * 4;
                 const typename Pro::Par par = Pro::params(a, kcol);
+                if (kCsr && c_kc == 0 && c_lt >= 2)   // the epilogue has drained this tile's stash buffer (tile c_lt - 2)
+                    mbar_wait(smem_u32(&s_accempty[c_lt & 1]), (uint32_t)(((c_lt >> 1) - 1) & 1));
                 cp_async_wait<S - kLag - 1>();   // this thread's pieces of chunk c have landed
                 // pass 1: every raw piece (and the V rows of the gather) in flight together; pass 2: math,
                 // TF32 split, in-place stores.  (The shared-memory accesses are volatile asm: without the
@@ -343,6 +367,14 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
                     split_tf32_trunc<4>(x, hi, lo);
                     sts4(st + aoff[i], hi[0], hi[1], hi[2], hi[3]);
                     sts4(st + C::A_BYTES + aoff[i], lo[0], lo[1], lo[2], lo[3]);
+                    if (kCsr) {   // relu'(z) == (a2 > 0): one byte per channel, 4 channels = one 32-bit store
+                        const uint32_t m = (x[0] > 0.f ? 1u : 0u) | (x[1] > 0.f ? 0x100u : 0u) |
+                                           (x[2] > 0.f ? 0x10000u : 0u) | (x[3] > 0.f ? 0x1000000u : 0u);
+                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(mstash + (uint32_t)(c_lt & 1) * mstash_tile +
+                                                                       (uint32_t)((a_row + C::RSTEP * i) * a.N + kcol)),
+                                     "r"(m)
+                                     : "memory");
+                    }
                 }
             }
             fence_proxy_async();   // generic-proxy writes (st.shared and cp.async) -> async proxy (tensor core)
@@ -407,6 +439,45 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
                                     }
                                 }
                             }
+                        } else if constexpr (kCsr) {
+                            const int ns = a.ns, sh = a.reserved;
+                            const float bias = act && a.ebias ? __ldg(a.ebias + n) : 0.f;
+                            const uint32_t ms = mstash + (uint32_t)buf * mstash_tile + (uint32_t)(h * 128 * a.N + (act ? ch : 0));
+                            for (int blk = 0; blk < 8; ++blk) {
+                                const long long pb = p0 + blk * 16;
+                                if (pb >= a.P) break;
+                                float v[16];
+                                tc_ld16(tbase + blk * 16, v);
+                                if (act) {
+                                    // routed term: rows pb..pb+15 lie in ONE group (ns >= 16, a power of two)
+                                    const long long g = pb >> sh;
+                                    const int32_t *rs = a.src + g * (ns + 1) + (int)(pb & (ns - 1));
+                                    const int32_t *en = a.selpos + g * a.C3;
+                                    const float *gv = a.g3s + g * a.C3;
+                                    const float *w3 = a.x1 + n;
+                                    int s0 = __ldg(rs);
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) {
+                                        const int e0 = __ldg(rs + i + 1);
+                                        for (int t = s0; t < e0; ++t) {
+                                            const int c3 = __ldg(en + t);
+                                            v[i] = fmaf(__ldg(gv + c3), __ldg(w3 + (long long)c3 * a.N), v[i]);
+                                        }
+                                        s0 = e0;
+                                    }
+                                    float *op = a.out + pb * a.N + n;
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) {
+                                        uint32_t m;
+                                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(m) : "r"(ms + (uint32_t)((blk * 16 + i) * a.N)));
+                                        if (pb + i < a.P) {
+                                            const float x = m ? v[i] + bias : 0.f;
+                                            if (!(dbg & 32)) op[(long long)i * a.N] = x;
+                                            fs += x;
+                                        }
+                                    }
+                                }
+                            }
                         } else {
                             const typename Epi::Par par = Epi::params(a, n, act);
                             for (int blk = 0; blk < 8; ++blk) {
@@ -437,7 +508,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
                 }
                 if (Epi::kStats && act) {
                     atomicAdd(a.stats + n, acc_s);
-                    atomicAdd(a.stats + a.N + n, acc_q);
+                    if (!kCsr) atomicAdd(a.stats + a.N + n, acc_q);
                 }
             }
         } else {
@@ -622,6 +693,32 @@ static int ws_ey_bytes(int N) {
     return ey > 64 * 1024 ? 64 * 1024 : ey;
 }
 
+// stages of the operand ring that fit beside the two-tile ReLU-mask stash of the CSR epilogue (4, else 3, else 0)
+static int ws_csr_stages(int N) {
+    const int BN = N < MMA_M ? N : MMA_M;
+    for (int S = 4; S >= 3; --S)
+        if (1024 + (size_t)S * (2 * Cfg<16>::A_BYTES + 2 * BN * 16 * 4) + 2 * (size_t)TILE_ROWS * N <= (size_t)kSmemMax) return S;
+    return 0;
+}
+
+template <int KC, class Pro, class Epi, int S>
+static int launch_ws_s(const PclRowGemm &a, cudaStream_t st) {
+    using C = Cfg<KC>;
+    const int BN = a.N < MMA_M ? a.N : MMA_M;
+    const size_t ring = (size_t)S * (2 * C::A_BYTES + 2 * BN * KC * 4);
+    const size_t smem = 1024 + ring + 2 * (size_t)TILE_ROWS * a.N;
+    auto kern = rowgemm_ws_kernel<KC, Pro, Epi, S>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("pcl_rowgemm(ws): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    const long long n_tiles = (a.P + TILE_ROWS - 1) / TILE_ROWS;
+    const long long grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+    kern<<<(unsigned)grid, kThreadsWS, smem, st>>>(a);
+    return check_launch("pcl_rowgemm(ws)");
+}
+
 template <int KC, class Pro, class Epi>
 static int launch_ws(const PclRowGemm &a, cudaStream_t st) {
     using C = Cfg<KC>;
@@ -649,6 +746,12 @@ static int launch_ws(const PclRowGemm &a, cudaStream_t st) {
 
 // Shapes the warp-specialised kernel covers; everything else stays on rowgemm_tc_kernel.
 bool rowgemm_ws_supported(const PclRowGemm &a, int pro, int epi) {
+    if (pro == PCL_PRO_BN_ACT && epi == PCL_EPI_BWD_Y_CSR) {
+        // the ReLU mask comes from the staged operand: K == N, one pass, ReLU (slope 0); 16-row blocks inside a group
+        return a.K == a.N && a.N <= ws::MMA_M && a.N % 32 == 0 && a.K % 16 == 0 && a.slope == 0.f && a.eslope == 0.f &&
+               a.reserved >= 4 && a.P % a.ns == 0 && a.x1 && a.g3s && a.src && a.selpos && a.C3 >= 1 &&
+               ws::ws_csr_stages(a.N) >= 3 && a.P >= 1;
+    }
     const bool combo = (pro == PCL_PRO_BN_ACT && epi == PCL_EPI_MAXMIN_STATS) ||
                        (pro == PCL_PRO_BN_ACT && epi == PCL_EPI_STORE_STATS) ||
                        (pro == PCL_PRO_GATHER_BN_ACT && epi == PCL_EPI_STORE_STATS) ||
@@ -682,6 +785,9 @@ bool rowgemm_ws_supported(const PclRowGemm &a, int pro, int epi) {
 
 int rowgemm_ws_dispatch(const PclRowGemm &a, int pro, int epi, cudaStream_t st) {
     using namespace ws;
+    if (pro == PCL_PRO_BN_ACT && epi == PCL_EPI_BWD_Y_CSR)
+        return ws_csr_stages(a.N) == 4 ? launch_ws_s<16, WProBnAct, WEpiBwdYCsr, 4>(a, st)
+                                       : launch_ws_s<16, WProBnAct, WEpiBwdYCsr, 3>(a, st);
 #define PCL_WS(P_, E_, PRO_, EPI_) \
     if (pro == P_ && epi == E_) return launch_ws<16, PRO_, EPI_>(a, st)
     PCL_WS(PCL_PRO_BN_ACT, PCL_EPI_MAXMIN_STATS, WProBnAct, WEpiMaxMinStats);

@@ -24,7 +24,7 @@ from . import _lib
 from ._lib import lib, ptr, stream
 
 PRO_PLAIN2, PRO_BN_ACT, PRO_GATHER_BN_ACT, PRO_BN_BWD, PRO_G3_A2, PRO_BN_ACT_ONES = range(6)
-EPI_STORE, EPI_STORE_STATS, EPI_MAXMIN_STATS, EPI_BWD_Y, EPI_BWD_GATHER, EPI_BWD_Y_ROUTED = range(6)
+EPI_STORE, EPI_STORE_STATS, EPI_MAXMIN_STATS, EPI_BWD_Y, EPI_BWD_GATHER, EPI_BWD_Y_ROUTED, EPI_BWD_Y_CSR = range(7)
 
 _PTR_FIELDS = ("W", "x0", "x1", "U", "V", "scale", "shift", "mean", "rstd", "bscale", "m1", "m2",
                "g3s", "src", "selpos", "out", "gmax", "gmin", "amax", "amin", "stats", "ebias",
@@ -66,6 +66,8 @@ def _bind():
         "pcl_gather_bn_backward": [P, P, P, P, P, P, P, P, P, L, I, I, Fl, P, P, P],
         "pcl_gather_maxmin": [P, P, P, L, I, I, Fl, P, P, P, P, P],
         "pcl_gather_bn_backward_routed": [P, P, P, P, P, P, P, P, P, P, L, I, I, Fl, P, P, P],
+        "pcl_routed_csr": [P, P, L, I, I, P, P, P],
+        "pcl_sel_outer_csr": [P, P, P, P, P, P, Fl, L, I, I, I, P, P],
     }
     for name, argtypes in sigs.items():
         fn = getattr(l, name)
@@ -76,7 +78,8 @@ def _bind():
 
 SIGNATURE_NAMES = ("pcl_rowgemm", "pcl_wgrad", "pcl_gather_stats", "pcl_bn_param",
                    "pcl_maxpool_finalize", "pcl_maxpool_backward", "pcl_sel_outer",
-                   "pcl_gather_bn_backward", "pcl_gather_maxmin", "pcl_gather_bn_backward_routed")
+                   "pcl_gather_bn_backward", "pcl_gather_maxmin", "pcl_gather_bn_backward_routed",
+                   "pcl_routed_csr", "pcl_sel_outer_csr")
 
 
 def _args(**kw):
@@ -116,6 +119,7 @@ def pack_weight(w: torch.Tensor, sign: float = 1.0) -> torch.Tensor:
 
 
 DEBUG = None   # tests: a dict that FusedSAFn.forward fills with its routing state (selpos, y2, U, V, src, BN vectors)
+CSR_ROUTED = 1   # 0: last-layer backward on the round-1 kernels (dense ey operand, per-entry sel_outer) for A/B runs
 WS_DBG = 0   # profiling knobs of rowgemm_ws.cu (scratch/ws_branch_knobs.py); 0 in production
 WS_FETCH_EPI = 0   # 1: also route the BWD_Y / BWD_GATHER epilogues to rowgemm_ws.cu (slower today)
 
@@ -255,11 +259,50 @@ class FusedSAFn(torch.autograd.Function):
         Q = W3d.t() @ (t.view(-1, 1) * W3d)               # (C2, C2)
         const = ((t * mu3.double()) - (s3 * c1 / P)) @ W3d  # q0 - r0, (C2)
 
+        # the routed gradient (one entry per (group, channel)) bucketed by row once; both of its consumers walk rows
+        use_csr = bool(CSR_ROUTED and MODE == 3 and slope == 0.0 and C2 <= 128 and C2 % 32 == 0
+                       and 16 <= ns <= 256 and ns & (ns - 1) == 0)
+        if use_csr:
+            rstart = torch.empty((G, ns + 1), dtype=torch.int32, device=dev)
+            ent = torch.empty((G, C3), dtype=torch.int32, device=dev)
+            _lib.call("pcl_routed_csr", ptr(selpos), ptr(g3s), G, C3, ns, ptr(rstart), ptr(ent), stream(g3s),
+                      key=("sa_routed_csr", G, C3))
+
+        # ---- Gram matrix of a2 and the sparse routed outer product (dW3; on the CSR path also the 2nd BN2 sum) ----
+        gram = torch.zeros((C2, C2 + 4), **f32)            # [:, :C2] = a2^T a2, [:, C2] = colsum(a2)
+        a2kw = dict(x0=y2, scale=sc2, shift=sh2, slope=slope, K=C2)
+        wgrad(PRO_BN_ACT, a2kw, PRO_BN_ACT_ONES, a2kw, P, C2, C2 + 1, gram, name="sa_gram")
+        T = torch.zeros((C3, C2), **f32)
+        if use_csr:
+            _lib.call("pcl_sel_outer_csr", ptr(g3s), ptr(rstart), ptr(ent), ptr(y2), ptr(sc2), ptr(sh2), float(slope),
+                      G, ns, C3, C2, ptr(T), stream(g3s), key=("sa_sel_outer", G, C3, C2))
+        else:
+            _lib.call("pcl_sel_outer", ptr(g3s), ptr(selpos), ptr(y2), ptr(sc2), ptr(sh2), float(slope), G,
+                      ns, C3, C2, ptr(T), stream(), key=("sa_sel_outer", G, C3, C2))
+        M2, S2 = gram[:, :C2].double(), gram[:, C2].double()
+        dW3 = (T.double() - (s3 * c1 / P).view(-1, 1) * S2.view(1, -1)
+               - t.view(-1, 1) * (W3d @ M2 - mu3.double().view(-1, 1) * S2.view(1, -1))).float()
+
         # ---- da2 -> dyhat2 (grad at the BN2 output masked by ReLU'), BN2 sums -----------------
         dyh2 = torch.empty((P, C2), **f32)
         sums2 = torch.zeros((2, C2), **f64)
         constf = const.float().contiguous()
-        if MODE >= 2:
+        if use_csr:
+            # warp-specialised kernel: ReLU mask from the operand tile it stages itself, routed term from the CSR;
+            # its epilogue reads nothing of size (P, C2) and accumulates sum(dyhat2) only
+            Wq = pack_weight(Q.t(), sign=-1.0)
+            W3f = W3m.contiguous()
+            rowgemm(PRO_BN_ACT, EPI_BWD_Y_CSR, "sa_b3", W=Wq, x0=y2, x1=W3f, g3s=g3s, src=rstart, selpos=ent, C3=C3,
+                    ns=ns, scale=sc2, shift=sh2, slope=0.0, P=P, K=C2, N=C2, ldw=Wq.shape[-1], out=dyh2,
+                    stats=sums2, ebias=constf, eslope=0.0)
+            # sum_p dyhat2*xhat2 without a pass: a2 = mask*(gamma2*xhat2 + beta2)  =>
+            #   sum_p dA2*mask*xhat2 = (sum_p dA2*a2 - beta2 * sum_p dyhat2) / gamma2,   dA2 = -a2.Q + R.W3 + const
+            #   sum_p dA2[p,n]*a2[p,n] = -sum_k Q[k,n] M2[k,n] + sum_c3 W3[c3,n] T[c3,n] + const[n] S2[n]
+            D2 = -(Q * M2).sum(dim=0) + (W3d * T.double()).sum(dim=0) + const * S2
+            gamma2 = sc2.double() / rs2.double()
+            beta2 = sh2.double() + mu2.double() * sc2.double()
+            sums2[1] = torch.where(gamma2 != 0, (D2 - beta2 * sums2[0]) / gamma2, torch.zeros_like(D2))
+        elif MODE >= 2:
             # dense part -a2.Q on the tensor core (K = C2); the routed part G3s.W3 is one row update per
             # (group, channel) added in fp32 by the epilogue (PCL_EPI_BWD_Y_ROUTED)
             Wq = pack_weight(Q.t(), sign=-1.0)                               # (C2, C2) = -Q^T
@@ -274,17 +317,6 @@ class FusedSAFn(torch.autograd.Function):
                     scale=sc2, shift=sh2, slope=slope, P=P, K=C3 + C2, N=C2, ldw=Wb.shape[-1], out=dyh2,
                     stats=sums2, ebias=constf, ey=y2, escale=sc2, eshift=sh2, emean=mu2, erstd=rs2,
                     eslope=slope)
-
-        # ---- dW3 from the Gram matrix of a2 and the sparse routed term -------------------------
-        gram = torch.zeros((C2, C2 + 4), **f32)            # [:, :C2] = a2^T a2, [:, C2] = colsum(a2)
-        a2kw = dict(x0=y2, scale=sc2, shift=sh2, slope=slope, K=C2)
-        wgrad(PRO_BN_ACT, a2kw, PRO_BN_ACT_ONES, a2kw, P, C2, C2 + 1, gram, name="sa_gram")
-        T = torch.zeros((C3, C2), **f32)
-        _lib.call("pcl_sel_outer", ptr(g3s), ptr(selpos), ptr(y2), ptr(sc2), ptr(sh2), float(slope), G,
-                  ns, C3, C2, ptr(T), stream(), key=("sa_sel_outer", G, C3, C2))
-        M2, S2 = gram[:, :C2].double(), gram[:, C2].double()
-        dW3 = (T.double() - (s3 * c1 / P).view(-1, 1) * S2.view(1, -1)
-               - t.view(-1, 1) * (W3d @ M2 - mu3.double().view(-1, 1) * S2.view(1, -1))).float()
 
         # ---- layer 2 backward -----------------------------------------------------------------
         m1_2 = (sums2[0] / P).float().contiguous()

@@ -170,11 +170,11 @@ int pcl_compute_density(const float *xyz, int B, int N, float bandwidth, float *
  *                          acc[g*ns + selpos[g,k], :] += g3s[g,k] * x1[k, :], x1 = (C3, N) row-major
  *                          (the sparse form of PCL_PRO_G3_A2's one-hot block; tcgen05 cores only,
  *                          ns a power of two <= 128, P % ns == 0)
- *     PCL_EPI_BWD_Y_CSR    the same values, warp-specialised kernel only (x3 == 3), with PCL_PRO_BN_ACT, K == N
- *                          <= 128, ReLU: no per-element operand is read from global memory — act' comes from the
- *                          operand tile the prologue just staged; the routed term comes as the per-group CSR of
- *                          pcl_routed_csr (src = rstart (G, ns+1), selpos = ent (G, C3), g3s, x1 = (C3, N));
- *                          stats[0..N) += sum v only (the caller derives sum v*xhat algebraically)
+ *     PCL_EPI_BWD_Y_MASK   v = relu'(.)*(acc+ebias); out = v; stats[0..N) += sum v ONLY.  Warp-specialised kernel
+ *                          (x3 == 3) with PCL_PRO_G3_A2, K == C3 + N, N <= 128, ReLU: no per-element operand is read
+ *                          from global memory — relu' is the sign of the operand tile the prologue just staged
+ *                          (A-operand element (p, C3 + n)), handed to the epilogue through shared memory; the caller
+ *                          derives sum v*xhat algebraically
  */
 /* Field notes: c0 / c1 are the widths of x0 / x1 for PCL_PRO_PLAIN2 only.  For every other prologue
  * c0 carries opt-in switches of the tcgen05 kernels and must be 0 in production: bit 15 routes the
@@ -193,9 +193,11 @@ typedef struct PclRowGemm {
     float vsign, slope, eslope, reserved_f;
 } PclRowGemm;
 enum { PCL_PRO_PLAIN2 = 0, PCL_PRO_BN_ACT = 1, PCL_PRO_GATHER_BN_ACT = 2, PCL_PRO_BN_BWD = 3,
-       PCL_PRO_G3_A2 = 4, PCL_PRO_BN_ACT_ONES = 5 /* pcl_wgrad only: [act(bn(x0)) | 1] */ };
+       PCL_PRO_G3_A2 = 4, PCL_PRO_BN_ACT_ONES = 5 /* pcl_wgrad only: [act(bn(x0)) | 1] */,
+       PCL_PRO_GATHER_BN_ACT_MASK = 6 /* pcl_wgrad R operand only (x3 == 3): [a1 | relu'] with a1 as
+                                         PCL_PRO_GATHER_BN_ACT, K % 32 == 0, N = 2K <= 160 */ };
 enum { PCL_EPI_STORE = 0, PCL_EPI_STORE_STATS = 1, PCL_EPI_MAXMIN_STATS = 2, PCL_EPI_BWD_Y = 3,
-       PCL_EPI_BWD_GATHER = 4, PCL_EPI_BWD_Y_ROUTED = 5, PCL_EPI_BWD_Y_CSR = 6 };
+       PCL_EPI_BWD_GATHER = 4, PCL_EPI_BWD_Y_ROUTED = 5, PCL_EPI_BWD_Y_MASK = 6 };
 int pcl_rowgemm(const PclRowGemm *args, int prologue, int epilogue, int x3, void *stream);
 /* Weight operand of pcl_rowgemm: w (N,K) fp32, row stride ldi -> out (3, N, ld), ld = K rounded up to
  * 32, zero padded: [sign*w | tf32 hi | tf32 lo] with hi = rna_tf32(sign*w), lo = rna_tf32(sign*w - hi).
@@ -231,21 +233,19 @@ int pcl_maxpool_backward(const float *dout, const float *out, const float *ysel,
 int pcl_sel_outer(const float *g3s, const int32_t *selpos, const float *y2, const float *scale2,
                   const float *shift2, float slope, long long G, int ns, int C3, int C2, float *T,
                   void *stream);
-/* The routed max-gradient (one non-zero per (group, channel): row selpos[g,c] carries g3s[g,c]) bucketed by
- * ROW per group: rstart (G, ns+1) offsets, ent (G, C3) channels sorted by (row, channel); entries with
- * g3s == 0 are dropped.  ns <= 256. */
-int pcl_routed_csr(const int32_t *selpos, const float *g3s, long long G, int C3, int ns, int32_t *rstart,
-                   int32_t *ent, void *stream);
-/* pcl_sel_outer from the CSR: every selected y2 row is read once (T zeroed by the caller). */
-int pcl_sel_outer_csr(const float *g3s, const int32_t *rstart, const int32_t *ent, const float *y2,
-                      const float *scale2, const float *shift2, float slope, long long G, int ns, int C3,
-                      int C2, float *T, void *stream);
 /* layer-1 backward scatter: dz1 = bscale*(dyh - m1 - xhat*m2) with y1 gathered again;
  * dU[src[p],:] += dz1 (atomics); dV[p/ns,:] = vsign * sum over the group of dz1. */
 int pcl_gather_bn_backward(const float *dyh, const float *U, const float *V, const int32_t *src,
                            const float *mean, const float *rstd, const float *bscale,
                            const float *m1, const float *m2, long long P, int ns, int C,
                            float vsign, float *dU, float *dV, void *stream);
+
+/* pcl_gather_bn_backward for an UNMASKED incoming gradient dA (the row GEMM stored acc without act'):
+ * dyh = relu'(bscale*y1 + shift) * dA is applied here, where y1 is gathered anyway. */
+int pcl_gather_bn_backward_masked(const float *dA, const float *U, const float *V, const int32_t *src,
+                                  const float *mean, const float *rstd, const float *bscale, const float *shift,
+                                  const float *m1, const float *m2, long long P, int ns, int C, float vsign,
+                                  float *dU, float *dV, void *stream);
 
 /* ---- a7 / a8: fused EdgeConv (networks/cls/dgcnn.py:29-50 + :72-83,100-111) -------------------
  * W.[x_j - x_i ; x_i] = W1.x_j + (W2-W1).x_i  =>  y[i,j] = u[src[i,j]] + vsign*v[i] on per-point

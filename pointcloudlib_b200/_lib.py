@@ -54,7 +54,7 @@ _SIGNATURES = {
 FUSED_SYMBOLS = ("pcl_rowgemm", "pcl_wgrad", "pcl_gather_stats", "pcl_bn_param",
                  "pcl_maxpool_finalize", "pcl_maxpool_backward", "pcl_sel_outer",
                  "pcl_gather_bn_backward", "pcl_gather_maxmin", "pcl_gather_bn_backward_routed",
-                 "pcl_routed_csr", "pcl_sel_outer_csr")
+                 "pcl_gather_bn_backward_masked")
 
 
 def declared_symbols(header: str = HEADER_PATH):

@@ -17,13 +17,18 @@
 //   * One WARP per centroid, 128 points per iteration; the ballot of the LARGEST radius gates the others
 //     (a 32-point chunk with no hit in the big ball has none in the small ones), hit slots come from
 //     popc-prefix, no serial loop; the scan stops when every list is full.
-//   * Writer: after the CTA's lists are in shared memory, ALL 256 threads write the CTA's grouped rows as
-//     one flat, 16-byte-aligned float4 stream per radius (a centroid's ns*(3+C) floats are contiguous and
-//     ns % 4 == 0 makes them a whole number of float4s): 16-byte coalesced stores, kU float4s (4*kU
-//     gathers) per thread in flight before the first store — the round-1 writer had one warp per centroid
-//     and 12 loads per lane in flight, i.e. ~6 MB in flight chip-wide, right at Little's law for HBM3e,
-//     and every warp wrote its 165 KB alone (load imbalance across the single wave of CTAs).
+//   * Writer, wide rows (3 + C channels, C % 4 == 0, C >= 32: the SA2 level writes 3 + 320): one warp moves FOUR
+//     grouped rows at a time.  4*(3+C) floats are a whole number of 16-byte units and the output of a centroid is
+//     16-byte aligned, so the four rows are assembled in a warp-private shared-memory buffer — feature rows arrive
+//     as 128-bit loads (12 per lane in flight), are dropped at their (mis)aligned float offsets (the alignment of
+//     row r is the compile-time constant (3r + 3) % 4), the 12 centred coordinates are filled in — and leave as
+//     128-bit, 512-byte-coalesced stores.  ~2.7 instructions per float; the round-1 writer (scalar load, compare,
+//     scalar store per element, flat-index bookkeeping) needed ~20 and ncu showed it ISSUE bound (57-66 % issue
+//     active at 3.8 TB/s), not memory bound.
+//   * Writer, narrow rows: ALL threads write the CTA's grouped rows as one flat float4 stream per radius;
 //     (row, channel) of a flat index come from two multiply-high divisions.
+//   * Scan-heavy launches (narrow rows, query only) run 512-thread CTAs: the staged cloud (48 KB at N = 4096) is
+//     shared by 16 warps, so four CTAs keep all 64 warp slots of an SM busy.
 // HBM traffic = read xyz/feat once (L2-resident per cloud), write idx + grouped tensors once.
 #include <stdlib.h>
 
@@ -32,7 +37,7 @@
 namespace pcl {
 
 constexpr int kMR = 3;            // radii per launch
-constexpr int kMThreads = 256, kMWarps = 8;
+
 
 struct BQMArgs {
     const float *new_xyz, *xyz, *feat;
@@ -48,9 +53,10 @@ struct BQMArgs {
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <int U>
+template <int U, int NT>
 __device__ __forceinline__ void write_rows(const BQMArgs &a, int r, int b, int s0, int n_c, const float *s_pts_f,
                                            const float4 *s_ctr, const int *s_idx) {
+    constexpr int kMThreads = NT;
     const int off = a.use_xyz ? 3 : 0;
     const int W = off + (a.feat ? a.C : 0);
     const int ns = a.ns[r];
@@ -93,13 +99,70 @@ __device__ __forceinline__ void write_rows(const BQMArgs &a, int r, int b, int s
     }
 }
 
-// Dynamic smem: float ctr4[cpb][4] | float pts[3*N (padded to 16 B)] | int idx[R][cpb*ns_r]
-template <int R, bool GROUP, int U>
-__global__ void __launch_bounds__(kMThreads) ball_query_msg_kernel(const BQMArgs a) {
+__device__ __forceinline__ void sts32(float *p, float v) { *p = v; }
+__device__ __forceinline__ void sts64(float *p, float x, float y) { *reinterpret_cast<float2 *>(p) = make_float2(x, y); }
+
+// Wide rows: W = 3 + C, C % 4 == 0, 32 <= C <= 384, ns % 4 == 0.  stage = this warp's 4*W floats.
+template <int NT>
+__device__ __forceinline__ void write_rows_wide(const BQMArgs &a, int r, int b, int s0, int n_c, const float *s_pts_f,
+                                                const float4 *s_ctr, const int *s_idx, float *stage) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int C = a.C, W = 3 + C, C4 = C >> 2, ns = a.ns[r], nb = ns >> 2;
+    const float *fb = a.feat + (long long)b * a.N * C;
+    const float *s_ctr_f = reinterpret_cast<const float *>(s_ctr);
+    for (int bt = warp; bt < n_c * nb; bt += NT / 32) {
+        const int cen = bt / nb, l0 = (bt - cen * nb) << 2;
+        const int *si = s_idx + cen * ns + l0;
+        int k[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) k[q] = si[q];
+        float4 v[4][3];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj) {
+                const int j = lane + 32 * jj;
+                if (j < C4) v[q][jj] = __ldg(reinterpret_cast<const float4 *>(fb + (long long)k[q] * C) + j);
+            }
+        if (lane < 12) {   // ops.py:401 local_xyz = grouped_xyz - new_xyz
+            const int q = lane / 3, c = lane - 3 * q;
+            stage[q * W + c] = __fsub_rn(s_pts_f[3 * k[q] + c], s_ctr_f[4 * cen + c]);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj) {
+            const int j = lane + 32 * jj;
+            if (j < C4) {
+                float *d0 = stage + 3 + 4 * j;             // row 0: float offset = 3 (mod 4)
+                sts32(d0, v[0][jj].x);
+                sts64(d0 + 1, v[0][jj].y, v[0][jj].z);
+                sts32(d0 + 3, v[0][jj].w);
+                float *d1 = stage + W + 3 + 4 * j;         // row 1: 2 (mod 4)
+                sts64(d1, v[1][jj].x, v[1][jj].y);
+                sts64(d1 + 2, v[1][jj].z, v[1][jj].w);
+                float *d2 = stage + 2 * W + 3 + 4 * j;     // row 2: 1 (mod 4)
+                sts32(d2, v[2][jj].x);
+                sts64(d2 + 1, v[2][jj].y, v[2][jj].z);
+                sts32(d2 + 3, v[2][jj].w);
+                *reinterpret_cast<float4 *>(stage + 3 * W + 3 + 4 * j) = v[3][jj];   // row 3: aligned
+            }
+        }
+        __syncwarp();
+        float4 *o4 = reinterpret_cast<float4 *>(a.out[r] + (((long long)b * a.S + s0 + cen) * ns + l0) * W);
+        const float4 *s4 = reinterpret_cast<const float4 *>(stage);
+        for (int m = lane; m < W; m += 32) o4[m] = s4[m];
+        __syncwarp();
+    }
+}
+
+// Dynamic smem: [WIDE: float stage[NT/32][4*W]] | float ctr4[cpb][4] | float pts[3*N (padded to 16 B)] | int idx[R][cpb*ns_r]
+template <int R, bool GROUP, int U, int NT, bool WIDE>
+__global__ void __launch_bounds__(NT) ball_query_msg_kernel(const BQMArgs a) {
+    constexpr int kMThreads = NT, kMWarps = NT / 32;
     extern __shared__ float4 smem4[];
     __shared__ __align__(8) uint64_t s_bar;
-    float4 *s_ctr = smem4;
-    float *s_pts = reinterpret_cast<float *>(smem4 + a.cpb);
+    float *s_stage = reinterpret_cast<float *>(smem4);                      // WIDE: [kMWarps][4*(3+C)] floats
+    float4 *s_ctr = smem4 + (WIDE ? kMWarps * (3 + a.C) : 0);
+    float *s_pts = reinterpret_cast<float *>(s_ctr + a.cpb);
     int *s_idx[R];
     {
         int *p = reinterpret_cast<int *>(s_pts + ((3 * a.N + 3) & ~3));
@@ -205,7 +268,12 @@ __global__ void __launch_bounds__(kMThreads) ball_query_msg_kernel(const BQMArgs
     if (GROUP) {
         __syncthreads();
 #pragma unroll
-        for (int r = 0; r < R; ++r) write_rows<U>(a, r, b, s0, n_c, s_pts, s_ctr, s_idx[r]);
+        for (int r = 0; r < R; ++r) {
+            if (WIDE)
+                write_rows_wide<NT>(a, r, b, s0, n_c, s_pts, s_ctr, s_idx[r], s_stage + (tid >> 5) * 4 * (3 + a.C));
+            else
+                write_rows<U, NT>(a, r, b, s0, n_c, s_pts, s_ctr, s_idx[r]);
+        }
     }
 }
 
@@ -239,32 +307,42 @@ template <int R, bool GROUP>
 static int launch_msg_r(BQMArgs a, cudaStream_t st, const char *what) {
     const int W = (a.use_xyz ? 3 : 0) + (a.feat ? a.C : 0);
     int sum_ns = 0, max_per4 = 1;
+    bool ns4 = true;
     for (int r = 0; r < R; ++r) {
         sum_ns += a.ns[r];
+        ns4 = ns4 && a.ns[r] % 4 == 0;
         const int per4 = GROUP ? a.ns[r] * W / 4 : 1;
         a.m_per4[r] = magic_u32((unsigned)per4);
         max_per4 = per4 > max_per4 ? per4 : max_per4;
     }
     a.m_w = magic_u32((unsigned)(W > 0 ? W : 1));
-    // centroids per CTA: wide rows -> few (the writer is the work, many resident CTAs = many loads in
-    // flight); narrow rows -> 16 (amortise the cloud staging; the scan is the work)
-    int cpb = GROUP ? (W >= 64 ? 4 : 16) : 32;
+    // wide rows: the four-row staged writer (128-bit loads and stores); else the flat float4 writer
+    const bool wide = GROUP && a.use_xyz && a.feat && a.C % 4 == 0 && a.C >= 32 && a.C <= 384 && ns4 &&
+                      (reinterpret_cast<uintptr_t>(a.feat) & 15u) == 0 && env_int("PCL_BQ_WIDE", 1) != 0;
+    // scan-heavy launches (narrow rows / query only): 512 threads share one staged cloud
+    const int nt = wide ? 256 : env_int("PCL_BQ_THREADS", 512);
+    // centroids per CTA: wide rows -> few (the writer is the work; many resident CTAs); else one per warp
+    int cpb = wide ? 4 : nt / 32;
     cpb = env_int("PCL_BQ_CPB", cpb);
     while (cpb > 1 && (long long)a.B * ceil_div(a.S, cpb) < 2 * kNumSMs) cpb >>= 1;
     // multiply-high division is exact while n < 2^32 / d
-    while (cpb > 1 && (long long)cpb * max_per4 * max_per4 >= (1ll << 32)) cpb >>= 1;
-    auto smem_for = [&](int c) { return (((size_t)a.N * 12 + 15) & ~(size_t)15) + (size_t)c * (16 + 4 * sum_ns); };
+    while (!wide && cpb > 1 && (long long)cpb * max_per4 * max_per4 >= (1ll << 32)) cpb >>= 1;
+    auto smem_for = [&](int c) {
+        return (((size_t)a.N * 12 + 15) & ~(size_t)15) + (size_t)c * (16 + 4 * sum_ns) + (wide ? (size_t)(nt / 32) * 16 * W : 0);
+    };
     while (cpb > 1 && smem_for(cpb) > 200 * 1024) cpb >>= 1;
-    if (smem_for(cpb) > 227 * 1024 || (long long)cpb * max_per4 * max_per4 >= (1ll << 32) ||
-        (GROUP && (long long)max_per4 * 4 * W >= (1ll << 32))) {
+    if (smem_for(cpb) > 227 * 1024 || (!wide && ((long long)cpb * max_per4 * max_per4 >= (1ll << 32) ||
+                                                  (GROUP && (long long)max_per4 * 4 * W >= (1ll << 32))))) {
         set_error("%s: shape not covered by the one-scan kernel", what);
         return PCL_ERR_UNSUPPORTED;
     }
     a.cpb = cpb;
     const size_t smem = smem_for(cpb);
     const int grid = a.B * ceil_div(a.S, cpb);
-    const int U = env_int("PCL_BQ_UNROLL", W >= 64 ? 8 : 4);
-    auto kern = U >= 8 ? ball_query_msg_kernel<R, GROUP, 8> : (U >= 4 ? ball_query_msg_kernel<R, GROUP, 4> : ball_query_msg_kernel<R, GROUP, 2>);
+    void (*kern)(const BQMArgs) = nullptr;
+    if (wide) kern = ball_query_msg_kernel<R, GROUP, 4, 256, true>;
+    else if (nt >= 512) kern = ball_query_msg_kernel<R, GROUP, 4, 512, false>;
+    else kern = ball_query_msg_kernel<R, GROUP, 4, 256, false>;
     if (smem > 40 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
@@ -272,7 +350,7 @@ static int launch_msg_r(BQMArgs a, cudaStream_t st, const char *what) {
             return (int)e;
         }
     }
-    kern<<<grid, kMThreads, smem, st>>>(a);
+    kern<<<grid, wide || nt < 512 ? 256 : 512, smem, st>>>(a);
     return check_launch(what);
 }
 

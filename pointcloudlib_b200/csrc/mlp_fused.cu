@@ -511,12 +511,15 @@ __global__ void __launch_bounds__(256) sel_outer_kernel(
     }
 }
 
-// one warp per group; lanes over channel quads (C <= 256)
+// one warp per group; lanes over channel quads (C <= 256).  MASK: dyh holds the UNMASKED gradient dA and
+// relu'(bscale*y1 + shift) is applied here (y1 is gathered anyway).
+template <bool MASK>
 __global__ void __launch_bounds__(256) gather_bn_backward_kernel(
     const float *__restrict__ dyh, const float *__restrict__ U, const float *__restrict__ V,
     const int32_t *__restrict__ src, const float *__restrict__ mean, const float *__restrict__ rstd,
-    const float *__restrict__ bscale, const float *__restrict__ m1, const float *__restrict__ m2,
-    long long G, int ns, int C, float vsign, float *__restrict__ dU, float *__restrict__ dV) {
+    const float *__restrict__ bscale, const float *__restrict__ shift, const float *__restrict__ m1,
+    const float *__restrict__ m2, long long G, int ns, int C, float vsign, float *__restrict__ dU,
+    float *__restrict__ dV) {
     const int lane = threadIdx.x & 31;
     const long long gi = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (gi >= G) return;
@@ -529,6 +532,7 @@ __global__ void __launch_bounds__(256) gather_bn_backward_kernel(
         const float4 mu = ld4(mean + k), rs = ld4(rstd + k), bs = ld4(bscale + k), a1 = ld4(m1 + k),
                      a2 = ld4(m2 + k);
         const float4 v = V ? ld4(V + gi * C + k) : f4zero();
+        const float4 sh = MASK ? ld4(shift + k) : f4zero();
         float4 sum = f4zero();
         for (int l0 = 0; l0 < ns; l0 += 4 * rpp) {
             long long sr[4];
@@ -549,6 +553,12 @@ __global__ void __launch_bounds__(256) gather_bn_backward_kernel(
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (!ok[j]) continue;
+                if (MASK) {
+                    d[j].x = fmaf(bs.x, fmaf(vsign, v.x, u[j].x), sh.x) > 0.f ? d[j].x : 0.f;
+                    d[j].y = fmaf(bs.y, fmaf(vsign, v.y, u[j].y), sh.y) > 0.f ? d[j].y : 0.f;
+                    d[j].z = fmaf(bs.z, fmaf(vsign, v.z, u[j].z), sh.z) > 0.f ? d[j].z : 0.f;
+                    d[j].w = fmaf(bs.w, fmaf(vsign, v.w, u[j].w), sh.w) > 0.f ? d[j].w : 0.f;
+                }
                 float4 dz;
                 dz.x = bs.x * (d[j].x - a1.x - (fmaf(vsign, v.x, u[j].x) - mu.x) * rs.x * a2.x);
                 dz.y = bs.y * (d[j].y - a1.y - (fmaf(vsign, v.y, u[j].y) - mu.y) * rs.y * a2.y);
@@ -577,11 +587,19 @@ __global__ void __launch_bounds__(256) gather_bn_backward_kernel(
         const float4 mu = ld4(mean + k), rs = ld4(rstd + k), bs = ld4(bscale + k), a1 = ld4(m1 + k),
                      a2 = ld4(m2 + k);
         const float4 v = V ? ld4(V + gi * C + k) : f4zero();
+        const float4 sh = MASK ? ld4(shift + k) : f4zero();
         float4 sum = f4zero();
         for (int l = 0; l < ns; ++l) {
             const long long p = gi * ns + l;
             const long long sr = __ldg(src + p);
-            const float4 u = ld4(U + sr * C + k), d = ld4(dyh + p * C + k);
+            const float4 u = ld4(U + sr * C + k);
+            float4 d = ld4(dyh + p * C + k);
+            if (MASK) {
+                d.x = fmaf(bs.x, fmaf(vsign, v.x, u.x), sh.x) > 0.f ? d.x : 0.f;
+                d.y = fmaf(bs.y, fmaf(vsign, v.y, u.y), sh.y) > 0.f ? d.y : 0.f;
+                d.z = fmaf(bs.z, fmaf(vsign, v.z, u.z), sh.z) > 0.f ? d.z : 0.f;
+                d.w = fmaf(bs.w, fmaf(vsign, v.w, u.w), sh.w) > 0.f ? d.w : 0.f;
+            }
             float4 dz;
             dz.x = bs.x * (d.x - a1.x - (fmaf(vsign, v.x, u.x) - mu.x) * rs.x * a2.x);
             dz.y = bs.y * (d.y - a1.y - (fmaf(vsign, v.y, u.y) - mu.y) * rs.y * a2.y);
@@ -740,9 +758,9 @@ extern "C" int pcl_rowgemm(const PclRowGemm *args, int prologue, int epilogue, i
     if (epilogue == PCL_EPI_BWD_Y_ROUTED)
         PCL_REQUIRE(x3 >= 2 && a.reserved >= 0 && a.ns <= BM && a.P % a.ns == 0 && a.x1 && a.g3s && a.selpos && a.C3 >= 1,
                     "pcl_rowgemm: routed epilogue needs a tcgen05 core, ns = 2^j <= 128, P %% ns == 0, x1/g3s/selpos");
-    if (epilogue == PCL_EPI_BWD_Y_CSR && !(x3 == 3 && rowgemm_ws_supported(a, prologue, epilogue))) {
-        set_error("pcl_rowgemm: PCL_EPI_BWD_Y_CSR needs x3 == 3, PCL_PRO_BN_ACT, K == N <= 128, N %% 32 == 0, ReLU, "
-                  "ns = 2^j >= 16 (K=%d N=%d ns=%d)", a.K, a.N, a.ns);
+    if (epilogue == PCL_EPI_BWD_Y_MASK && !(x3 == 3 && rowgemm_ws_supported(a, prologue, epilogue))) {
+        set_error("pcl_rowgemm: PCL_EPI_BWD_Y_MASK needs x3 == 3, PCL_PRO_G3_A2, K == C3 + N, N <= 128, N %% 32 == 0, "
+                  "C3 %% 16 == 0, ReLU, ns = 2^j in [4, 256] (K=%d N=%d C3=%d ns=%d)", a.K, a.N, a.C3, a.ns);
         return PCL_ERR_UNSUPPORTED;
     }
     if (a.P == 0) return PCL_OK;
@@ -850,7 +868,22 @@ extern "C" int pcl_gather_bn_backward(const float *dyh, const float *U, const fl
                 "pcl_gather_bn_backward: bad shape");
     const long long G = P / ns;
     if (G == 0) return PCL_OK;
-    gather_bn_backward_kernel<<<(unsigned)ceil_div_ll(G, 8), 256, 0, (cudaStream_t)stream>>>(
-        dyh, U, V, src, mean, rstd, bscale, m1, m2, G, ns, C, vsign, dU, dV);
+    gather_bn_backward_kernel<false><<<(unsigned)ceil_div_ll(G, 8), 256, 0, (cudaStream_t)stream>>>(
+        dyh, U, V, src, mean, rstd, bscale, nullptr, m1, m2, G, ns, C, vsign, dU, dV);
     return check_launch("pcl_gather_bn_backward");
+}
+
+extern "C" int pcl_gather_bn_backward_masked(const float *dA, const float *U, const float *V, const int32_t *src,
+                                             const float *mean, const float *rstd, const float *bscale,
+                                             const float *shift, const float *m1, const float *m2, long long P,
+                                             int ns, int C, float vsign, float *dU, float *dV, void *stream) {
+    PCL_REQUIRE(dA && U && src && mean && rstd && bscale && shift && m1 && m2 && dU,
+                "pcl_gather_bn_backward_masked: null pointer");
+    PCL_REQUIRE(P >= 0 && ns >= 1 && P % ns == 0 && C % 4 == 0 && C <= 256,
+                "pcl_gather_bn_backward_masked: bad shape");
+    const long long G = P / ns;
+    if (G == 0) return PCL_OK;
+    gather_bn_backward_kernel<true><<<(unsigned)ceil_div_ll(G, 8), 256, 0, (cudaStream_t)stream>>>(
+        dA, U, V, src, mean, rstd, bscale, shift, m1, m2, G, ns, C, vsign, dU, dV);
+    return check_launch("pcl_gather_bn_backward_masked");
 }

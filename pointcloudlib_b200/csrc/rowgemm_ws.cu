@@ -92,23 +92,23 @@ struct WEpiBwdGather {
     static __device__ __forceinline__ void apply(const PclRowGemm &a, const Par &e, float &v, float &q, float y) { bwd_act1(a, e, v, q, y); }
 };
 
-// Last-layer backward with NO per-element epilogue operand in global memory (PCL_EPI_BWD_Y_CSR):
-//   v = relu'(z2) * (acc + routed + ebias),  out = v,  stats[n] += sum v
-// K == N (the dense part is -a2.Q with a2 = relu(bn2(y2)) staged by THIS kernel's transform warps), so the
-// ReLU mask of output element (p, n) is the sign of the A-operand element (p, k = n) the transform warps just
-// produced: they drop one byte per element into a shared-memory stash (256 x N bytes per tile, two tiles),
-// the epilogue reads it back.  The routed term arrives as a per-group CSR by row (routed.cu): thread = channel n
-// adds g3s[g,c3] * W3[c3, n] for the entries of each of its 16 rows (warp-uniform trip counts, W3 rows read
-// coalesced from L1/L2).  The second BatchNorm-backward sum (sum v * xhat) needs no pass at all: with
-// a2 = mask*(gamma*xhat + beta) it equals (sum_p dA2*a2 - beta*sum v)/gamma, and sum_p dA2*a2 follows from the
-// Gram matrix, the column sums and the routed outer product the step computes anyway (fused.py).
-struct WEpiBwdYCsr {
+// Last-layer backward with NO per-element epilogue operand in global memory (PCL_EPI_BWD_Y_MASK):
+//   v = relu'(z2) * (acc + ebias),  out = v,  stats[n] += sum v
+// with PCL_PRO_G3_A2: K = C3 + N, the routed max-gradient enters as the one-hot K block (scattered into a zeroed
+// operand tile, contracted with W3 by the tensor core), the dense part is -a2.Q with a2 = relu(bn2(y2)) staged by
+// THIS kernel's transform warps.  The ReLU mask of output element (p, n) is the sign of the A-operand element
+// (p, k = C3 + n) they just produced: they drop one byte per element into a shared-memory stash (256 x N bytes per
+// tile, two tiles) and the epilogue reads it back — the round-1 kernel re-read y2 (P x N floats) in its epilogue.
+// The second BatchNorm-backward sum (sum v * xhat) needs no pass at all: with a2 = mask*(gamma*xhat + beta) it
+// equals (sum_p dA2*a2 - beta*sum v)/gamma, and sum_p dA2*a2 follows from the Gram matrix, the column sums and
+// the routed outer product the step computes anyway (fused.py).
+struct WEpiBwdYMask {
     static constexpr bool kMaxMin = false, kFetch = false, kStats = true, kSrc = false;
     using Par = int;
     static __device__ __forceinline__ Par params(const PclRowGemm &, int, bool) { return 0; }
 };
-template <class Epi> struct EpiTraits { static constexpr bool kCsr = false; };
-template <> struct EpiTraits<WEpiBwdYCsr> { static constexpr bool kCsr = true; };
+template <class Epi> struct EpiTraits { static constexpr bool kMask = false; };
+template <> struct EpiTraits<WEpiBwdYMask> { static constexpr bool kMask = true; };
 
 constexpr int kTransformWarps = 8, kEpilogueWarps = 8;
 constexpr int kThreadsWS = (kTransformWarps + kEpilogueWarps + 1) * 32;   // 544
@@ -140,7 +140,7 @@ template <int KC, class Pro, class Epi, int S = stages<KC, Epi>()>
 __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowGemm a) {
     using C = Cfg<KC>;
     constexpr int CPR = C::CPR;
-    constexpr bool kCsr = EpiTraits<Epi>::kCsr;
+    constexpr bool kMaskStash = EpiTraits<Epi>::kMask;
     // instruction descriptor: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), both K-major, N>>3, M>>4
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TILE_ROWS >> 3) << 17) |
                                ((uint32_t)(MMA_M >> 4) << 24);
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
     // loads, 16 no transform math
     const int dbg = a.c0 >> 16;
     const float *Whi = a.W + (long long)a.N * a.ldw;   // W = [raw | hi | lo]; lo = hi + N*ldw
-    // kCsr: ReLU-mask stash, one byte per (row, channel), [2 tiles][256 rows][N], right after the operand ring
+    // kMaskStash: ReLU-mask stash, one byte per (row, channel), [2 tiles][256 rows][N], right after the operand ring
     const uint32_t mstash = sbase + S * stage_bytes;
     const uint32_t mstash_tile = (uint32_t)(TILE_ROWS * a.N);
 
@@ -296,6 +296,8 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
             const int s = c % S;
             const uint32_t st = sbase + s * stage_bytes;
             const int k0 = c_kc * KC;
+            if (kMaskStash && c_kc == 0 && c_lt >= 2)   // the epilogue has drained this tile's stash buffer (tile c_lt - 2)
+                mbar_wait(smem_u32(&s_accempty[c_lt & 1]), (uint32_t)(((c_lt >> 1) - 1) & 1));
             if (Pro::kOneHot && k0 < kbase) {
                 // routed one-hot chunk: per (group, channel) ONE row carries g3s; everything else is 0.
                 // Zero the tile, then scatter the (256/ns)*KC entries (instead of 1024 compare-selects).
@@ -337,8 +339,6 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
             } else {
                 const int kcol = k0 - kbase + a_c * 4;
                 const typename Pro::Par par = Pro::params(a, kcol);
-                if (kCsr && c_kc == 0 && c_lt >= 2)   // the epilogue has drained this tile's stash buffer (tile c_lt - 2)
-                    mbar_wait(smem_u32(&s_accempty[c_lt & 1]), (uint32_t)(((c_lt >> 1) - 1) & 1));
                 cp_async_wait<S - kLag - 1>();   // this thread's pieces of chunk c have landed
                 // pass 1: every raw piece (and the V rows of the gather) in flight together; pass 2: math,
                 // TF32 split, in-place stores.  (The shared-memory accesses are volatile asm: without the
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
                     split_tf32_trunc<4>(x, hi, lo);
                     sts4(st + aoff[i], hi[0], hi[1], hi[2], hi[3]);
                     sts4(st + C::A_BYTES + aoff[i], lo[0], lo[1], lo[2], lo[3]);
-                    if (kCsr) {   // relu'(z) == (a2 > 0): one byte per channel, 4 channels = one 32-bit store
+                    if (kMaskStash) {   // relu'(z) == (a2 > 0): one byte per channel, 4 channels = one 32-bit store
                         const uint32_t m = (x[0] > 0.f ? 1u : 0u) | (x[1] > 0.f ? 0x100u : 0u) |
                                            (x[2] > 0.f ? 0x10000u : 0u) | (x[3] > 0.f ? 0x1000000u : 0u);
                         asm volatile("st.shared.b32 [%0], %1;" ::"r"(mstash + (uint32_t)(c_lt & 1) * mstash_tile +
@@ -439,8 +439,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
                                     }
                                 }
                             }
-                        } else if constexpr (kCsr) {
-                            const int ns = a.ns, sh = a.reserved;
+                        } else if constexpr (kMaskStash) {
                             const float bias = act && a.ebias ? __ldg(a.ebias + n) : 0.f;
                             const uint32_t ms = mstash + (uint32_t)buf * mstash_tile + (uint32_t)(h * 128 * a.N + (act ? ch : 0));
                             for (int blk = 0; blk < 8; ++blk) {
@@ -449,22 +448,6 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
                                 float v[16];
                                 tc_ld16(tbase + blk * 16, v);
                                 if (act) {
-                                    // routed term: rows pb..pb+15 lie in ONE group (ns >= 16, a power of two)
-                                    const long long g = pb >> sh;
-                                    const int32_t *rs = a.src + g * (ns + 1) + (int)(pb & (ns - 1));
-                                    const int32_t *en = a.selpos + g * a.C3;
-                                    const float *gv = a.g3s + g * a.C3;
-                                    const float *w3 = a.x1 + n;
-                                    int s0 = __ldg(rs);
-#pragma unroll
-                                    for (int i = 0; i < 16; ++i) {
-                                        const int e0 = __ldg(rs + i + 1);
-                                        for (int t = s0; t < e0; ++t) {
-                                            const int c3 = __ldg(en + t);
-                                            v[i] = fmaf(__ldg(gv + c3), __ldg(w3 + (long long)c3 * a.N), v[i]);
-                                        }
-                                        s0 = e0;
-                                    }
                                     float *op = a.out + pb * a.N + n;
 #pragma unroll
                                     for (int i = 0; i < 16; ++i) {
@@ -508,7 +491,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
                 }
                 if (Epi::kStats && act) {
                     atomicAdd(a.stats + n, acc_s);
-                    if (!kCsr) atomicAdd(a.stats + a.N + n, acc_q);
+                    if (!kMaskStash) atomicAdd(a.stats + a.N + n, acc_q);
                 }
             }
         } else {
@@ -693,8 +676,8 @@ static int ws_ey_bytes(int N) {
     return ey > 64 * 1024 ? 64 * 1024 : ey;
 }
 
-// stages of the operand ring that fit beside the two-tile ReLU-mask stash of the CSR epilogue (4, else 3, else 0)
-static int ws_csr_stages(int N) {
+// stages of the operand ring that fit beside the two-tile ReLU-mask stash (4, else 3, else 0)
+static int ws_mask_stages(int N) {
     const int BN = N < MMA_M ? N : MMA_M;
     for (int S = 4; S >= 3; --S)
         if (1024 + (size_t)S * (2 * Cfg<16>::A_BYTES + 2 * BN * 16 * 4) + 2 * (size_t)TILE_ROWS * N <= (size_t)kSmemMax) return S;
@@ -746,11 +729,12 @@ static int launch_ws(const PclRowGemm &a, cudaStream_t st) {
 
 // Shapes the warp-specialised kernel covers; everything else stays on rowgemm_tc_kernel.
 bool rowgemm_ws_supported(const PclRowGemm &a, int pro, int epi) {
-    if (pro == PCL_PRO_BN_ACT && epi == PCL_EPI_BWD_Y_CSR) {
-        // the ReLU mask comes from the staged operand: K == N, one pass, ReLU (slope 0); 16-row blocks inside a group
-        return a.K == a.N && a.N <= ws::MMA_M && a.N % 32 == 0 && a.K % 16 == 0 && a.slope == 0.f && a.eslope == 0.f &&
-               a.reserved >= 4 && a.P % a.ns == 0 && a.x1 && a.g3s && a.src && a.selpos && a.C3 >= 1 &&
-               ws::ws_csr_stages(a.N) >= 3 && a.P >= 1;
+    if (epi == PCL_EPI_BWD_Y_MASK) {
+        // the ReLU mask comes from the staged operand: K == C3 + N, one pass, ReLU (slope 0); the one-hot scatter needs
+        // whole groups inside a 256-row tile and at most 4 entries per transform thread
+        return pro == PCL_PRO_G3_A2 && a.K == a.C3 + a.N && a.N <= ws::MMA_M && a.N % 32 == 0 && a.K % 16 == 0 &&
+               a.C3 % 16 == 0 && a.slope == 0.f && a.eslope == 0.f && a.reserved >= 2 && a.reserved <= 8 &&
+               a.P % a.ns == 0 && a.g3s && a.selpos && ws::ws_mask_stages(a.N) >= 3 && a.P >= 1;
     }
     const bool combo = (pro == PCL_PRO_BN_ACT && epi == PCL_EPI_MAXMIN_STATS) ||
                        (pro == PCL_PRO_BN_ACT && epi == PCL_EPI_STORE_STATS) ||
@@ -785,9 +769,9 @@ bool rowgemm_ws_supported(const PclRowGemm &a, int pro, int epi) {
 
 int rowgemm_ws_dispatch(const PclRowGemm &a, int pro, int epi, cudaStream_t st) {
     using namespace ws;
-    if (pro == PCL_PRO_BN_ACT && epi == PCL_EPI_BWD_Y_CSR)
-        return ws_csr_stages(a.N) == 4 ? launch_ws_s<16, WProBnAct, WEpiBwdYCsr, 4>(a, st)
-                                       : launch_ws_s<16, WProBnAct, WEpiBwdYCsr, 3>(a, st);
+    if (pro == PCL_PRO_G3_A2 && epi == PCL_EPI_BWD_Y_MASK)
+        return ws_mask_stages(a.N) == 4 ? launch_ws_s<16, WProG3A2, WEpiBwdYMask, 4>(a, st)
+                                        : launch_ws_s<16, WProG3A2, WEpiBwdYMask, 3>(a, st);
 #define PCL_WS(P_, E_, PRO_, EPI_) \
     if (pro == P_ && epi == E_) return launch_ws<16, PRO_, EPI_>(a, st)
     PCL_WS(PCL_PRO_BN_ACT, PCL_EPI_MAXMIN_STATS, WProBnAct, WEpiMaxMinStats);

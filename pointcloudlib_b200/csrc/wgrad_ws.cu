@@ -84,6 +84,16 @@ struct GGatherBnAct {    // act(scale*(U[src[p]] + vsign*V[p/ns]) + shift)
     }
 };
 
+// [act(bn(gathered)) | relu'(bn(gathered))]: the weight gradient dz^T.a1 and, in the SAME pass, dz^T.mask1 — the
+// matrix from which the BatchNorm-backward sums of the layer BELOW follow by algebra (fused.py: sum_p mask1*dA1 =
+// sum_k W2[k,n] (dz2^T mask1)[k,n]), so that layer's row GEMM needs no gathered epilogue operand.  The mask block
+// (0/1, exact in TF32: its lo tile stays at the zeros written once) occupies the K channels after the a1 block.
+struct GGatherBnActMask : GGatherBnAct {
+    static constexpr bool kMask = true;
+};
+template <class Pro> struct MaskTrait { static constexpr bool value = false; };
+template <> struct MaskTrait<GGatherBnActMask> { static constexpr bool value = true; };
+
 constexpr int kWgThreads = 9 * 32;
 constexpr int WG_ROWS = 32;     // rows per chunk = MMA K of 4 x 8
 constexpr int WG_BLK = 4096;    // bytes of one 32-channel block of a tile (hi or lo)
@@ -96,6 +106,7 @@ constexpr int kSrcSlot = NPR * 256 * 4;              // gather-index slots of on
 template <int NP, class Pro>
 struct Operand {
     uint32_t off[NP];        // byte offset of the piece in the hi tile (relative to the stage)
+    uint32_t offm[NP];       // (mask variant) byte offset of the piece's slot in the mask block
     const float *gp[NP];     // global pointer of the piece's raw data for the next chunk to ISSUE
     int row[NP], kq[NP];     // row inside the chunk, channel quad
     int n_live;              // pieces i < n_live are live (the rest are pre-written constants)
@@ -194,6 +205,7 @@ wgrad_ws_kernel(const PclRowGemm al, const PclRowGemm ar, long long P, int M, in
             R.row[i] = e / liveR;
             R.kq[i] = e % liveR;
             R.off[i] = 2 * l_tile + mn_off(R.row[i] & 31, R.kq[i]);
+            R.offm[i] = MaskTrait<ProR>::value ? 2 * l_tile + mn_off(R.row[i] & 31, R.kq[i] + liveR) : 0u;
             R.gp[i] = ProR::kSrc ? nullptr : ProR::ptr(ar, c_begin * WG_ROWS + R.row[i], R.kq[i] * 4);
             if (e < WG_ROWS * liveR) R.n_live = i + 1;
         }
@@ -309,6 +321,9 @@ wgrad_ws_kernel(const PclRowGemm al, const PclRowGemm ar, long long P, int M, in
                     split_tf32_trunc<4>(x, hi, lo);
                     sts4(o, hi[0], hi[1], hi[2], hi[3]);
                     sts4(o + r_tile, lo[0], lo[1], lo[2], lo[3]);
+                    if (MaskTrait<ProR>::value)   // relu'(z) == (a1 > 0)
+                        sts4(st + R.offm[i], v.x > 0.f ? 0x3F800000u : 0u, v.y > 0.f ? 0x3F800000u : 0u,
+                             v.z > 0.f ? 0x3F800000u : 0u, v.w > 0.f ? 0x3F800000u : 0u);
                 }
             }
             if (ProR::kOnes && rows_valid < WG_ROWS) {
@@ -423,14 +438,20 @@ static bool gram_shares(const PclRowGemm &al, int pl, const PclRowGemm &ar, int 
 }  // namespace ws
 
 bool wgrad_ws_supported(const PclRowGemm &al, int pl, const PclRowGemm &ar, int pr, long long P, int M, int N) {
+    if (pl == PCL_PRO_BN_BWD && pr == PCL_PRO_GATHER_BN_ACT_MASK) {
+        // [a1 | mask1]: N = 2 K_r columns, the mask block starts on a 32-channel block, ReLU
+        if (N != 2 * ar.K || ar.K % 32 != 0 || ar.slope != 0.f) return false;
+    }
     const bool combo = (pl == PCL_PRO_BN_ACT && pr == PCL_PRO_BN_ACT_ONES) ||
                        (pl == PCL_PRO_BN_BWD && pr == PCL_PRO_BN_ACT) ||
-                       (pl == PCL_PRO_BN_BWD && pr == PCL_PRO_GATHER_BN_ACT);
+                       (pl == PCL_PRO_BN_BWD && pr == PCL_PRO_GATHER_BN_ACT) ||
+                       (pl == PCL_PRO_BN_BWD && pr == PCL_PRO_GATHER_BN_ACT_MASK);
     if (!combo || M > 128 || N > 160 || M % 4 != 0 || P < 1) return false;
     if (al.K % 4 != 0 || ar.K % 4 != 0 || al.K < M) return false;
     size_t stage, slack;
     int S;
-    ws::wgrad_ws_geometry(M, N, ws::gram_shares(al, pl, ar, pr, M), pr == PCL_PRO_GATHER_BN_ACT, stage, slack, S);
+    ws::wgrad_ws_geometry(M, N, ws::gram_shares(al, pl, ar, pr, M),
+                          pr == PCL_PRO_GATHER_BN_ACT || pr == PCL_PRO_GATHER_BN_ACT_MASK, stage, slack, S);
     return S != 0;
 }
 
@@ -443,6 +464,7 @@ int wgrad_ws_dispatch(const PclRowGemm &al, int pl, const PclRowGemm &ar, int pr
     PCL_WS(PCL_PRO_BN_ACT, PCL_PRO_BN_ACT_ONES, GBnAct, GBnActOnes);
     PCL_WS(PCL_PRO_BN_BWD, PCL_PRO_BN_ACT, GBnBwd, GBnAct);
     PCL_WS(PCL_PRO_BN_BWD, PCL_PRO_GATHER_BN_ACT, GBnBwd, GGatherBnAct);
+    PCL_WS(PCL_PRO_BN_BWD, PCL_PRO_GATHER_BN_ACT_MASK, GBnBwd, GGatherBnActMask);
 #undef PCL_WS
     set_error("pcl_wgrad(ws): unsupported (L prologue %d, R prologue %d) pair", pl, pr);
     return PCL_ERR_UNSUPPORTED;

@@ -23,8 +23,8 @@ import torch
 from . import _lib
 from ._lib import lib, ptr, stream
 
-PRO_PLAIN2, PRO_BN_ACT, PRO_GATHER_BN_ACT, PRO_BN_BWD, PRO_G3_A2, PRO_BN_ACT_ONES = range(6)
-EPI_STORE, EPI_STORE_STATS, EPI_MAXMIN_STATS, EPI_BWD_Y, EPI_BWD_GATHER, EPI_BWD_Y_ROUTED, EPI_BWD_Y_CSR = range(7)
+PRO_PLAIN2, PRO_BN_ACT, PRO_GATHER_BN_ACT, PRO_BN_BWD, PRO_G3_A2, PRO_BN_ACT_ONES, PRO_GATHER_BN_ACT_MASK = range(7)
+EPI_STORE, EPI_STORE_STATS, EPI_MAXMIN_STATS, EPI_BWD_Y, EPI_BWD_GATHER, EPI_BWD_Y_ROUTED, EPI_BWD_Y_MASK = range(7)
 
 _PTR_FIELDS = ("W", "x0", "x1", "U", "V", "scale", "shift", "mean", "rstd", "bscale", "m1", "m2",
                "g3s", "src", "selpos", "out", "gmax", "gmin", "amax", "amin", "stats", "ebias",
@@ -66,8 +66,7 @@ def _bind():
         "pcl_gather_bn_backward": [P, P, P, P, P, P, P, P, P, L, I, I, Fl, P, P, P],
         "pcl_gather_maxmin": [P, P, P, L, I, I, Fl, P, P, P, P, P],
         "pcl_gather_bn_backward_routed": [P, P, P, P, P, P, P, P, P, P, L, I, I, Fl, P, P, P],
-        "pcl_routed_csr": [P, P, L, I, I, P, P, P],
-        "pcl_sel_outer_csr": [P, P, P, P, P, P, Fl, L, I, I, I, P, P],
+        "pcl_gather_bn_backward_masked": [P, P, P, P, P, P, P, P, P, P, L, I, I, Fl, P, P, P],
     }
     for name, argtypes in sigs.items():
         fn = getattr(l, name)
@@ -79,7 +78,7 @@ def _bind():
 SIGNATURE_NAMES = ("pcl_rowgemm", "pcl_wgrad", "pcl_gather_stats", "pcl_bn_param",
                    "pcl_maxpool_finalize", "pcl_maxpool_backward", "pcl_sel_outer",
                    "pcl_gather_bn_backward", "pcl_gather_maxmin", "pcl_gather_bn_backward_routed",
-                   "pcl_routed_csr", "pcl_sel_outer_csr")
+                   "pcl_gather_bn_backward_masked")
 
 
 def _args(**kw):
@@ -119,7 +118,8 @@ def pack_weight(w: torch.Tensor, sign: float = 1.0) -> torch.Tensor:
 
 
 DEBUG = None   # tests: a dict that FusedSAFn.forward fills with its routing state (selpos, y2, U, V, src, BN vectors)
-CSR_ROUTED = 1   # 0: last-layer backward on the round-1 kernels (dense ey operand, per-entry sel_outer) for A/B runs
+DEFER_MASK1 = 1  # 0: layer-2 backward row GEMM on the round-1 kernel (gathered epilogue operand) for A/B runs
+MASK_STASH = 1   # 0: last-layer backward row GEMM on the round-1 kernel (re-reads y2 in its epilogue) for A/B runs
 WS_DBG = 0   # profiling knobs of rowgemm_ws.cu (scratch/ws_branch_knobs.py); 0 in production
 WS_FETCH_EPI = 0   # 1: also route the BWD_Y / BWD_GATHER epilogues to rowgemm_ws.cu (slower today)
 
@@ -259,26 +259,16 @@ class FusedSAFn(torch.autograd.Function):
         Q = W3d.t() @ (t.view(-1, 1) * W3d)               # (C2, C2)
         const = ((t * mu3.double()) - (s3 * c1 / P)) @ W3d  # q0 - r0, (C2)
 
-        # the routed gradient (one entry per (group, channel)) bucketed by row once; both of its consumers walk rows
-        use_csr = bool(CSR_ROUTED and MODE == 3 and slope == 0.0 and C2 <= 128 and C2 % 32 == 0
-                       and 16 <= ns <= 256 and ns & (ns - 1) == 0)
-        if use_csr:
-            rstart = torch.empty((G, ns + 1), dtype=torch.int32, device=dev)
-            ent = torch.empty((G, C3), dtype=torch.int32, device=dev)
-            _lib.call("pcl_routed_csr", ptr(selpos), ptr(g3s), G, C3, ns, ptr(rstart), ptr(ent), stream(g3s),
-                      key=("sa_routed_csr", G, C3))
+        use_mask = bool(MASK_STASH and MODE == 3 and slope == 0.0 and C2 <= 128 and C2 % 32 == 0 and C3 % 16 == 0
+                        and 4 <= ns <= 256 and ns & (ns - 1) == 0)
 
-        # ---- Gram matrix of a2 and the sparse routed outer product (dW3; on the CSR path also the 2nd BN2 sum) ----
+        # ---- Gram matrix of a2 and the sparse routed outer product (dW3; on the mask-stash path also the 2nd BN2 sum) ----
         gram = torch.zeros((C2, C2 + 4), **f32)            # [:, :C2] = a2^T a2, [:, C2] = colsum(a2)
         a2kw = dict(x0=y2, scale=sc2, shift=sh2, slope=slope, K=C2)
         wgrad(PRO_BN_ACT, a2kw, PRO_BN_ACT_ONES, a2kw, P, C2, C2 + 1, gram, name="sa_gram")
         T = torch.zeros((C3, C2), **f32)
-        if use_csr:
-            _lib.call("pcl_sel_outer_csr", ptr(g3s), ptr(rstart), ptr(ent), ptr(y2), ptr(sc2), ptr(sh2), float(slope),
-                      G, ns, C3, C2, ptr(T), stream(g3s), key=("sa_sel_outer", G, C3, C2))
-        else:
-            _lib.call("pcl_sel_outer", ptr(g3s), ptr(selpos), ptr(y2), ptr(sc2), ptr(sh2), float(slope), G,
-                      ns, C3, C2, ptr(T), stream(), key=("sa_sel_outer", G, C3, C2))
+        _lib.call("pcl_sel_outer", ptr(g3s), ptr(selpos), ptr(y2), ptr(sc2), ptr(sh2), float(slope), G,
+                  ns, C3, C2, ptr(T), stream(g3s), key=("sa_sel_outer", G, C3, C2))
         M2, S2 = gram[:, :C2].double(), gram[:, C2].double()
         dW3 = (T.double() - (s3 * c1 / P).view(-1, 1) * S2.view(1, -1)
                - t.view(-1, 1) * (W3d @ M2 - mu3.double().view(-1, 1) * S2.view(1, -1))).float()
@@ -287,13 +277,13 @@ class FusedSAFn(torch.autograd.Function):
         dyh2 = torch.empty((P, C2), **f32)
         sums2 = torch.zeros((2, C2), **f64)
         constf = const.float().contiguous()
-        if use_csr:
-            # warp-specialised kernel: ReLU mask from the operand tile it stages itself, routed term from the CSR;
-            # its epilogue reads nothing of size (P, C2) and accumulates sum(dyhat2) only
-            Wq = pack_weight(Q.t(), sign=-1.0)
-            W3f = W3m.contiguous()
-            rowgemm(PRO_BN_ACT, EPI_BWD_Y_CSR, "sa_b3", W=Wq, x0=y2, x1=W3f, g3s=g3s, src=rstart, selpos=ent, C3=C3,
-                    ns=ns, scale=sc2, shift=sh2, slope=0.0, P=P, K=C2, N=C2, ldw=Wq.shape[-1], out=dyh2,
+        if use_mask:
+            # warp-specialised kernel: the routed gradient enters as a one-hot K block, the ReLU mask comes from the
+            # operand tile the kernel stages itself; its epilogue reads nothing of size (P, C2) and accumulates
+            # sum(dyhat2) only
+            Wb = pack_weight(torch.cat([W3d.t(), -Q.t()], dim=1).float())      # (C2, C3 + C2)
+            rowgemm(PRO_G3_A2, EPI_BWD_Y_MASK, "sa_b3", W=Wb, g3s=g3s, selpos=selpos, C3=C3, ns=ns, x0=y2,
+                    scale=sc2, shift=sh2, slope=0.0, P=P, K=C3 + C2, N=C2, ldw=Wb.shape[-1], out=dyh2,
                     stats=sums2, ebias=constf, eslope=0.0)
             # sum_p dyhat2*xhat2 without a pass: a2 = mask*(gamma2*xhat2 + beta2)  =>
             #   sum_p dA2*mask*xhat2 = (sum_p dA2*a2 - beta2 * sum_p dyhat2) / gamma2,   dA2 = -a2.Q + R.W3 + const
@@ -323,23 +313,47 @@ class FusedSAFn(torch.autograd.Function):
         m2_2 = (sums2[1] / P).float().contiguous()
         dz2kw = dict(x0=dyh2, x1=y2, mean=mu2, rstd=rs2, bscale=sc2, m1=m1_2, m2=m2_2, K=C2)
         a1kw = dict(U=U, V=V, src=src, ns=ns, vsign=-1.0, scale=sc1, shift=sh1, slope=slope, K=C1)
-        dW2 = torch.zeros((C2, C1), **f32)
-        wgrad(PRO_BN_BWD, dz2kw, PRO_GATHER_BN_ACT, a1kw, P, C2, C1, dW2, name="sa_dw2")
-        dyh1 = torch.empty((P, C1), **f32)
-        sums1 = torch.zeros((2, C1), **f64)
         W2t = pack_weight(W2m.t().contiguous())             # (C1, C2): da1 = dz2 . W2
-        rowgemm(PRO_BN_BWD, EPI_BWD_GATHER, "sa_b2", W=W2t, P=P, N=C1, ldw=W2t.shape[-1], out=dyh1,
-                stats=sums1, U=U, V=V, src=src, ns=ns, vsign=-1.0, escale=sc1, eshift=sh1, emean=mu1,
-                erstd=rs1, eslope=slope, **dz2kw)
+        dyh1 = torch.empty((P, C1), **f32)
+        defer = bool(DEFER_MASK1 and MODE == 3 and slope == 0.0 and C1 % 32 == 0 and C1 <= 64 and C2 % 16 == 0
+                     and C2 <= 128 and 16 <= ns and ns & (ns - 1) == 0)
+        if defer:
+            # ONE reduction pass gives dW2 = dz2^T a1 AND dz2^T mask1 (mask1 = relu'(z1), an extra 0/1 block of the
+            # right operand): the BatchNorm-1 backward sums follow by algebra, so the row GEMM da1 = dz2 . W2 stores
+            # its accumulator as is (no gathered epilogue operand) and relu' is applied where y1 is gathered anyway
+            #   sum_p mask1*dA1        = sum_k W2[k,n] (dz2^T mask1)[k,n]
+            #   sum_p mask1*dA1*xhat1  = (sum_k W2[k,n] dW2[k,n] - beta1 * sum_p mask1*dA1) / gamma1
+            dwm = torch.zeros((C2, 2 * C1), **f32)
+            wgrad(PRO_BN_BWD, dz2kw, PRO_GATHER_BN_ACT_MASK, a1kw, P, C2, 2 * C1, dwm, name="sa_dw2")
+            dW2 = dwm[:, :C1]
+            W2d = W2m.double()
+            s0 = (W2d * dwm[:, C1:].double()).sum(dim=0)
+            gamma1 = sc1.double() / rs1.double()
+            beta1 = sh1.double() + mu1.double() * sc1.double()
+            s1 = torch.where(gamma1 != 0, ((W2d * dW2.double()).sum(dim=0) - beta1 * s0) / gamma1, torch.zeros_like(s0))
+            sums1 = torch.stack([s0, s1])
+            rowgemm(PRO_BN_BWD, EPI_STORE, "sa_b2", W=W2t, P=P, N=C1, ldw=W2t.shape[-1], out=dyh1, **dz2kw)
+        else:
+            dW2 = torch.zeros((C2, C1), **f32)
+            wgrad(PRO_BN_BWD, dz2kw, PRO_GATHER_BN_ACT, a1kw, P, C2, C1, dW2, name="sa_dw2")
+            sums1 = torch.zeros((2, C1), **f64)
+            rowgemm(PRO_BN_BWD, EPI_BWD_GATHER, "sa_b2", W=W2t, P=P, N=C1, ldw=W2t.shape[-1], out=dyh1,
+                    stats=sums1, U=U, V=V, src=src, ns=ns, vsign=-1.0, escale=sc1, eshift=sh1, emean=mu1,
+                    erstd=rs1, eslope=slope, **dz2kw)
 
         # ---- layer 1 backward: BN1 backward + scatter onto the source points / centres ---------
         m1_1 = (sums1[0] / P).float().contiguous()
         m2_1 = (sums1[1] / P).float().contiguous()
         dU = torch.zeros((B * N, C1), **f32)
         dV = torch.empty((G, C1), **f32)
-        _lib.call("pcl_gather_bn_backward", ptr(dyh1), ptr(U), ptr(V), ptr(src), ptr(mu1), ptr(rs1),
-                  ptr(sc1), ptr(m1_1), ptr(m2_1), P, ns, C1, -1.0, ptr(dU), ptr(dV), stream(),
-                  key=("sa_b1_scatter", P, C1))
+        if defer:
+            _lib.call("pcl_gather_bn_backward_masked", ptr(dyh1), ptr(U), ptr(V), ptr(src), ptr(mu1), ptr(rs1),
+                      ptr(sc1), ptr(sh1), ptr(m1_1), ptr(m2_1), P, ns, C1, -1.0, ptr(dU), ptr(dV), stream(dyh1),
+                      key=("sa_b1_scatter", P, C1))
+        else:
+            _lib.call("pcl_gather_bn_backward", ptr(dyh1), ptr(U), ptr(V), ptr(src), ptr(mu1), ptr(rs1),
+                      ptr(sc1), ptr(m1_1), ptr(m2_1), P, ns, C1, -1.0, ptr(dU), ptr(dV), stream(),
+                      key=("sa_b1_scatter", P, C1))
         # dW1 = dU^T [xyz|feat] + dV^T [cen|0] over the B*N source points / G centres, dfeat = dU . W1[:, 3:]
         if 3 + C <= 160 and C1 <= 128 and C1 % 4 == 0:
             # narrow outputs over 131k rows: the Gram / weight-gradient kernel (tcgen05, atomics into dW1)

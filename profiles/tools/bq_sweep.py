@@ -32,13 +32,12 @@ def timeit(fn, reps=10):
 
 
 levels = [("SA1", cen1, xyz0, nrm0, (0.1, 0.2, 0.4), (16, 32, 128)), ("SA2", cen2, cen1, feat2, (0.2, 0.4, 0.8), (32, 64, 128))]
-configs = [("legacy", dict(PCL_BQ_LEGACY="1"))]
-for cpb in (2, 4, 8, 16, 32):
-    for u in (4, 8):
-        configs.append((f"new cpb={cpb} U={u}", dict(PCL_BQ_LEGACY="0", PCL_BQ_CPB=str(cpb), PCL_BQ_UNROLL=str(u))))
-configs.append(("new default", dict(PCL_BQ_LEGACY="0")))
+configs = [("legacy", dict(PCL_BQ_LEGACY="1")), ("flat writer, 256 thr", dict(PCL_BQ_WIDE="0", PCL_BQ_THREADS="256", PCL_BQ_CPB="8"))]
+for cpb in (2, 4, 8, 16):
+    configs.append((f"new cpb={cpb} (wide only)", dict(PCL_BQ_CPB=str(cpb))))
+configs.append(("new default", dict()))
 for name, env in configs:
-    for k in ("PCL_BQ_LEGACY", "PCL_BQ_CPB", "PCL_BQ_UNROLL"):
+    for k in ("PCL_BQ_LEGACY", "PCL_BQ_CPB", "PCL_BQ_UNROLL", "PCL_BQ_WIDE", "PCL_BQ_THREADS"):
         os.environ.pop(k, None)
     os.environ.update(env)
     row = []

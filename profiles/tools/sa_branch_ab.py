@@ -1,5 +1,6 @@
-"""Per-kernel times of one big SA1 branch (P = 2,097,152 rows) fwd+bwd: last-layer backward on the round-1 kernels
-(fused.CSR_ROUTED = 0) vs the warp-specialised CSR path, with the gradients of both compared."""
+"""Per-kernel times of one SA1 branch fwd+bwd (P = 2,097,152 rows, and a ns = 32 branch): backward row GEMMs on the
+round-1 kernels (fused.MASK_STASH = fused.DEFER_MASK1 = 0) vs the warp-specialised mask-stash / deferred-mask paths,
+with the gradients compared."""
 import sys, torch
 sys.path.insert(0, '.')
 from torch import nn
@@ -18,8 +19,8 @@ for (r, ns, chans) in ((0.4, 128, (64, 96, 128)), (0.2, 32, (64, 64, 128))):
     seq = nn.Sequential(*layers).to(dev).train()
     g = BallQueryGrouper(r, ns, True)
     grads = {}
-    for csr in (0, 1):
-        fused.CSR_ROUTED = csr
+    for csr in (0, 1, 2):
+        fused.MASK_STASH, fused.DEFER_MASK1 = int(csr >= 1), int(csr >= 2)
         def run():
             for p in seq.parameters(): p.grad = None
             out = sa.sa_branch(g, seq, new_xyz, xyz, nrm); out.square().sum().backward()
@@ -29,6 +30,7 @@ for (r, ns, chans) in ((0.4, 128, (64, 96, 128)), (0.2, 32, (64, 64, 128))):
             torch.cuda.synchronize()
         s = kt.summary()
         tot = sum(v[2] for v in s.values()) / 3
-        print(f"ns={ns} csr={csr} own-kernel total {tot*1e3:.0f} us:", {(k[1][0] if k[1] and isinstance(k[1][0], str) else k[0]): round(v[1]*1e3) for k, v in sorted(s.items(), key=lambda kv: -kv[1][2])[:12]}, flush=True)
+        print(f"ns={ns} variant={csr} own-kernel total {tot*1e3:.0f} us:", {(k[1][0] if k[1] and isinstance(k[1][0], str) else k[0]): round(v[1]*1e3) for k, v in sorted(s.items(), key=lambda kv: -kv[1][2])[:12]}, flush=True)
         grads[csr] = [p.grad.clone() for p in seq.parameters()]
-    print("  max rel grad diff csr vs round-1:", max(((a - b).norm() / b.norm().clamp_min(1e-20)).item() for a, b in zip(grads[1], grads[0])))
+    for c in (1, 2):
+        print(f"  max rel grad diff variant {c} vs round-1:", max(((a - b).norm() / b.norm().clamp_min(1e-20)).item() for a, b in zip(grads[c], grads[0])))

@@ -8,7 +8,7 @@ Checked per network:
   * its state_dict loads into this repo's mirror (pointcloudlib_b200.networks.*) key for key;
   * its logits equal the float64 CPU restatement of the reference graph (oracle/model_oracle.py, same
     weights) within 1e-3 of the logit scale;
-  * on the GPU, its logits equal the mirror's (same kernels underneath) to 1e-5, and where the network
+  * on the GPU, its logits equal the mirror's (same kernels underneath) to 1e-4, and where the network
     has `BallQueryGrouper -> transpose -> Sequential(Conv,BN,ReLU x3) -> transpose -> argmax(dim=2)[1]`
     (networks/cls/pointnet2.py:51-57) that chain ran on the FUSED kernels (rowgemm_ws launches counted),
     i.e. the grouped tensor was not materialised although the file is unchanged.
@@ -149,4 +149,5 @@ def test_reference_network_file_runs_unchanged(case, device):
         if device == "cuda" and mirror is not None:
             mirror = mirror.to(device)
             np.random.seed(0)
-            _close(out, mirror(*dev_args), f"{cls}: reference file on the shim vs the mirror", rtol=1e-5)
+            # same kernels underneath; the statistics are reduced with atomics, so the two runs differ by rounding order
+            _close(out, mirror(*dev_args), f"{cls}: reference file on the shim vs the mirror", rtol=1e-4)

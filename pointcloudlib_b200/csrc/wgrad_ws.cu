@@ -94,13 +94,19 @@ struct GGatherBnActMask : GGatherBnAct {
 template <class Pro> struct MaskTrait { static constexpr bool value = false; };
 template <> struct MaskTrait<GGatherBnActMask> { static constexpr bool value = true; };
 
-constexpr int kWgThreads = 9 * 32;
+// Transform warps: 16 (round 1: 8).  ncu on the 8-warp kernel: issue active 36-39 %, the stalls are fixed-latency
+// dependencies ("wait" 1.6-1.8 per issue) and shared-memory round trips — two warps per scheduler cannot cover
+// them.  Sixteen warps halve the pieces (and the piece registers) per thread and double the warps per scheduler.
+constexpr int kTW = 16;                      // transform warps
+constexpr int kTT = kTW * 32;                // transform threads
+constexpr int kWgThreads = (kTW + 1) * 32;
 constexpr int WG_ROWS = 32;     // rows per chunk = MMA K of 4 x 8
 constexpr int WG_BLK = 4096;    // bytes of one 32-channel block of a tile (hi or lo)
-constexpr int NPL = 4, NPR = 5; // max 16-byte pieces per thread and chunk: L (128 ch), R (160 ch)
+constexpr int NPL = (128 / 4 * WG_ROWS + kTT - 1) / kTT;   // max 16-byte pieces per thread and chunk: L (128 ch)
+constexpr int NPR = (160 / 4 * WG_ROWS + kTT - 1) / kTT;   // R (160 ch)
 constexpr int kTabQuads = 40;
 constexpr int kSlackBytes = 2 * WG_BLK + 1024;       // the 128-lane operand read past the last staged block
-constexpr int kSrcSlot = NPR * 256 * 4;              // gather-index slots of one chunk   // channel quads covered by a parameter table (160 channels)
+constexpr int kSrcSlot = NPR * kTT * 4;              // gather-index slots of one chunk   // channel quads covered by a parameter table (160 channels)
 
 // one operand (L or R) of the transform: piece bookkeeping of this thread
 template <int NP, class Pro>
@@ -138,7 +144,7 @@ wgrad_ws_kernel(const PclRowGemm al, const PclRowGemm ar, long long P, int M, in
     }
     if (tid == 32) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(smem_u32(&s_full[s]), 8);
+            mbar_init(smem_u32(&s_full[s]), kTW);
             mbar_init(smem_u32(&s_free[s]), 1);
         }
         mbar_init(smem_u32(&s_done), 1);
@@ -181,7 +187,7 @@ wgrad_ws_kernel(const PclRowGemm al, const PclRowGemm ar, long long P, int M, in
     const long long c_end = n_chunks < c_begin + per ? n_chunks : c_begin + per;
     const int total = c_end > c_begin ? (int)(c_end - c_begin) : 0;
 
-    if (warp < 8) {
+    if (warp < kTW) {
         // ============================ TRANSFORM warps ============================
         Operand<NPL, ProL> L;
         Operand<NPR, ProR> R;
@@ -191,7 +197,7 @@ wgrad_ws_kernel(const PclRowGemm al, const PclRowGemm ar, long long P, int M, in
         L.n_live = 0;
 #pragma unroll
         for (int i = 0; i < NPL; ++i) {
-            const int e = tid + 256 * i;
+            const int e = tid + kTT * i;
             L.row[i] = e / liveL;
             L.kq[i] = e % liveL;
             L.off[i] = mn_off(L.row[i] & 31, L.kq[i]);
@@ -201,7 +207,7 @@ wgrad_ws_kernel(const PclRowGemm al, const PclRowGemm ar, long long P, int M, in
         R.n_live = 0;
 #pragma unroll
         for (int i = 0; i < NPR; ++i) {
-            const int e = tid + 256 * i;
+            const int e = tid + kTT * i;
             R.row[i] = e / liveR;
             R.kq[i] = e % liveR;
             R.off[i] = 2 * l_tile + mn_off(R.row[i] & 31, R.kq[i]);
@@ -217,7 +223,7 @@ wgrad_ws_kernel(const PclRowGemm al, const PclRowGemm ar, long long P, int M, in
         // need, so they arrive with a whole pipeline depth of lead time instead of a dependent register load
         static_assert(!ProL::kSrc, "gathered L operands are not implemented");
         const uint32_t src_base = sbase + S * stage_bytes + kSlackBytes;   // [PD + 1][NPR][256] ints
-        auto src_slot = [&](int k, int i) { return src_base + (uint32_t)((((k % (PD + 1)) * NPR + i) * 256 + tid) * 4); };
+        auto src_slot = [&](int k, int i) { return src_base + (uint32_t)((((k % (PD + 1)) * NPR + i) * kTT + tid) * 4); };
         int i_c = 0;
         auto issue_next = [&]() {
             if (i_c < total) {
@@ -343,9 +349,9 @@ wgrad_ws_kernel(const PclRowGemm al, const PclRowGemm ar, long long P, int M, in
         if (total > 0 && !(dbg & 128)) {
             mbar_wait(smem_u32(&s_done), 0);
             tc_fence_after();
-            const int q = warp & 3, h = warp >> 2;
+            const int q = warp & 3, h = warp >> 2;   // TMEM lane quarter; kTW / 4 warps share a quarter's columns
             const int m = q * 32 + lane;
-            for (int c0 = h * 16; c0 < Npad; c0 += 32) {
+            for (int c0 = h * 16; c0 < Npad; c0 += 16 * (kTW / 4)) {
                 float v[16];
                 tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
                 if (m < M) {

@@ -1,0 +1,182 @@
+"""Shared dense MLP on channels-last rows: [1x1 conv -> BatchNorm(train) -> act]* as row GEMMs on the tcgen05 kernels.
+
+Reference call sites (all `Conv(kernel 1) -> BatchNorm -> ReLU/LeakyReLU` stacks applied per point):
+  * PointNetFeaturePropagation, misc/ops.py:97-107 (Conv1d bias=True + BatchNorm1d + ReLU on (B,C,N));
+  * the PointConv shared MLP, misc/pointconv_utils.py:384-389 (Conv2d bias=True + BatchNorm2d + ReLU on (B,C,ns,S));
+  * DGCNN's conv5, networks/cls/dgcnn.py:84-86,113 (Conv1d 512->1024 bias=False + BatchNorm1d + LeakyReLU(0.2)).
+The reference permutes to channels-first for cuDNN and back; here the activation matrix stays (P rows, C channels):
+    y_1 = x . W_1^T                      pcl_rowgemm PLAIN2 -> STORE_STATS   (BatchNorm sums in the GEMM epilogue)
+    y_l = act(bn_{l-1}(y_{l-1})) . W_l^T pcl_rowgemm BN_ACT -> STORE_STATS   (BatchNorm + act in the GEMM prologue)
+    out = act(bn_L(y_L))
+and the backward is the matching chain: BatchNorm backward in the prologue of both the data-gradient row GEMM
+(BN_BWD -> BWD_Y: act' and the next layer's BatchNorm sums in its epilogue) and the weight-gradient reduction
+(pcl_wgrad BN_BWD x BN_ACT).  3xTF32 (fp32-equivalent).  A conv bias in front of a training-mode BatchNorm cancels
+(it only shifts the running mean, which is updated accordingly; its gradient is exactly zero).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as TF
+
+from . import _lib, fused
+from .fused import (EPI_BWD_Y, EPI_STORE, EPI_STORE_STATS, PRO_BN_ACT, PRO_BN_BWD, PRO_PLAIN2, bn_param,
+                    pack_weight, rowgemm, wgrad)
+
+
+def _widths_ok(cin, chans):
+    """Channel widths the row-GEMM tiles cover (N % 32 == 0, N <= 128 or N % 128 == 0; K % 16 == 0 past layer 1)."""
+    ok_n = lambda n: n % 32 == 0 and (n <= 128 or n % 128 == 0)
+    return cin >= 1 and all(ok_n(c) for c in chans)
+
+
+def supported(x, convs, bns, acts) -> bool:
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[0] >= 1):
+        return False
+    if not convs or len(convs) != len(bns) or len(convs) != len(acts):
+        return False
+    slopes = set()
+    for c, b, a in zip(convs, bns, acts):
+        if b is None or not b.training or b.weight is None:
+            return False
+        if isinstance(a, torch.nn.LeakyReLU):
+            slopes.add(float(a.negative_slope))
+        elif isinstance(a, torch.nn.ReLU):
+            slopes.add(0.0)
+        else:
+            return False
+        if any(k != 1 for k in c.kernel_size) or c.groups != 1:
+            return False
+    if len(slopes) != 1 or not 0.0 <= next(iter(slopes)) <= 1.0:
+        return False
+    return _widths_ok(x.shape[1], [c.weight.shape[0] for c in convs])
+
+
+def _wgrad_any(pro_l, kw_l, pro_r, kw_r, P, M, N, out, name):
+    """dW (M,N) = L^T R.  The tcgen05 reduction kernels hold one accumulator tile (M <= 128 lanes, N <= 160 columns):
+    wider LEFT operands are walked in 128-channel slices (same row stride K, pointers advanced by the slice offset);
+    wider right operands take the mma.sync 3xTF32 kernel, which tiles both."""
+    if N <= 160:
+        for m0 in range(0, M, 128):
+            kl = dict(kw_l)
+            if m0:
+                for f, v in kw_l.items():
+                    if torch.is_tensor(v):
+                        kl[f] = v.reshape(-1)[m0:]      # (P, K) row-major -> column m0 onwards; per-channel vectors alike
+            wgrad(pro_l, kl, pro_r, kw_r, P, min(128, M - m0), N, out[m0:m0 + 128], name=name)
+        return
+    old = fused.MODE
+    fused.MODE = 1
+    try:
+        wgrad(pro_l, kw_l, pro_r, kw_r, P, M, N, out, name=name)
+    finally:
+        fused.MODE = old
+
+
+class RowMLPFn(torch.autograd.Function):
+    """out (P, C_L) = act(bn_L(... act(bn_1(x . W_1^T)) ... . W_L^T)); x (P, Cin) fp32 rows."""
+
+    @staticmethod
+    def forward(ctx, x, slope, bns, biases, *params):
+        fused._bind()
+        L = len(bns)
+        Ws, gammas, betas = params[:L], params[L:2 * L], params[2 * L:3 * L]
+        x = _lib.f32(x)
+        P, Cin = x.shape
+        dev = x.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        ys, bnp = [], []
+        h, K = None, Cin
+        for l in range(L):
+            Wm = Ws[l].reshape(Ws[l].shape[0], -1)
+            C = Wm.shape[0]
+            Wp = pack_weight(Wm)
+            y = torch.empty((P, C), **f32)
+            stats = torch.zeros((2, C), dtype=torch.float64, device=dev)
+            if l == 0:
+                rowgemm(PRO_PLAIN2, EPI_STORE_STATS, "mlp_l1", W=Wp, x0=x, c0=Cin, c1=0, P=P, K=Cin, N=C,
+                        ldw=Wp.shape[-1], out=y, stats=stats)
+            else:
+                sc, sh, _, _ = bnp[-1]
+                rowgemm(PRO_BN_ACT, EPI_STORE_STATS, "mlp_l", W=Wp, x0=h, scale=sc, shift=sh, slope=slope, P=P, K=K,
+                        N=C, ldw=Wp.shape[-1], out=y, stats=stats)
+            p = bn_param(stats, P, bns[l], C)
+            if biases[l] is not None and bns[l].track_running_stats and bns[l].running_mean is not None:
+                m = bns[l].momentum if bns[l].momentum is not None else 0.1
+                bns[l].running_mean.add_(biases[l].detach(), alpha=m)     # the batch mean of y + bias
+            bnp.append(p)
+            ys.append(y)
+            h, K = y, C
+        sc, sh, _, _ = bnp[-1]
+        out = TF.leaky_relu(torch.addcmul(sh, h, sc), slope) if slope else torch.relu_(torch.addcmul(sh, h, sc))
+        flat = [t for p in bnp for t in p]
+        ctx.save_for_backward(x, *ys, *flat, *Ws)
+        ctx.meta = (L, slope, [b is not None for b in biases], [tuple(w.shape) for w in Ws])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L, slope, has_bias, wshapes = ctx.meta
+        saved = ctx.saved_tensors
+        x, ys = saved[0], saved[1:1 + L]
+        flat = saved[1 + L:1 + L + 4 * L]
+        Ws = saved[1 + 5 * L:]
+        bnp = [flat[4 * l:4 * l + 4] for l in range(L)]           # (scale, shift, mean, rstd)
+        P, Cin = x.shape
+        dev = x.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        f64 = dict(dtype=torch.float64, device=dev)
+        dWs, dgs, dbs = [None] * L, [None] * L, [None] * L
+        # output layer: dyhat_L = dout * act'(z_L) and its BatchNorm sums (one elementwise + two reductions)
+        sc, sh, mu, rs = bnp[L - 1]
+        z = torch.addcmul(sh, ys[L - 1], sc)
+        dyh = _lib.f32(dout) * (torch.where(z > 0, 1.0, slope) if slope else (z > 0))
+        xh = (ys[L - 1] - mu) * rs
+        sums = torch.stack([dyh.sum(dim=0, dtype=torch.float64), (dyh * xh).sum(dim=0, dtype=torch.float64)])
+        del z, xh
+        dx = None
+        for l in range(L - 1, -1, -1):
+            sc, sh, mu, rs = bnp[l]
+            C = ys[l].shape[1]
+            dgs[l], dbs[l] = sums[1].float(), sums[0].float()
+            m1 = (sums[0] / P).float().contiguous()
+            m2 = (sums[1] / P).float().contiguous()
+            dzkw = dict(x0=dyh, x1=ys[l], mean=mu, rstd=rs, bscale=sc, m1=m1, m2=m2, K=C)
+            Wm = Ws[l].reshape(C, -1)
+            Kin = Wm.shape[1]
+            dW = torch.zeros((C, Kin), **f32)
+            if l > 0:
+                psc, psh, pmu, prs = bnp[l - 1]
+                akw = dict(x0=ys[l - 1], scale=psc, shift=psh, slope=slope, K=Kin)
+                _wgrad_any(PRO_BN_BWD, dzkw, PRO_BN_ACT, akw, P, C, Kin, dW, "mlp_dw")
+                Wt = pack_weight(Wm.t().contiguous())              # (Kin, C): da = dz . W
+                dprev = torch.empty((P, Kin), **f32)
+                sums = torch.zeros((2, Kin), **f64)
+                rowgemm(PRO_BN_BWD, EPI_BWD_Y, "mlp_b", W=Wt, P=P, N=Kin, ldw=Wt.shape[-1], out=dprev, stats=sums,
+                        ey=ys[l - 1], escale=psc, eshift=psh, emean=pmu, erstd=prs, eslope=slope, **dzkw)
+                dyh = dprev
+            else:
+                # first layer: dz_1 is materialised once (P x C_1) for the two library GEMMs against the raw input
+                dz = sc * (dyh - m1 - (ys[0] - mu) * rs * m2)
+                dW = dz.t() @ x
+                if ctx.needs_input_grad[0]:
+                    dx = dz @ Wm
+            dWs[l] = dW.view(wshapes[l])
+        return (dx, None, None, None, *dWs, *dgs, *dbs)
+
+
+def row_mlp(x, convs, bns, acts):
+    """x (P, Cin) -> (P, C_L) through [conv 1x1 -> BatchNorm(train) -> act]* (see module docstring)."""
+    a0 = acts[0]
+    slope = float(a0.negative_slope) if isinstance(a0, torch.nn.LeakyReLU) else 0.0
+    biases = [c.bias for c in convs]
+    out = RowMLPFn.apply(x, slope, list(bns), biases, *[c.weight for c in convs], *[b.weight for b in bns],
+                         *[b.bias for b in bns])
+    return out
+
+
+def conv_bias_zero_grads(convs):
+    """(Reference semantics) a conv bias in front of BatchNorm receives a mathematically zero gradient: give it one so
+    optimizers that expect .grad on every parameter see zeros instead of None."""
+    for c in convs:
+        if c.bias is not None and c.bias.requires_grad and c.bias.grad is None:
+            c.bias.grad = torch.zeros_like(c.bias)

@@ -74,6 +74,14 @@ class PointNetFeaturePropagation(Module):
         else:
             new_points = interpolated_points
 
+        from .. import dense
+        from ..sa import FUSED
+        convs, bns = list(self.mlp_convs), list(self.mlp_bns)
+        rows = new_points.reshape(B * N, -1)
+        if FUSED and dense.supported(rows, convs, bns, [self.relu] * len(convs)):
+            # the Conv1d(bias) -> BatchNorm1d -> ReLU stack of ops.py:97-107 on the channels-last rows it already
+            # has (no permutes): tcgen05 row GEMMs with BatchNorm / ReLU fused into their prologues and epilogues
+            return dense.row_mlp(rows.contiguous(), convs, bns, [self.relu] * len(convs)).view(B, N, -1)
         new_points = new_points.permute(0, 2, 1)
         for i, conv in enumerate(self.mlp_convs):
             bn = self.mlp_bns[i]

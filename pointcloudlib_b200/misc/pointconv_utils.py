@@ -126,9 +126,18 @@ class WeightNet(Module):
 
 def _density_conv_tail(mod, B, S, new_points, grouped_xyz_norm, grouped_density):
     """pointconv_utils.py:384-397 (shared by the set-abstraction and interpolation modules)."""
-    new_points = new_points.permute(0, 3, 2, 1)  # [B, C+D, nsample, npoint]
-    for i in range(len(mod.mlp_convs)):
-        new_points = mod.relu(mod.mlp_bns[i](mod.mlp_convs[i](new_points)))
+    from .. import dense
+    from ..sa import FUSED
+    convs, bns = list(mod.mlp_convs), list(mod.mlp_bns)
+    rows = new_points.reshape(-1, new_points.shape[-1])      # (B*S*ns, 3+D): already channels-last
+    if FUSED and dense.supported(rows, convs, bns, [mod.relu] * len(convs)):
+        # the shared MLP of pointconv_utils.py:384-389 as tcgen05 row GEMMs (BatchNorm / ReLU fused in)
+        h = dense.row_mlp(rows.contiguous(), convs, bns, [mod.relu] * len(convs))
+        new_points = h.view(new_points.shape[0], new_points.shape[1], new_points.shape[2], -1).permute(0, 3, 2, 1)
+    else:
+        new_points = new_points.permute(0, 3, 2, 1)  # [B, C+D, nsample, npoint]
+        for i in range(len(mod.mlp_convs)):
+            new_points = mod.relu(mod.mlp_bns[i](mod.mlp_convs[i](new_points)))
     grouped_xyz = grouped_xyz_norm.permute(0, 3, 2, 1)
     weights = mod.weightnet(grouped_xyz)
     new_points = new_points * grouped_density.permute(0, 3, 2, 1)

@@ -83,10 +83,21 @@ class DGCNN(Module):
         x2 = edge_conv(x1, self.knn, self.k, self.conv2)
         x3 = edge_conv(x2, self.knn, self.k, self.conv3)
         x4 = edge_conv(x3, self.knn, self.k, self.conv4)
-        x = torch.cat((x1, x2, x3, x4), dim=1)
-        x = self.conv5(x)
-        x1 = x.max(dim=2).values.reshape(batch_size, -1)
-        x2 = x.mean(dim=2).reshape(batch_size, -1)
+        from ... import dense
+        from ...sa import FUSED
+        conv5, bn5, act5 = list(self.conv5)
+        if FUSED and x.is_cuda and dense.supported(x1.new_empty((1, 512)), [conv5], [bn5], [act5]):
+            # conv5 on channels-last rows (B*N, 512) -> (B*N, 1024): tcgen05 row GEMM with the BatchNorm sums in its
+            # epilogue; max / mean over the N rows of a cloud (dgcnn.py:113-116)
+            rows = torch.cat([t.transpose(1, 2) for t in (x1, x2, x3, x4)], dim=2).reshape(-1, 512)
+            x = dense.row_mlp(rows, [conv5], [bn5], [act5]).view(batch_size, -1, 1024)
+            x1 = x.max(dim=1).values
+            x2 = x.mean(dim=1)
+        else:
+            x = torch.cat((x1, x2, x3, x4), dim=1)
+            x = self.conv5(x)
+            x1 = x.max(dim=2).values.reshape(batch_size, -1)
+            x2 = x.mean(dim=2).reshape(batch_size, -1)
         x = torch.cat((x1, x2), 1)
         x = TF.leaky_relu(self.bn6(self.linear1(x)), 0.2)
         x = self.dp1(x)

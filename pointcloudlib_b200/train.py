@@ -80,10 +80,18 @@ class Trainer:
     the step launches the tail's NCCL all-reduce on a side stream gated on that event, so it runs over NVLink
     while the first level's backward (the largest part of the step) is still executing; only the head
     region's all-reduce (tens of KB: launch latency) follows the backward.  NCCL itself stays outside the
-    graph: eager collectives on a side stream need no capture support and cannot deadlock the replay."""
+    graph: eager collectives on a side stream need no capture support and cannot deadlock the replay.
+
+    MEASURED (2 x B200, profiles/r02/ddp_check_2gpu.txt, bench lines beside it): the overlapped mode is SLOWER
+    than the single blocking all-reduce (13.23 vs 12.81 ms per step; 8.28 vs 7.92 ms on the smaller check): the
+    row-GEMM kernels are persistent, one CTA per SM with ~200 KB of shared memory and 544 threads, so the NCCL
+    CTAs cannot co-reside — they take whole SMs, and the next 148-CTA launch waits on the SMs they hold (a
+    straggler tail per kernel) for longer than the 0.13 ms the collective costs when it runs alone.  Hence
+    overlap_allreduce defaults to False (ONE blocking all-reduce of the 7 MB bucket right after the graph
+    replay); the bucketed mode stays available for models whose kernels leave SMs free."""
 
     def __init__(self, model, lr=0.02, momentum=0.9, weight_decay=0.0, distributed=None, graph=False,
-                 graph_warmup=3, loss_fn=None, overlap_allreduce=True, head_fraction=0.05):
+                 graph_warmup=3, loss_fn=None, overlap_allreduce=False, head_fraction=0.05):
         self.model = model
         self.loss_fn = loss_fn if loss_fn is not None else soft_cross_entropy_loss
         self.opt = FlatSGD(model, lr, momentum, weight_decay)

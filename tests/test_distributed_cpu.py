@@ -40,7 +40,7 @@ def _worker(rank, world, port, out_dir, head_fraction=0.05):
         with torch.no_grad():
             for p in model.parameters():
                 p.add_(1.0)
-    tr = Trainer(model, lr=0.1, head_fraction=head_fraction)
+    tr = Trainer(model, lr=0.1, head_fraction=head_fraction, overlap_allreduce=True)
     assert tr.world == world and tr.distributed
     assert (tr._split > 0) == (head_fraction > 0.5), tr.allreduce_mode
     torch.testing.assert_close(tr.opt.params, torch.cat([p.reshape(-1) for p in _make_model().parameters()]))

@@ -297,3 +297,49 @@ def test_fused_sa_branch_at_the_bench_shape():
     assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= 1e-3 * scale
     for (n, p), (_, q) in zip(seq_d.named_parameters(), ref_seq.named_parameters()):
         assert _rel(p.grad, q.grad) <= 2e-3, f"{n}: rel-L2 {_rel(p.grad, q.grad):.3e}"
+
+
+@pytest.mark.parametrize("P,cin,chans,slope,bias", [
+    (32768, 150, (128, 128, 128), 0.0, True),      # part-seg fp1: Conv1d(bias) + BatchNorm1d + ReLU (ops.py:97-107)
+    (8192, 384, (256, 128), 0.0, True),            # fp2
+    (32768, 512, (1024,), 0.2, False),             # DGCNN conv5 (dgcnn.py:84-86)
+    (5000, 6, (64, 64, 128), 0.0, True),           # PointConv shared MLP, ragged P
+])
+def test_row_mlp_matches_reference_sequence(P, cin, chans, slope, bias):
+    """pointcloudlib_b200.dense.row_mlp vs the reference's channels-first Conv1d -> BatchNorm1d -> act stack in
+    float64 on the CPU.  Forward 1e-3 of max; gradients 2e-3 relative L2 (5e-3 for the input gradient)."""
+    from pointcloudlib_b200 import dense
+    torch.manual_seed(5)
+    g = torch.Generator().manual_seed(6)
+    convs, bns, c = [], [], cin
+    for co in chans:
+        convs.append(nn.Conv1d(c, co, 1, bias=bias))
+        bn = nn.BatchNorm1d(co)
+        bn.weight.data = torch.randn(co, generator=g)
+        bn.bias.data = 0.3 * torch.randn(co, generator=g)
+        bns.append(bn)
+        c = co
+    act = nn.LeakyReLU(slope) if slope else nn.ReLU()
+    x = torch.randn(P, cin, generator=g)
+    ref_convs, ref_bns = [copy.deepcopy(m).double() for m in convs], [copy.deepcopy(m).double() for m in bns]
+    x64 = x.double().requires_grad_(True)
+    h = x64.t().unsqueeze(0)                               # (1, C, P) channels-first, like the reference
+    for cv, bn in zip(ref_convs, ref_bns):
+        h = act(bn(cv(h)))
+    ref = h.squeeze(0).t()
+    gout = torch.randn(ref.shape, generator=g)
+    ref.backward(gout.double())
+
+    convs_d, bns_d = [m.to(DEV).train() for m in convs], [m.to(DEV).train() for m in bns]
+    xd = x.to(DEV).requires_grad_(True)
+    assert dense.supported(xd, convs_d, bns_d, [act] * len(chans))
+    out = dense.row_mlp(xd, convs_d, bns_d, [act] * len(chans))
+    out.backward(gout.to(DEV))
+    scale = ref.abs().max().item()
+    assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= 1e-3 * scale
+    for i, (cv, rcv, bn, rbn) in enumerate(zip(convs_d, ref_convs, bns_d, ref_bns)):
+        assert _rel(cv.weight.grad, rcv.weight.grad) <= 2e-3, f"conv {i}: {_rel(cv.weight.grad, rcv.weight.grad):.3e}"
+        assert _rel(bn.weight.grad, rbn.weight.grad) <= 2e-3 and _rel(bn.bias.grad, rbn.bias.grad) <= 2e-3, i
+        np.testing.assert_allclose(bn.running_mean.cpu().numpy(), rbn.running_mean.float().numpy(), rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(bn.running_var.cpu().numpy(), rbn.running_var.float().numpy(), rtol=2e-3, atol=1e-4)
+    assert _rel(xd.grad, x64.grad) <= 5e-3

@@ -247,6 +247,16 @@ int pcl_gather_bn_backward_masked(const float *dA, const float *U, const float *
                                   const float *m1, const float *m2, long long P, int ns, int C, float vsign,
                                   float *dU, float *dV, void *stream);
 
+/* Output side of a dense [1x1 conv -> BatchNorm(train) -> ReLU/LeakyReLU]* stack on channels-last rows
+ * (misc/ops.py:97-107, misc/pointconv_utils.py:384-389, networks/cls/dgcnn.py:84-86): y (P,C), C % 4 == 0.
+ * forward: out = act(scale*y + shift).  backward: dyh = dout*act'(scale*y + shift) and
+ * sums (2,C) fp64 += (sum dyh, sum dyh*(y-mean)*rstd) in ONE pass (sums zeroed by the caller). */
+int pcl_bn_act_forward(const float *y, const float *scale, const float *shift, float slope, long long P, int C,
+                       float *out, void *stream);
+int pcl_bn_act_backward(const float *dout, const float *y, const float *scale, const float *shift,
+                        const float *mean, const float *rstd, float slope, long long P, int C, float *dyh,
+                        double *sums, void *stream);
+
 /* ---- a7 / a8: fused EdgeConv (networks/cls/dgcnn.py:29-50 + :72-83,100-111) -------------------
  * W.[x_j - x_i ; x_i] = W1.x_j + (W2-W1).x_i  =>  y[i,j] = u[src[i,j]] + vsign*v[i] on per-point
  * projections u, v (pcl_rowgemm PCL_PRO_PLAIN2); statistics by pcl_gather_stats; then:

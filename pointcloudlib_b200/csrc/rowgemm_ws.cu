@@ -110,8 +110,14 @@ struct WEpiBwdYMask {
 template <class Epi> struct EpiTraits { static constexpr bool kMask = false; };
 template <> struct EpiTraits<WEpiBwdYMask> { static constexpr bool kMask = true; };
 
-constexpr int kTransformWarps = 8, kEpilogueWarps = 8;
-constexpr int kThreadsWS = (kTransformWarps + kEpilogueWarps + 1) * 32;   // 544
+// 16 transform warps (round 1: 8).  The transform was the critical stage: per 16-float chunk a thread spent ~200
+// instructions on its four 16-byte pieces (address arithmetic + cp.async issue, read-back, BatchNorm / ReLU, TF32
+// split, two stores) with two warps per scheduler — dependent-issue bound at ~1500-1800 cycles per chunk against
+// ~870 cycles of tensor-core work.  With 16 warps a thread owns two pieces and each scheduler has four transform
+// warps to interleave.
+constexpr int kTransformWarps = 16, kEpilogueWarps = 8;
+constexpr int kTT = kTransformWarps * 32;                                // transform threads
+constexpr int kThreadsWS = (kTransformWarps + kEpilogueWarps + 1) * 32;   // 800
 constexpr int TILE_ROWS = 256;    // activation rows per macro tile = MMA N
 constexpr int MMA_M = 128;        // output channels per pass, zero padded
 
@@ -125,8 +131,9 @@ struct Cfg {
     static constexpr int A_BYTES = TILE_ROWS * KC * 4;       // one of hi / lo
     static constexpr int W_BYTES = MMA_M * KC * 4;
     static constexpr int STAGE = 2 * A_BYTES + 2 * W_BYTES;
-    static constexpr int RSTEP = 256 / CPR;                  // row step between a thread's pieces
-    static constexpr int NWJ = 2 * MMA_M * CPR / 256;        // weight pieces per thread and chunk (max)
+    static constexpr int RSTEP = kTT / CPR;                  // row step between a thread's pieces
+    static constexpr int NPT = TILE_ROWS / RSTEP;            // activation pieces per thread and chunk
+    static constexpr int NWJ = (2 * MMA_M * CPR + kTT - 1) / kTT;   // weight pieces per thread and chunk (max)
 };
 
 // stages of the operand ring; a stage is [act hi 256 x KC | act lo | W hi BN x KC | W lo] floats.  The
@@ -139,7 +146,7 @@ constexpr int kLag = 2;   // the transform refills the stage of chunk c - kLag (
 template <int KC, class Pro, class Epi, int S = stages<KC, Epi>()>
 __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowGemm a) {
     using C = Cfg<KC>;
-    constexpr int CPR = C::CPR;
+    constexpr int CPR = C::CPR, NPT = C::NPT;
     constexpr bool kMaskStash = EpiTraits<Epi>::kMask;
     // instruction descriptor: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), both K-major, N>>3, M>>4
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TILE_ROWS >> 3) << 17) |
@@ -197,9 +204,9 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
         // ============================ TRANSFORM warps ============================
         const int a_c = tid % CPR, a_row = tid / CPR;
         const int stride = Pro::stride(a), kbase = Pro::kbase(a);
-        uint32_t aoff[CPR];   // swizzled byte offset of this thread's pieces inside an operand tile
+        uint32_t aoff[NPT];   // swizzled byte offset of this thread's pieces inside an operand tile
 #pragma unroll
-        for (int i = 0; i < CPR; ++i) aoff[i] = sw_off<KC>(a_row + C::RSTEP * i, a_c);
+        for (int i = 0; i < NPT; ++i) aoff[i] = sw_off<KC>(a_row + C::RSTEP * i, a_c);
         // this thread's weight pieces: smem offset inside a stage, global pointer at K column 0
         uint32_t woff[C::NWJ];
         const float *wptr[C::NWJ];
@@ -209,7 +216,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
             n_w = 0;
 #pragma unroll
             for (int j = 0; j < C::NWJ; ++j) {
-                const int e = tid + 256 * j;
+                const int e = tid + kTT * j;
                 const int half = e >= per_half ? 1 : 0, r = e - half * per_half;
                 const int n = r / CPR, c = r % CPR;
                 woff[j] = 2 * C::A_BYTES + half * w_bytes + sw_off<KC>(n, c);
@@ -221,29 +228,29 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
 
         // ---- issue cursor (S-1 chunks ahead of the consume cursor) ----
         int i_pass = 0, i_lt = 0, i_kc = 0, i_c = 0;
-        long long ebase[CPR];
+        long long ebase[NPT];
         uint32_t i_ok = 0;
-        int srcN[CPR];
-        auto load_src = [&](int lt, int (&dst)[CPR]) {
+        int srcN[NPT];
+        auto load_src = [&](int lt, int (&dst)[NPT]) {
             const long long row0 = (blockIdx.x + (long long)(lt % my_tiles) * gridDim.x) * TILE_ROWS;
 #pragma unroll
-            for (int i = 0; i < CPR; ++i) {
+            for (int i = 0; i < NPT; ++i) {
                 const long long p = row0 + a_row + C::RSTEP * i;
                 dst[i] = p < a.P ? __ldg(a.src + p) : 0;
             }
         };
-        auto enter_tile = [&](int lt, const int (&srcv)[CPR]) {
+        auto enter_tile = [&](int lt, const int (&srcv)[NPT]) {
             const long long row0 = (blockIdx.x + (long long)lt * gridDim.x) * TILE_ROWS;
             i_ok = 0;
 #pragma unroll
-            for (int i = 0; i < CPR; ++i) {
+            for (int i = 0; i < NPT; ++i) {
                 const long long p = row0 + a_row + C::RSTEP * i;
                 if (p < a.P) i_ok |= 1u << i;
                 ebase[i] = (Pro::kSrc ? (long long)srcv[i] : p) * stride;
             }
         };
         if (total_chunks > 0) {
-            int src0[CPR] = {};
+            int src0[NPT] = {};
             if (Pro::kSrc) {
                 load_src(0, src0);
                 load_src(1, srcN);
@@ -257,7 +264,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
                 if (!(Pro::kOneHot && k0 < kbase) && !(dbg & 4)) {
                     const int kcol = k0 - kbase + a_c * 4;
 #pragma unroll
-                    for (int i = 0; i < CPR; ++i)
+                    for (int i = 0; i < NPT; ++i)
                         Pro::issue(a, ebase[i], kcol, (i_ok >> i) & 1u, st + aoff[i], st + C::A_BYTES + aoff[i]);
                 }
                 if (!(dbg & 8)) {
@@ -274,13 +281,13 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
                         if (i_pass < n_pass) set_w(i_pass);
                     }
                     if (Pro::kSrc) {
-                        int cur[CPR];
+                        int cur[NPT];
 #pragma unroll
-                        for (int i = 0; i < CPR; ++i) cur[i] = srcN[i];
+                        for (int i = 0; i < NPT; ++i) cur[i] = srcN[i];
                         load_src(i_lt + 1, srcN);
                         enter_tile(i_lt, cur);
                     } else {
-                        const int none[CPR] = {};
+                        const int none[NPT] = {};
                         enter_tile(i_lt, none);
                     }
                 }
@@ -304,11 +311,11 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
                 const int sh = a.reserved, gpt = TILE_ROWS >> sh;       // groups per macro tile
                 const long long g0 = c_row0 >> sh;
                 const int n_ent = gpt * KC;
-                int sp[CPR];
-                float gv[CPR];
+                int sp[NPT];
+                float gv[NPT];
 #pragma unroll
-                for (int j = 0; j < CPR; ++j) {      // entries tid + 256*j: prefetch selpos / g3s
-                    const int e = tid + 256 * j;
+                for (int j = 0; j < NPT; ++j) {      // entries tid + kTT*j: prefetch selpos / g3s
+                    const int e = tid + kTT * j;
                     const long long g = g0 + e / KC;
                     sp[j] = -1;
                     gv[j] = 0.f;
@@ -319,15 +326,15 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
                 }
                 cp_async_wait<S - kLag - 1>();   // (the weights of this chunk)
 #pragma unroll
-                for (int i = 0; i < CPR; ++i) {
+                for (int i = 0; i < NPT; ++i) {
                     sts4(st + aoff[i], 0u, 0u, 0u, 0u);
                     sts4(st + C::A_BYTES + aoff[i], 0u, 0u, 0u, 0u);
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(kTT) : "memory");
 #pragma unroll
-                for (int j = 0; j < CPR; ++j) {
+                for (int j = 0; j < NPT; ++j) {
                     if (sp[j] >= 0) {
-                        const int e = tid + 256 * j;
+                        const int e = tid + kTT * j;
                         const int row = ((e / KC) << sh) + sp[j], kk = e % KC;
                         const uint32_t hi = __float_as_uint(gv[j]) & 0xFFFFE000u;
                         const uint32_t lo = __float_as_uint(gv[j] - __uint_as_float(hi));
@@ -343,10 +350,10 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
                 // pass 1: every raw piece (and the V rows of the gather) in flight together; pass 2: math,
                 // TF32 split, in-place stores.  (The shared-memory accesses are volatile asm: without the
                 // two passes each piece's load would wait for the previous piece's stores.)
-                float4 r0[CPR], r1[CPR], rv[CPR];
-                float vsg[CPR];
+                float4 r0[NPT], r1[NPT], rv[NPT];
+                float vsg[NPT];
 #pragma unroll
-                for (int i = 0; i < CPR; ++i) {
+                for (int i = 0; i < NPT; ++i) {
                     r0[i] = lds4(st + aoff[i]);
                     r1[i] = Pro::kTwo ? lds4(st + C::A_BYTES + aoff[i]) : f4zero();
                     rv[i] = f4zero();
@@ -359,7 +366,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
                     }
                 }
 #pragma unroll
-                for (int i = 0; i < CPR; ++i) {
+                for (int i = 0; i < NPT; ++i) {
                     if (dbg & 16) break;
                     const float4 x4 = Pro::finish(a, par, r0[i], r1[i], rv[i], vsg[i]);
                     const float x[4] = {x4.x, x4.y, x4.z, x4.w};

@@ -16,9 +16,9 @@ and the backward is the matching chain: BatchNorm backward in the prologue of bo
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as TF
 
 from . import _lib, fused
+from ._lib import ptr, stream
 from .fused import (EPI_BWD_Y, EPI_STORE, EPI_STORE_STATS, PRO_BN_ACT, PRO_BN_BWD, PRO_PLAIN2, bn_param,
                     pack_weight, rowgemm, wgrad)
 
@@ -73,13 +73,14 @@ def _wgrad_any(pro_l, kw_l, pro_r, kw_r, P, M, N, out, name):
 
 
 class RowMLPFn(torch.autograd.Function):
-    """out (P, C_L) = act(bn_L(... act(bn_1(x . W_1^T)) ... . W_L^T)); x (P, Cin) fp32 rows."""
+    """out (P, C_L) = act(bn_L(... act(bn_1(x . W_1^T)) ... . W_L^T)); x (P, Cin) fp32 rows.
+    params = W_1..W_L, gamma_1..gamma_L, beta_1..beta_L, bias_1..bias_L (a bias may be None)."""
 
     @staticmethod
-    def forward(ctx, x, slope, bns, biases, *params):
+    def forward(ctx, x, slope, bns, *params):
         fused._bind()
         L = len(bns)
-        Ws, gammas, betas = params[:L], params[L:2 * L], params[2 * L:3 * L]
+        Ws, biases = params[:L], params[3 * L:4 * L]
         x = _lib.f32(x)
         P, Cin = x.shape
         dev = x.device
@@ -107,7 +108,9 @@ class RowMLPFn(torch.autograd.Function):
             ys.append(y)
             h, K = y, C
         sc, sh, _, _ = bnp[-1]
-        out = TF.leaky_relu(torch.addcmul(sh, h, sc), slope) if slope else torch.relu_(torch.addcmul(sh, h, sc))
+        out = torch.empty((P, K), **f32)
+        _lib.call("pcl_bn_act_forward", ptr(h), ptr(sc), ptr(sh), float(slope), P, K, ptr(out), stream(h),
+                  key=("mlp_out", P, K))
         flat = [t for p in bnp for t in p]
         ctx.save_for_backward(x, *ys, *flat, *Ws)
         ctx.meta = (L, slope, [b is not None for b in biases], [tuple(w.shape) for w in Ws])
@@ -126,13 +129,14 @@ class RowMLPFn(torch.autograd.Function):
         f32 = dict(dtype=torch.float32, device=dev)
         f64 = dict(dtype=torch.float64, device=dev)
         dWs, dgs, dbs = [None] * L, [None] * L, [None] * L
-        # output layer: dyhat_L = dout * act'(z_L) and its BatchNorm sums (one elementwise + two reductions)
+        # output layer: dyhat_L = dout * act'(z_L) and its BatchNorm sums in one pass
         sc, sh, mu, rs = bnp[L - 1]
-        z = torch.addcmul(sh, ys[L - 1], sc)
-        dyh = _lib.f32(dout) * (torch.where(z > 0, 1.0, slope) if slope else (z > 0))
-        xh = (ys[L - 1] - mu) * rs
-        sums = torch.stack([dyh.sum(dim=0, dtype=torch.float64), (dyh * xh).sum(dim=0, dtype=torch.float64)])
-        del z, xh
+        CL = ys[L - 1].shape[1]
+        dyh = torch.empty((P, CL), **f32)
+        sums = torch.zeros((2, CL), **f64)
+        dout = _lib.f32(dout)
+        _lib.call("pcl_bn_act_backward", ptr(dout), ptr(ys[L - 1]), ptr(sc), ptr(sh), ptr(mu), ptr(rs), float(slope),
+                  P, CL, ptr(dyh), ptr(sums), stream(dout), key=("mlp_out_bwd", P, CL))
         dx = None
         for l in range(L - 1, -1, -1):
             sc, sh, mu, rs = bnp[l]
@@ -155,28 +159,30 @@ class RowMLPFn(torch.autograd.Function):
                         ey=ys[l - 1], escale=psc, eshift=psh, emean=pmu, erstd=prs, eslope=slope, **dzkw)
                 dyh = dprev
             else:
-                # first layer: dz_1 is materialised once (P x C_1) for the two library GEMMs against the raw input
-                dz = sc * (dyh - m1 - (ys[0] - mu) * rs * m2)
-                dW = dz.t() @ x
+                # first layer: dW_1 = dz_1^T . x on the mma.sync reduction kernel (BatchNorm backward in its prologue,
+                # raw input as the right operand); dx = dz_1 . W_1 as a row GEMM when the input width tiles
+                old = fused.MODE
+                fused.MODE = 1
+                try:
+                    wgrad(PRO_BN_BWD, dzkw, PRO_PLAIN2, dict(x0=x, c0=Cin, c1=0, K=Cin), P, C, Cin, dW, name="mlp_dw1")
+                finally:
+                    fused.MODE = old
                 if ctx.needs_input_grad[0]:
-                    dx = dz @ Wm
+                    if Cin % 32 == 0 and (Cin <= 128 or Cin % 128 == 0):
+                        Wt = pack_weight(Wm.t().contiguous())
+                        dx = torch.empty((P, Cin), **f32)
+                        rowgemm(PRO_BN_BWD, EPI_STORE, "mlp_dx", W=Wt, P=P, N=Cin, ldw=Wt.shape[-1], out=dx, **dzkw)
+                    else:
+                        dz = sc * (dyh - m1 - (ys[0] - mu) * rs * m2)
+                        dx = dz @ Wm
             dWs[l] = dW.view(wshapes[l])
-        return (dx, None, None, None, *dWs, *dgs, *dbs)
+        dbias = [torch.zeros(w[0], **f32) if hb else None for w, hb in zip(wshapes, has_bias)]
+        return (dx, None, None, *dWs, *dgs, *dbs, *dbias)
 
 
 def row_mlp(x, convs, bns, acts):
     """x (P, Cin) -> (P, C_L) through [conv 1x1 -> BatchNorm(train) -> act]* (see module docstring)."""
     a0 = acts[0]
     slope = float(a0.negative_slope) if isinstance(a0, torch.nn.LeakyReLU) else 0.0
-    biases = [c.bias for c in convs]
-    out = RowMLPFn.apply(x, slope, list(bns), biases, *[c.weight for c in convs], *[b.weight for b in bns],
-                         *[b.bias for b in bns])
-    return out
-
-
-def conv_bias_zero_grads(convs):
-    """(Reference semantics) a conv bias in front of BatchNorm receives a mathematically zero gradient: give it one so
-    optimizers that expect .grad on every parameter see zeros instead of None."""
-    for c in convs:
-        if c.bias is not None and c.bias.requires_grad and c.bias.grad is None:
-            c.bias.grad = torch.zeros_like(c.bias)
+    return RowMLPFn.apply(x, slope, list(bns), *[c.weight for c in convs], *[b.weight for b in bns],
+                          *[b.bias for b in bns], *[c.bias for c in convs])

@@ -253,6 +253,9 @@ int pcl_gather_bn_backward_masked(const float *dA, const float *U, const float *
  * sums (2,C) fp64 += (sum dyh, sum dyh*(y-mean)*rstd) in ONE pass (sums zeroed by the caller). */
 int pcl_bn_act_forward(const float *y, const float *scale, const float *shift, float slope, long long P, int C,
                        float *out, void *stream);
+/* dz (P,C) = bscale*(dyh - m1 - (y - mean)*rstd*m2): BatchNorm backward materialised in one pass */
+int pcl_bn_bwd_apply(const float *dyh, const float *y, const float *mean, const float *rstd, const float *bscale,
+                     const float *m1, const float *m2, long long P, int C, float *dz, void *stream);
 int pcl_bn_act_backward(const float *dout, const float *y, const float *scale, const float *shift,
                         const float *mean, const float *rstd, float slope, long long P, int C, float *dyh,
                         double *sums, void *stream);

@@ -25,6 +25,26 @@ __global__ void __launch_bounds__(256) bn_act_forward_kernel(const float *__rest
     }
 }
 
+// dz = bscale*(dyh - m1 - (y - mean)*rstd*m2): BatchNorm backward materialised (first layer of a wide dense stack,
+// whose weight gradient against the raw input is a plain library GEMM)
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float *__restrict__ dyh, const float *__restrict__ y,
+                                                           const float *__restrict__ mean, const float *__restrict__ rstd,
+                                                           const float *__restrict__ bscale, const float *__restrict__ m1,
+                                                           const float *__restrict__ m2, long long n4, int QC,
+                                                           float *__restrict__ dz) {
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < n4; e += (long long)gridDim.x * 256) {
+        const int k = (int)(e % QC) * 4;
+        const float4 d = ld4(dyh + e * 4), v = ld4(y + e * 4), mu = ld4(mean + k), rs = ld4(rstd + k), bs = ld4(bscale + k),
+                     a1 = ld4(m1 + k), a2 = ld4(m2 + k);
+        float4 o;
+        o.x = bs.x * (d.x - a1.x - (v.x - mu.x) * rs.x * a2.x);
+        o.y = bs.y * (d.y - a1.y - (v.y - mu.y) * rs.y * a2.y);
+        o.z = bs.z * (d.z - a1.z - (v.z - mu.z) * rs.z * a2.z);
+        o.w = bs.w * (d.w - a1.w - (v.w - mu.w) * rs.w * a2.w);
+        *reinterpret_cast<float4 *>(dz + e * 4) = o;
+    }
+}
+
 __global__ void __launch_bounds__(256) bn_act_backward_kernel(const float *__restrict__ dout, const float *__restrict__ y,
                                                               const float *__restrict__ scale, const float *__restrict__ shift,
                                                               const float *__restrict__ mean, const float *__restrict__ rstd,
@@ -106,4 +126,17 @@ extern "C" int pcl_bn_act_backward(const float *dout, const float *y, const floa
     bn_act_backward_kernel<<<(unsigned)grid, 256, 2 * C * sizeof(double), (cudaStream_t)stream>>>(
         dout, y, scale, shift, mean, rstd, slope, P, C, dyh, sums);
     return check_launch("pcl_bn_act_backward");
+}
+
+extern "C" int pcl_bn_bwd_apply(const float *dyh, const float *y, const float *mean, const float *rstd,
+                                const float *bscale, const float *m1, const float *m2, long long P, int C, float *dz,
+                                void *stream) {
+    PCL_REQUIRE(dyh && y && mean && rstd && bscale && m1 && m2 && dz, "pcl_bn_bwd_apply: null pointer");
+    PCL_REQUIRE(P >= 0 && C >= 4 && C % 4 == 0, "pcl_bn_bwd_apply: bad shape (C %% 4 == 0)");
+    const long long n4 = P * (C / 4);
+    if (n4 == 0) return PCL_OK;
+    long long grid = ceil_div_ll(n4, 256);
+    if (grid > 16LL * kNumSMs) grid = 16LL * kNumSMs;
+    bn_bwd_apply_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(dyh, y, mean, rstd, bscale, m1, m2, n4, C / 4, dz);
+    return check_launch("pcl_bn_bwd_apply");
 }

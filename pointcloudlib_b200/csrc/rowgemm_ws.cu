@@ -110,14 +110,14 @@ struct WEpiBwdYMask {
 template <class Epi> struct EpiTraits { static constexpr bool kMask = false; };
 template <> struct EpiTraits<WEpiBwdYMask> { static constexpr bool kMask = true; };
 
-// 16 transform warps (round 1: 8).  The transform was the critical stage: per 16-float chunk a thread spent ~200
-// instructions on its four 16-byte pieces (address arithmetic + cp.async issue, read-back, BatchNorm / ReLU, TF32
-// split, two stores) with two warps per scheduler — dependent-issue bound at ~1500-1800 cycles per chunk against
-// ~870 cycles of tensor-core work.  With 16 warps a thread owns two pieces and each scheduler has four transform
-// warps to interleave.
-constexpr int kTransformWarps = 16, kEpilogueWarps = 8;
+// Transform warps: 8.  Sixteen were tried in round 2 (a thread then owns two 16-byte pieces per chunk instead of
+// four): sa_l2 -9 %, sa_l3 +4 %, sa_b3 +6 % — the transform is NOT the critical stage.  What is: shared-memory
+// bandwidth.  Per 16-float chunk the ring sees cp.async writes (28 KB), the transform's read-back (16 KB) and hi/lo
+// stores (32 KB), and the tensor core's operand reads (3 MMAs per K step read the activation tile three times and
+// the weights three times: 66 KB) = ~140 KB at 128 B/clk = ~1100 cycles, against ~870 cycles of MMA issue.
+constexpr int kTransformWarps = 8, kEpilogueWarps = 8;
 constexpr int kTT = kTransformWarps * 32;                                // transform threads
-constexpr int kThreadsWS = (kTransformWarps + kEpilogueWarps + 1) * 32;   // 800
+constexpr int kThreadsWS = (kTransformWarps + kEpilogueWarps + 1) * 32;   // 544
 constexpr int TILE_ROWS = 256;    // activation rows per macro tile = MMA N
 constexpr int MMA_M = 128;        // output channels per pass, zero padded
 

@@ -159,21 +159,33 @@ class RowMLPFn(torch.autograd.Function):
                         ey=ys[l - 1], escale=psc, eshift=psh, emean=pmu, erstd=prs, eslope=slope, **dzkw)
                 dyh = dprev
             else:
-                # first layer: dW_1 = dz_1^T . x on the mma.sync reduction kernel (BatchNorm backward in its prologue,
-                # raw input as the right operand); dx = dz_1 . W_1 as a row GEMM when the input width tiles
-                old = fused.MODE
-                fused.MODE = 1
-                try:
-                    wgrad(PRO_BN_BWD, dzkw, PRO_PLAIN2, dict(x0=x, c0=Cin, c1=0, K=Cin), P, C, Cin, dW, name="mlp_dw1")
-                finally:
-                    fused.MODE = old
+                # first layer, narrow: dW_1 = dz_1^T . x on the mma.sync reduction kernel (BatchNorm backward in its
+                # prologue, raw input as the right operand).  Wide (more than one 128 x 160 accumulator tile, e.g. DGCNN's
+                # conv5 1024 x 512): dz_1 is materialised by one elementwise pass and the product is a library GEMM —
+                # the mma.sync kernel took 1.24 ms there against 0.6 ms.
+                dz = None
+                if C <= 128 and Cin <= 160:
+                    old = fused.MODE
+                    fused.MODE = 1
+                    try:
+                        wgrad(PRO_BN_BWD, dzkw, PRO_PLAIN2, dict(x0=x, c0=Cin, c1=0, K=Cin), P, C, Cin, dW, name="mlp_dw1")
+                    finally:
+                        fused.MODE = old
+                else:
+                    dz = torch.empty((P, C), **f32)
+                    _lib.call("pcl_bn_bwd_apply", ptr(dyh), ptr(ys[0]), ptr(mu), ptr(rs), ptr(sc), ptr(m1), ptr(m2), P, C,
+                              ptr(dz), stream(dyh), key=("mlp_dz1", P, C))
+                    dW = dz.t() @ x
                 if ctx.needs_input_grad[0]:
                     if Cin % 32 == 0 and (Cin <= 128 or Cin % 128 == 0):
                         Wt = pack_weight(Wm.t().contiguous())
                         dx = torch.empty((P, Cin), **f32)
                         rowgemm(PRO_BN_BWD, EPI_STORE, "mlp_dx", W=Wt, P=P, N=Cin, ldw=Wt.shape[-1], out=dx, **dzkw)
                     else:
-                        dz = sc * (dyh - m1 - (ys[0] - mu) * rs * m2)
+                        if dz is None:
+                            dz = torch.empty((P, C), **f32)
+                            _lib.call("pcl_bn_bwd_apply", ptr(dyh), ptr(ys[0]), ptr(mu), ptr(rs), ptr(sc), ptr(m1), ptr(m2),
+                                      P, C, ptr(dz), stream(dyh), key=("mlp_dz1", P, C))
                         dx = dz @ Wm
             dWs[l] = dW.view(wshapes[l])
         dbias = [torch.zeros(w[0], **f32) if hb else None for w, hb in zip(wshapes, has_bias)]

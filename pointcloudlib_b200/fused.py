@@ -69,6 +69,7 @@ def _bind():
         "pcl_gather_bn_backward_masked": [P, P, P, P, P, P, P, P, P, P, L, I, I, Fl, P, P, P],
         "pcl_bn_act_forward": [P, P, P, Fl, L, I, P, P],
         "pcl_bn_act_backward": [P, P, P, P, P, P, Fl, L, I, P, P, P],
+        "pcl_bn_bwd_apply": [P, P, P, P, P, P, P, L, I, P, P],
     }
     for name, argtypes in sigs.items():
         fn = getattr(l, name)
@@ -80,7 +81,7 @@ def _bind():
 SIGNATURE_NAMES = ("pcl_rowgemm", "pcl_wgrad", "pcl_gather_stats", "pcl_bn_param",
                    "pcl_maxpool_finalize", "pcl_maxpool_backward", "pcl_sel_outer",
                    "pcl_gather_bn_backward", "pcl_gather_maxmin", "pcl_gather_bn_backward_routed",
-                   "pcl_gather_bn_backward_masked", "pcl_bn_act_forward", "pcl_bn_act_backward")
+                   "pcl_gather_bn_backward_masked", "pcl_bn_act_forward", "pcl_bn_act_backward", "pcl_bn_bwd_apply")
 
 
 def _args(**kw):

@@ -260,6 +260,24 @@ int pcl_bn_act_backward(const float *dout, const float *y, const float *scale, c
                         const float *mean, const float *rstd, float slope, long long P, int C, float *dyh,
                         double *sums, void *stream);
 
+/* The small fp64 algebra of the fused set-abstraction backward, one launch each:
+ * pcl_sa_bwd_prepare: from W3 (C3,C2), the BatchNorm-3 sums of the routed gradient sums3 (2,C3) and the BatchNorm-3
+ *   vectors: t (C3), Q = W3^T diag(t) W3 (C2,C2 fp64), const (C2) and the PACKED weight [W3^T | -Q^T] (3, C2, ld),
+ *   ld = C3 + C2 rounded up to 32, of the last-layer-backward row GEMM (PCL_PRO_G3_A2).
+ * pcl_sa_bwd_finish: dW3 (C3,C2) from gram (C2, ldg): [:, :C2] = a2^T a2, [:, C2] = colsum(a2), and T (C3,C2) the
+ *   routed outer product; if algebraic != 0 also sums2[1] (the second BatchNorm-2 sum, PCL_EPI_BWD_Y_MASK computes
+ *   only the first); m1 = sums2[0]/P, m2 = sums2[1]/P for the BatchNorm-backward prologues.
+ * pcl_sa_bwd_sums1: BatchNorm-1 sums (2,C1) and their means from dwm (C2, 2*C1) = [dz2^T a1 | dz2^T relu'(z1)]
+ *   (pcl_wgrad with PCL_PRO_GATHER_BN_ACT_MASK) and W2 (C2,C1). */
+int pcl_sa_bwd_prepare(const float *W3, const double *sums3, const float *sc3, const float *mu3, const float *rs3,
+                       long long P, int C3, int C2, double *Q, float *constf, double *tvec, float *Wb, void *stream);
+int pcl_sa_bwd_finish(const float *W3, const double *Q, const double *tvec, const double *sums3, const float *sc3,
+                      const float *mu3, const float *gram, int ldg, const float *T, const float *constf,
+                      const float *sc2, const float *sh2, const float *mu2, const float *rs2, long long P, int C3,
+                      int C2, int algebraic, float *dW3, double *sums2, float *m1, float *m2, void *stream);
+int pcl_sa_bwd_sums1(const float *W2, const float *dwm, const float *sc1, const float *sh1, const float *mu1,
+                     const float *rs1, long long P, int C2, int C1, double *sums1, float *m1, float *m2, void *stream);
+
 /* ---- a7 / a8: fused EdgeConv (networks/cls/dgcnn.py:29-50 + :72-83,100-111) -------------------
  * W.[x_j - x_i ; x_i] = W1.x_j + (W2-W1).x_i  =>  y[i,j] = u[src[i,j]] + vsign*v[i] on per-point
  * projections u, v (pcl_rowgemm PCL_PRO_PLAIN2); statistics by pcl_gather_stats; then:

@@ -1,0 +1,164 @@
+// sa_algebra.cu — the small fp64 matrix algebra of the fused set-abstraction backward, one kernel per
+// step of it instead of ~60 torch launches per radius branch (dtype conversions, C2 x C2 GEMMs, broadcasts, packs).
+//
+// Backward of `[Conv1x1 -> BatchNorm(train) -> ReLU] -> max over the group` (networks/cls/pointnet2.py:52-57) for the
+// LAST layer is analytic: with c1 = sum g3, c2 = sum g3*xhat_sel (the BatchNorm-3 sums of the routed gradient),
+//     s3 = gamma3*rstd3,  t = s3*c2*rstd3/P,  r = t*mu3 - s3*c1/P
+//     da2 = G3s.W3 - a2.Q + const,      Q = W3^T diag(t) W3 (C2 x C2),   const = r . W3
+//     dW3 = T - (s3 c1/P) (x) S2 - t (.) (W3.M2 - mu3 (x) S2),      M2 = a2^T a2,  S2 = colsum(a2)
+// and the second BatchNorm-2 sum follows from quantities the step has anyway (rowgemm_ws.cu, PCL_EPI_BWD_Y_MASK):
+//     D2[n] = -sum_k Q[k,n] M2[k,n] + sum_c3 W3[c3,n] T[c3,n] + const[n] S2[n],   sum2[n] = (D2 - beta2*sum1)/gamma2.
+// pcl_sa_bwd_prepare  builds Q, const and the PACKED row-GEMM weight [W3^T | -Q^T] (raw | tf32 hi | tf32 lo planes);
+// pcl_sa_bwd_finish   builds dW3, the second BatchNorm-2 sum and the two means the next kernels take;
+// pcl_sa_bwd_sums1    builds the BatchNorm-1 sums of the deferred-mask layer-2 backward from [dW2 | dz2^T mask1].
+// All accumulation in fp64; sizes are C <= 256, so every kernel is a few microseconds.
+#include "common.cuh"
+
+namespace pcl {
+
+__device__ __forceinline__ void pack3(float x, float *raw, long long plane, long long i) {
+    const float hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    const float lo = __uint_as_float((__float_as_uint(__fsub_rn(x, hi)) + 0x1000u) & 0xFFFFE000u);
+    raw[i] = x;
+    raw[plane + i] = hi;
+    raw[2 * plane + i] = lo;
+}
+
+// grid = C2 (row i of Q / of the packed weight), block = 256
+__global__ void __launch_bounds__(256) sa_bwd_prepare_kernel(const float *__restrict__ W3, const double *__restrict__ sums3,
+                                                             const float *__restrict__ sc3, const float *__restrict__ mu3,
+                                                             const float *__restrict__ rs3, double invP, int C3, int C2,
+                                                             int ld, double *__restrict__ Q, float *__restrict__ constf,
+                                                             double *__restrict__ tvec, float *__restrict__ Wb) {
+    extern __shared__ double s_tw[];   // t[c3] * W3[c3, i]
+    const int i = blockIdx.x, tid = threadIdx.x;
+    for (int c = tid; c < C3; c += 256) {
+        const double s3 = (double)sc3[c];
+        const double t = s3 * sums3[C3 + c] * (double)rs3[c] * invP;
+        s_tw[c] = t * (double)W3[(long long)c * C2 + i];
+        if (i == 0) tvec[c] = t;
+    }
+    __syncthreads();
+    const long long plane = (long long)C2 * ld;
+    for (int j = tid; j < C2; j += 256) {
+        double q = 0.0;
+        for (int c = 0; c < C3; ++c) q += s_tw[c] * (double)W3[(long long)c * C2 + j];
+        Q[(long long)i * C2 + j] = q;
+        pack3((float)(-q), Wb, plane, (long long)i * ld + C3 + j);   // -Q^T[i][j] = -Q[j][i] = -Q[i][j] (symmetric)
+    }
+    for (int c = tid; c < C3; c += 256) pack3(W3[(long long)c * C2 + i], Wb, plane, (long long)i * ld + c);   // W3^T
+    for (int k = C3 + C2 + tid; k < ld; k += 256) pack3(0.f, Wb, plane, (long long)i * ld + k);
+    if (i == 0) {
+        for (int j = tid; j < C2; j += 256) {
+            double acc = 0.0;
+            for (int c = 0; c < C3; ++c) {
+                const double s3 = (double)sc3[c];
+                const double t = s3 * sums3[C3 + c] * (double)rs3[c] * invP;
+                acc += (t * (double)mu3[c] - s3 * sums3[c] * invP) * (double)W3[(long long)c * C2 + j];
+            }
+            constf[j] = (float)acc;
+        }
+    }
+}
+
+// grid = C3 + 1: blocks 0..C3-1 write row c3 of dW3; the last block writes the BatchNorm-2 sums / means
+__global__ void __launch_bounds__(256) sa_bwd_finish_kernel(
+    const float *__restrict__ W3, const double *__restrict__ Q, const double *__restrict__ tvec,
+    const double *__restrict__ sums3, const float *__restrict__ sc3, const float *__restrict__ mu3,
+    const float *__restrict__ gram, int ldg, const float *__restrict__ T, const float *__restrict__ constf,
+    const float *__restrict__ sc2, const float *__restrict__ sh2, const float *__restrict__ mu2,
+    const float *__restrict__ rs2, double invP, int C3, int C2, int algebraic, float *__restrict__ dW3,
+    double *__restrict__ sums2, float *__restrict__ m1, float *__restrict__ m2) {
+    const int tid = threadIdx.x;
+    if ((int)blockIdx.x < C3) {
+        const int c = blockIdx.x;
+        extern __shared__ double s_w[];   // W3[c, :]
+        for (int k = tid; k < C2; k += 256) s_w[k] = (double)W3[(long long)c * C2 + k];
+        __syncthreads();
+        const double t = tvec[c], a = (double)sc3[c] * sums3[c] * invP, mu = (double)mu3[c];
+        for (int j = tid; j < C2; j += 256) {
+            double wm = 0.0;
+            for (int k = 0; k < C2; ++k) wm += s_w[k] * (double)gram[(long long)k * ldg + j];   // (W3 . M2)[c, j]
+            const double S2 = (double)gram[(long long)j * ldg + C2];
+            dW3[(long long)c * C2 + j] = (float)((double)T[(long long)c * C2 + j] - a * S2 - t * (wm - mu * S2));
+        }
+        return;
+    }
+    for (int n = tid; n < C2; n += 256) {
+        double s1 = sums2[n];
+        if (algebraic) {
+            double d2 = 0.0;
+            for (int k = 0; k < C2; ++k) d2 -= Q[(long long)k * C2 + n] * (double)gram[(long long)k * ldg + n];
+            for (int c = 0; c < C3; ++c) d2 += (double)W3[(long long)c * C2 + n] * (double)T[(long long)c * C2 + n];
+            d2 += (double)constf[n] * (double)gram[(long long)n * ldg + C2];
+            const double gamma = (double)sc2[n] / (double)rs2[n];
+            const double beta = (double)sh2[n] + (double)mu2[n] * (double)sc2[n];
+            sums2[C2 + n] = gamma != 0.0 ? (d2 - beta * s1) / gamma : 0.0;
+        }
+        m1[n] = (float)(s1 * invP);
+        m2[n] = (float)(sums2[C2 + n] * invP);
+    }
+}
+
+// dwm (C2, 2*C1) = [dW2 | dz2^T mask1]; W2 (C2, C1).  One block.
+__global__ void __launch_bounds__(256) sa_bwd_sums1_kernel(const float *__restrict__ W2, const float *__restrict__ dwm,
+                                                           const float *__restrict__ sc1, const float *__restrict__ sh1,
+                                                           const float *__restrict__ mu1, const float *__restrict__ rs1,
+                                                           double invP, int C2, int C1, double *__restrict__ sums1,
+                                                           float *__restrict__ m1, float *__restrict__ m2) {
+    for (int n = threadIdx.x; n < C1; n += 256) {
+        double s0 = 0.0, d = 0.0;
+        for (int k = 0; k < C2; ++k) {
+            const double w = (double)W2[(long long)k * C1 + n];
+            s0 += w * (double)dwm[(long long)k * 2 * C1 + C1 + n];
+            d += w * (double)dwm[(long long)k * 2 * C1 + n];
+        }
+        const double gamma = (double)sc1[n] / (double)rs1[n];
+        const double beta = (double)sh1[n] + (double)mu1[n] * (double)sc1[n];
+        const double s1 = gamma != 0.0 ? (d - beta * s0) / gamma : 0.0;
+        sums1[n] = s0;
+        sums1[C1 + n] = s1;
+        m1[n] = (float)(s0 * invP);
+        m2[n] = (float)(s1 * invP);
+    }
+}
+
+}  // namespace pcl
+
+using namespace pcl;
+
+extern "C" int pcl_sa_bwd_prepare(const float *W3, const double *sums3, const float *sc3, const float *mu3,
+                                  const float *rs3, long long P, int C3, int C2, double *Q, float *constf,
+                                  double *tvec, float *Wb, void *stream) {
+    PCL_REQUIRE(W3 && sums3 && sc3 && mu3 && rs3 && Q && constf && tvec && Wb, "pcl_sa_bwd_prepare: null pointer");
+    PCL_REQUIRE(P >= 1 && C3 >= 1 && C2 >= 1 && C3 <= 4096, "pcl_sa_bwd_prepare: bad shape");
+    const int ld = (C3 + C2 + 31) / 32 * 32;
+    sa_bwd_prepare_kernel<<<C2, 256, C3 * sizeof(double), (cudaStream_t)stream>>>(W3, sums3, sc3, mu3, rs3, 1.0 / (double)P,
+                                                                                 C3, C2, ld, Q, constf, tvec, Wb);
+    return check_launch("pcl_sa_bwd_prepare");
+}
+
+extern "C" int pcl_sa_bwd_finish(const float *W3, const double *Q, const double *tvec, const double *sums3,
+                                 const float *sc3, const float *mu3, const float *gram, int ldg, const float *T,
+                                 const float *constf, const float *sc2, const float *sh2, const float *mu2,
+                                 const float *rs2, long long P, int C3, int C2, int algebraic, float *dW3,
+                                 double *sums2, float *m1, float *m2, void *stream) {
+    PCL_REQUIRE(W3 && Q && tvec && sums3 && sc3 && mu3 && gram && T && constf && sc2 && sh2 && mu2 && rs2 && dW3 && sums2 &&
+                    m1 && m2,
+                "pcl_sa_bwd_finish: null pointer");
+    PCL_REQUIRE(P >= 1 && C3 >= 1 && C2 >= 1 && C2 <= 4096 && ldg > C2, "pcl_sa_bwd_finish: bad shape");
+    sa_bwd_finish_kernel<<<C3 + 1, 256, C2 * sizeof(double), (cudaStream_t)stream>>>(
+        W3, Q, tvec, sums3, sc3, mu3, gram, ldg, T, constf, sc2, sh2, mu2, rs2, 1.0 / (double)P, C3, C2, algebraic, dW3,
+        sums2, m1, m2);
+    return check_launch("pcl_sa_bwd_finish");
+}
+
+extern "C" int pcl_sa_bwd_sums1(const float *W2, const float *dwm, const float *sc1, const float *sh1, const float *mu1,
+                                const float *rs1, long long P, int C2, int C1, double *sums1, float *m1, float *m2,
+                                void *stream) {
+    PCL_REQUIRE(W2 && dwm && sc1 && sh1 && mu1 && rs1 && sums1 && m1 && m2, "pcl_sa_bwd_sums1: null pointer");
+    PCL_REQUIRE(P >= 1 && C2 >= 1 && C1 >= 1, "pcl_sa_bwd_sums1: bad shape");
+    sa_bwd_sums1_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(W2, dwm, sc1, sh1, mu1, rs1, 1.0 / (double)P, C2, C1, sums1, m1,
+                                                            m2);
+    return check_launch("pcl_sa_bwd_sums1");
+}

@@ -70,6 +70,9 @@ def _bind():
         "pcl_bn_act_forward": [P, P, P, Fl, L, I, P, P],
         "pcl_bn_act_backward": [P, P, P, P, P, P, Fl, L, I, P, P, P],
         "pcl_bn_bwd_apply": [P, P, P, P, P, P, P, L, I, P, P],
+        "pcl_sa_bwd_prepare": [P, P, P, P, P, L, I, I, P, P, P, P, P],
+        "pcl_sa_bwd_finish": [P, P, P, P, P, P, P, I, P, P, P, P, P, P, L, I, I, I, P, P, P, P, P],
+        "pcl_sa_bwd_sums1": [P, P, P, P, P, P, L, I, I, P, P, P, P],
     }
     for name, argtypes in sigs.items():
         fn = getattr(l, name)
@@ -81,7 +84,8 @@ def _bind():
 SIGNATURE_NAMES = ("pcl_rowgemm", "pcl_wgrad", "pcl_gather_stats", "pcl_bn_param",
                    "pcl_maxpool_finalize", "pcl_maxpool_backward", "pcl_sel_outer",
                    "pcl_gather_bn_backward", "pcl_gather_maxmin", "pcl_gather_bn_backward_routed",
-                   "pcl_gather_bn_backward_masked", "pcl_bn_act_forward", "pcl_bn_act_backward", "pcl_bn_bwd_apply")
+                   "pcl_gather_bn_backward_masked", "pcl_bn_act_forward", "pcl_bn_act_backward", "pcl_bn_bwd_apply",
+                   "pcl_sa_bwd_prepare", "pcl_sa_bwd_finish", "pcl_sa_bwd_sums1")
 
 
 def _args(**kw):
@@ -256,64 +260,73 @@ class FusedSAFn(torch.autograd.Function):
         _lib.call("pcl_maxpool_backward", ptr(dout), ptr(out), ptr(ysel), ptr(sc3), ptr(mu3), ptr(rs3),
                   float(slope), G, C3, ptr(g3s), ptr(sums3), stream())
         c1, c2 = sums3[0], sums3[1]                      # = dbeta3, dgamma3
-        W3d = W3m.double()
-        s3 = sc3.double()
-        t = s3 * c2 * rs3.double() / P                    # (C3)
-        Q = W3d.t() @ (t.view(-1, 1) * W3d)               # (C2, C2)
-        const = ((t * mu3.double()) - (s3 * c1 / P)) @ W3d  # q0 - r0, (C2)
-
         use_mask = bool(MASK_STASH and MODE == 3 and slope == 0.0 and C2 <= 128 and C2 % 32 == 0 and C3 % 16 == 0
                         and 4 <= ns <= 256 and ns & (ns - 1) == 0)
-
-        # ---- Gram matrix of a2 and the sparse routed outer product (dW3; on the mask-stash path also the 2nd BN2 sum) ----
-        gram = torch.zeros((C2, C2 + 4), **f32)            # [:, :C2] = a2^T a2, [:, C2] = colsum(a2)
-        a2kw = dict(x0=y2, scale=sc2, shift=sh2, slope=slope, K=C2)
-        wgrad(PRO_BN_ACT, a2kw, PRO_BN_ACT_ONES, a2kw, P, C2, C2 + 1, gram, name="sa_gram")
-        T = torch.zeros((C3, C2), **f32)
-        _lib.call("pcl_sel_outer", ptr(g3s), ptr(selpos), ptr(y2), ptr(sc2), ptr(sh2), float(slope), G,
-                  ns, C3, C2, ptr(T), stream(g3s), key=("sa_sel_outer", G, C3, C2))
-        M2, S2 = gram[:, :C2].double(), gram[:, C2].double()
-        dW3 = (T.double() - (s3 * c1 / P).view(-1, 1) * S2.view(1, -1)
-               - t.view(-1, 1) * (W3d @ M2 - mu3.double().view(-1, 1) * S2.view(1, -1))).float()
-
-        # ---- da2 -> dyhat2 (grad at the BN2 output masked by ReLU'), BN2 sums -----------------
+        W3f = W3m.contiguous()
         dyh2 = torch.empty((P, C2), **f32)
         sums2 = torch.zeros((2, C2), **f64)
-        constf = const.float().contiguous()
+        gram = torch.zeros((C2, C2 + 4), **f32)            # [:, :C2] = a2^T a2, [:, C2] = colsum(a2)
+        T = torch.zeros((C3, C2), **f32)
+        a2kw = dict(x0=y2, scale=sc2, shift=sh2, slope=slope, K=C2)
+
+        def gram_and_routed_outer():
+            wgrad(PRO_BN_ACT, a2kw, PRO_BN_ACT_ONES, a2kw, P, C2, C2 + 1, gram, name="sa_gram")
+            _lib.call("pcl_sel_outer", ptr(g3s), ptr(selpos), ptr(y2), ptr(sc2), ptr(sh2), float(slope), G,
+                      ns, C3, C2, ptr(T), stream(g3s), key=("sa_sel_outer", G, C3, C2))
+
         if use_mask:
-            # warp-specialised kernel: the routed gradient enters as a one-hot K block, the ReLU mask comes from the
-            # operand tile the kernel stages itself; its epilogue reads nothing of size (P, C2) and accumulates
-            # sum(dyhat2) only
-            Wb = pack_weight(torch.cat([W3d.t(), -Q.t()], dim=1).float())      # (C2, C3 + C2)
+            # -- the small fp64 algebra (Q, const, the packed [W3^T | -Q^T] weight) in ONE kernel (sa_algebra.cu)
+            ld = (C3 + C2 + 31) // 32 * 32
+            Qd = torch.empty((C2, C2), **f64)
+            constf = torch.empty(C2, **f32)
+            tvec = torch.empty(C3, **f64)
+            Wb = torch.empty((3, C2, ld), **f32)
+            _lib.call("pcl_sa_bwd_prepare", ptr(W3f), ptr(sums3), ptr(sc3), ptr(mu3), ptr(rs3), P, C3, C2, ptr(Qd),
+                      ptr(constf), ptr(tvec), ptr(Wb), stream(W3f))
+            gram_and_routed_outer()
+            # -- da2 -> dyhat2 on the warp-specialised kernel: the routed gradient enters as a one-hot K block, the
+            # ReLU mask comes from the operand tile the kernel stages itself; its epilogue reads nothing of size
+            # (P, C2) and accumulates sum(dyhat2) only
             rowgemm(PRO_G3_A2, EPI_BWD_Y_MASK, "sa_b3", W=Wb, g3s=g3s, selpos=selpos, C3=C3, ns=ns, x0=y2,
-                    scale=sc2, shift=sh2, slope=0.0, P=P, K=C3 + C2, N=C2, ldw=Wb.shape[-1], out=dyh2,
+                    scale=sc2, shift=sh2, slope=0.0, P=P, K=C3 + C2, N=C2, ldw=ld, out=dyh2,
                     stats=sums2, ebias=constf, eslope=0.0)
-            # sum_p dyhat2*xhat2 without a pass: a2 = mask*(gamma2*xhat2 + beta2)  =>
+            # -- dW3, and sum_p dyhat2*xhat2 without a pass: a2 = mask*(gamma2*xhat2 + beta2)  =>
             #   sum_p dA2*mask*xhat2 = (sum_p dA2*a2 - beta2 * sum_p dyhat2) / gamma2,   dA2 = -a2.Q + R.W3 + const
             #   sum_p dA2[p,n]*a2[p,n] = -sum_k Q[k,n] M2[k,n] + sum_c3 W3[c3,n] T[c3,n] + const[n] S2[n]
-            D2 = -(Q * M2).sum(dim=0) + (W3d * T.double()).sum(dim=0) + const * S2
-            gamma2 = sc2.double() / rs2.double()
-            beta2 = sh2.double() + mu2.double() * sc2.double()
-            sums2[1] = torch.where(gamma2 != 0, (D2 - beta2 * sums2[0]) / gamma2, torch.zeros_like(D2))
-        elif MODE >= 2:
-            # dense part -a2.Q on the tensor core (K = C2); the routed part G3s.W3 is one row update per
-            # (group, channel) added in fp32 by the epilogue (PCL_EPI_BWD_Y_ROUTED)
-            Wq = pack_weight(Q.t(), sign=-1.0)                               # (C2, C2) = -Q^T
-            W3f = W3m.contiguous()
-            rowgemm(PRO_BN_ACT, EPI_BWD_Y_ROUTED, "sa_b3", W=Wq, x0=y2, x1=W3f, g3s=g3s, selpos=selpos, C3=C3,
-                    ns=ns, scale=sc2, shift=sh2, slope=slope, P=P, K=C2, N=C2, ldw=Wq.shape[-1], out=dyh2,
-                    stats=sums2, ebias=constf, ey=y2, escale=sc2, eshift=sh2, emean=mu2, erstd=rs2,
-                    eslope=slope)
+            dW3 = torch.empty((C3, C2), **f32)
+            m1_2, m2_2 = torch.empty(C2, **f32), torch.empty(C2, **f32)
+            _lib.call("pcl_sa_bwd_finish", ptr(W3f), ptr(Qd), ptr(tvec), ptr(sums3), ptr(sc3), ptr(mu3), ptr(gram),
+                      gram.stride(0), ptr(T), ptr(constf), ptr(sc2), ptr(sh2), ptr(mu2), ptr(rs2), P, C3, C2, 1,
+                      ptr(dW3), ptr(sums2), ptr(m1_2), ptr(m2_2), stream(W3f))
         else:
-            Wb = pack_weight(torch.cat([W3d.t(), -Q.t()], dim=1).float())      # (C2, C3 + C2)
-            rowgemm(PRO_G3_A2, EPI_BWD_Y, "sa_b3", W=Wb, g3s=g3s, selpos=selpos, C3=C3, ns=ns, x0=y2,
-                    scale=sc2, shift=sh2, slope=slope, P=P, K=C3 + C2, N=C2, ldw=Wb.shape[-1], out=dyh2,
-                    stats=sums2, ebias=constf, ey=y2, escale=sc2, eshift=sh2, emean=mu2, erstd=rs2,
-                    eslope=slope)
+            W3d = W3m.double()
+            s3 = sc3.double()
+            t = s3 * c2 * rs3.double() / P                    # (C3)
+            Q = W3d.t() @ (t.view(-1, 1) * W3d)               # (C2, C2)
+            const = ((t * mu3.double()) - (s3 * c1 / P)) @ W3d  # q0 - r0, (C2)
+            constf = const.float().contiguous()
+            gram_and_routed_outer()
+            M2, S2 = gram[:, :C2].double(), gram[:, C2].double()
+            dW3 = (T.double() - (s3 * c1 / P).view(-1, 1) * S2.view(1, -1)
+                   - t.view(-1, 1) * (W3d @ M2 - mu3.double().view(-1, 1) * S2.view(1, -1))).float()
+            if MODE >= 2:
+                # dense part -a2.Q on the tensor core (K = C2); the routed part G3s.W3 is one row update per
+                # (group, channel) added in fp32 by the epilogue (PCL_EPI_BWD_Y_ROUTED)
+                Wq = pack_weight(Q.t(), sign=-1.0)                               # (C2, C2) = -Q^T
+                rowgemm(PRO_BN_ACT, EPI_BWD_Y_ROUTED, "sa_b3", W=Wq, x0=y2, x1=W3f, g3s=g3s, selpos=selpos, C3=C3,
+                        ns=ns, scale=sc2, shift=sh2, slope=slope, P=P, K=C2, N=C2, ldw=Wq.shape[-1], out=dyh2,
+                        stats=sums2, ebias=constf, ey=y2, escale=sc2, eshift=sh2, emean=mu2, erstd=rs2,
+                        eslope=slope)
+            else:
+                Wb = pack_weight(torch.cat([W3d.t(), -Q.t()], dim=1).float())      # (C2, C3 + C2)
+                rowgemm(PRO_G3_A2, EPI_BWD_Y, "sa_b3", W=Wb, g3s=g3s, selpos=selpos, C3=C3, ns=ns, x0=y2,
+                        scale=sc2, shift=sh2, slope=slope, P=P, K=C3 + C2, N=C2, ldw=Wb.shape[-1], out=dyh2,
+                        stats=sums2, ebias=constf, ey=y2, escale=sc2, eshift=sh2, emean=mu2, erstd=rs2,
+                        eslope=slope)
+            m1_2 = (sums2[0] / P).float().contiguous()
+            m2_2 = (sums2[1] / P).float().contiguous()
 
         # ---- layer 2 backward -----------------------------------------------------------------
-        m1_2 = (sums2[0] / P).float().contiguous()
-        m2_2 = (sums2[1] / P).float().contiguous()
         dz2kw = dict(x0=dyh2, x1=y2, mean=mu2, rstd=rs2, bscale=sc2, m1=m1_2, m2=m2_2, K=C2)
         a1kw = dict(U=U, V=V, src=src, ns=ns, vsign=-1.0, scale=sc1, shift=sh1, slope=slope, K=C1)
         W2t = pack_weight(W2m.t().contiguous())             # (C1, C2): da1 = dz2 . W2
@@ -329,12 +342,10 @@ class FusedSAFn(torch.autograd.Function):
             dwm = torch.zeros((C2, 2 * C1), **f32)
             wgrad(PRO_BN_BWD, dz2kw, PRO_GATHER_BN_ACT_MASK, a1kw, P, C2, 2 * C1, dwm, name="sa_dw2")
             dW2 = dwm[:, :C1]
-            W2d = W2m.double()
-            s0 = (W2d * dwm[:, C1:].double()).sum(dim=0)
-            gamma1 = sc1.double() / rs1.double()
-            beta1 = sh1.double() + mu1.double() * sc1.double()
-            s1 = torch.where(gamma1 != 0, ((W2d * dW2.double()).sum(dim=0) - beta1 * s0) / gamma1, torch.zeros_like(s0))
-            sums1 = torch.stack([s0, s1])
+            sums1 = torch.empty((2, C1), **f64)
+            m1_1, m2_1 = torch.empty(C1, **f32), torch.empty(C1, **f32)
+            _lib.call("pcl_sa_bwd_sums1", ptr(W2m.contiguous()), ptr(dwm), ptr(sc1), ptr(sh1), ptr(mu1), ptr(rs1), P,
+                      C2, C1, ptr(sums1), ptr(m1_1), ptr(m2_1), stream(dwm))
             rowgemm(PRO_BN_BWD, EPI_STORE, "sa_b2", W=W2t, P=P, N=C1, ldw=W2t.shape[-1], out=dyh1, **dz2kw)
         else:
             dW2 = torch.zeros((C2, C1), **f32)
@@ -345,8 +356,9 @@ class FusedSAFn(torch.autograd.Function):
                     erstd=rs1, eslope=slope, **dz2kw)
 
         # ---- layer 1 backward: BN1 backward + scatter onto the source points / centres ---------
-        m1_1 = (sums1[0] / P).float().contiguous()
-        m2_1 = (sums1[1] / P).float().contiguous()
+        if not defer:
+            m1_1 = (sums1[0] / P).float().contiguous()
+            m2_1 = (sums1[1] / P).float().contiguous()
         dU = torch.zeros((B * N, C1), **f32)
         dV = torch.empty((G, C1), **f32)
         if defer:

@@ -15,6 +15,7 @@
 // shuffle shift.  Stable on (distance, index) = the reference's insertion-sort order
 // (ops.py:535,541).  HBM traffic = inputs (re-read from L2 per query tile) + idx.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -173,6 +174,158 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float *__restric
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// TMA-staged variant (round 2).  Same arithmetic, same list — what changes is how the operands reach shared memory:
+//   * the CTA's query tile (C x TQ) is staged ONCE (round 1 re-staged it for every 128-reference chunk);
+//   * reference chunks [CC channels][128 refs] arrive by 1-D TMA bulk copies (cp.async.bulk, one 512-byte row per
+//     channel, completion on an mbarrier) into a 3-stage ring, issued TWO iterations ahead by one thread, so the L2
+//     latency sits behind two iterations of FMAs instead of in front of every one (round 1: load -> store ->
+//     __syncthreads -> compute, twice per 16 channels);
+//   * the layout in shared memory is the global one ([channel][reference], no permutation): lane l reads references
+//     {l, l+32, l+64, l+96} of the chunk with four conflict-free 32-bit loads.
+// Needs Nq % 4 == 0 and Nr % 4 == 0 (16-byte granules); other shapes take knn_kernel above.
+// Dynamic smem: float sQ[Cpad][TQ] | float sR[3][CC][128]; Cpad = C rounded up to CC.
+__device__ __forceinline__ uint32_t knn_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int R, int QW, int CC>
+__global__ void __launch_bounds__(kKnnThreads) knn_tma_kernel(const float *__restrict__ x_r,
+                                                              const float *__restrict__ x_q, int C, int Nr, int Nq,
+                                                              int k, int32_t *__restrict__ idx) {
+    constexpr int TQ = kKnnWarps * QW, NS = 3;
+    extern __shared__ __align__(16) float knn_sm[];
+    __shared__ __align__(8) uint64_t s_full[NS], s_q;
+    const int Cpad = (C + CC - 1) / CC * CC, nC = Cpad / CC;
+    float *sQ = knn_sm;                       // [Cpad][TQ]
+    float *sR = knn_sm + (size_t)Cpad * TQ;   // [NS][CC][128]
+    const int b = blockIdx.y;
+    const int q0 = blockIdx.x * TQ;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *xr = x_r + (size_t)b * C * Nr;
+    const float *xq = x_q + (size_t)b * C * Nq;
+    const int km1 = k - 1;
+    const int nR = (Nr + kKnnTR - 1) / kKnnTR, total = nR * nC;
+    const int q_valid = min(TQ, Nq - q0);     // queries of this tile that exist (a multiple of 4)
+
+    // zero what the bulk copies will not write: query columns past Nq, channel rows past C (all stages)
+    for (int e = tid; e < Cpad * TQ; e += kKnnThreads) {
+        const int c = e / TQ, q = e - c * TQ;
+        if (c >= C || q >= q_valid) sQ[e] = 0.f;
+    }
+    if (Cpad > C)
+        for (int e = tid; e < NS * CC * kKnnTR; e += kKnnThreads) sR[e] = 0.f;
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(knn_smem(&s_full[s])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(knn_smem(&s_q)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zero fills above vs the async-proxy writes below
+    __syncthreads();
+
+    auto issue_refs = [&](int it) {   // thread 0 only
+        const int s = it % NS, r0 = (it / nC) * kKnnTR, c0 = (it % nC) * CC;
+        const int rows = min(CC, C - c0), n = min(kKnnTR, Nr - r0);
+        const uint32_t bar = knn_smem(&s_full[s]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(rows * n * 4)) : "memory");
+        for (int cc = 0; cc < rows; ++cc)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             knn_smem(sR + ((size_t)s * CC + cc) * kKnnTR)),
+                         "l"(xr + (size_t)(c0 + cc) * Nr + r0), "r"((uint32_t)(n * 4)), "r"(bar)
+                         : "memory");
+    };
+    if (tid == 0) {
+        const uint32_t bar = knn_smem(&s_q);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(C * q_valid * 4)) : "memory");
+        for (int c = 0; c < C; ++c)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             knn_smem(sQ + (size_t)c * TQ)),
+                         "l"(xq + (size_t)c * Nq + q0), "r"((uint32_t)(q_valid * 4)), "r"(bar)
+                         : "memory");
+        issue_refs(0);
+        if (total > 1) issue_refs(1);
+    }
+    auto wait_bar = [&](uint64_t *barp, uint32_t parity) {
+        const uint32_t bar = knn_smem(barp);
+        uint32_t ok = 0;
+        while (!ok)
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(ok)
+                         : "r"(bar), "r"(parity)
+                         : "memory");
+    };
+    wait_bar(&s_q, 0);
+
+    float ld[QW][R];
+    int li[QW][R];
+    float thr[QW];
+#pragma unroll
+    for (int qi = 0; qi < QW; ++qi) {
+        thr[qi] = CUDART_INF_F;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            ld[qi][r] = CUDART_INF_F;
+            li[qi][r] = 0;
+        }
+    }
+    float acc[QW][4];
+    for (int it = 0; it < total; ++it) {
+        const int s = it % NS, rc = it / nC, cb = it - rc * nC;
+        if (cb == 0) {
+#pragma unroll
+            for (int qi = 0; qi < QW; ++qi)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[qi][j] = 0.f;
+        }
+        // stage (it + 2) % NS was last read in iteration it - 1, which every thread left through the barrier below
+        if (tid == 0 && it + 2 < total) issue_refs(it + 2);
+        wait_bar(&s_full[s], (uint32_t)((it / NS) & 1));
+        const float *R_ = sR + (size_t)s * CC * kKnnTR;
+        const float *Q_ = sQ + (size_t)cb * CC * TQ + warp * QW;
+#pragma unroll
+        for (int cc = 0; cc < CC; ++cc) {
+            // zero rows beyond C leave acc unchanged (fma(0,0,acc)), as in ops.py:474-481
+            const float r0v = R_[cc * kKnnTR + lane], r1v = R_[cc * kKnnTR + 32 + lane],
+                        r2v = R_[cc * kKnnTR + 64 + lane], r3v = R_[cc * kKnnTR + 96 + lane];
+#pragma unroll
+            for (int qi = 0; qi < QW; ++qi) {
+                const float qv = Q_[cc * TQ + qi];
+                float t;
+                t = __fsub_rn(r0v, qv);
+                acc[qi][0] = __fmaf_rn(t, t, acc[qi][0]);
+                t = __fsub_rn(r1v, qv);
+                acc[qi][1] = __fmaf_rn(t, t, acc[qi][1]);
+                t = __fsub_rn(r2v, qv);
+                acc[qi][2] = __fmaf_rn(t, t, acc[qi][2]);
+                t = __fsub_rn(r3v, qv);
+                acc[qi][3] = __fmaf_rn(t, t, acc[qi][3]);
+            }
+        }
+        if (cb == nC - 1) {
+            const int r0 = rc * kKnnTR;
+#pragma unroll
+            for (int qi = 0; qi < QW; ++qi) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r = r0 + j * 32 + lane;
+                    const float d = r < Nr ? acc[qi][j] : CUDART_INF_F;
+                    list_offer<R>(ld[qi], li[qi], thr[qi], d, r0 + j * 32, km1, lane);
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int qi = 0; qi < QW; ++qi) {
+        const int q = q0 + warp * QW + qi;
+        if (q < Nq) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int i = r * 32 + lane;
+                if (i < k) idx[((size_t)b * k + i) * Nq + q] = li[qi][r];
+            }
+        }
+    }
+}
+
 // knn_point: xyz (B,N,C) refs, new_xyz (B,S,C) queries, channels-last, matmul-form distance in
 // the oracle's canonical arithmetic.  One warp per query.  idx (B,S,ns), dist optional.
 template <int R>
@@ -252,6 +405,25 @@ template <int R, int QW>
 static int launch_knn(const float *x_r, const float *x_q, int B, int C, int Nr, int Nq, int k,
                       int32_t *idx, cudaStream_t st) {
     dim3 grid(ceil_div(Nq, kKnnWarps * QW), B);
+    {   // TMA-staged kernel: 16-byte granules and the whole query tile in shared memory
+        const int CC = C <= 4 ? 4 : 16, Cpad = (C + CC - 1) / CC * CC;
+        const size_t smem = ((size_t)Cpad * kKnnWarps * QW + (size_t)3 * CC * kKnnTR) * sizeof(float);
+        const char *leg = getenv("PCL_KNN_LEGACY");
+        // (a partial last channel block would leave stale rows of an earlier block in its ring stage)
+        if (Nq % 4 == 0 && Nr % 4 == 0 && (C % CC == 0 || C <= CC) && smem <= 96 * 1024 && !(leg && leg[0] == '1') &&
+            (reinterpret_cast<uintptr_t>(x_r) & 15u) == 0 && (reinterpret_cast<uintptr_t>(x_q) & 15u) == 0) {
+            auto kern = C <= 4 ? knn_tma_kernel<R, QW, 4> : knn_tma_kernel<R, QW, 16>;
+            if (smem > 40 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) {
+                    set_error("pcl_knn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+                    return (int)e;
+                }
+            }
+            kern<<<grid, kKnnThreads, smem, st>>>(x_r, x_q, C, Nr, Nq, k, idx);
+            return check_launch("pcl_knn");
+        }
+    }
     if (C <= 4)
         knn_kernel<R, QW, 4><<<grid, kKnnThreads, 0, st>>>(x_r, x_q, C, Nr, Nq, k, idx);
     else

@@ -511,86 +511,6 @@ __global__ void __launch_bounds__(256) sel_outer_kernel(
     }
 }
 
-// T (C3,C2) += sum_g g3s[g,c3] * a2[row(g,c3), :], one WARP PER GROUP.  Max-pooling concentrates the maxima of a
-// group on few of its ns rows, so the C3 row reads of one group hit the same few rows again and again: walking the
-// channels of ONE group inside one warp turns the repeats into L1 hits (this kernel uses no shared memory beyond
-// T, so L1 is large) and DRAM sees every selected row once — sel_outer_kernel above (one warp per channel, rows of
-// different groups) re-read them from L2 / DRAM per entry (0.4-0.66 of the HBM peak on G*C3 row gathers).  T is
-// accumulated in shared memory (C3*C2 floats) with conflict-free shared atomics and flushed once per CTA.
-template <int NT>
-__global__ void __launch_bounds__(NT) sel_outer_group_kernel(
-    const float *__restrict__ g3s, const int32_t *__restrict__ selpos, const float *__restrict__ y2,
-    const float *__restrict__ scale2, const float *__restrict__ shift2, float slope, long long G, int ns, int C3,
-    int C2, float *__restrict__ T) {
-    extern __shared__ float s_T[];
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    for (int i = tid; i < C3 * C2; i += NT) s_T[i] = 0.f;
-    __syncthreads();
-    const int nq = C2 / 4;   // <= 64: lane handles quads lane, lane + 32
-    float4 sc[2], sh[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int qd = lane + 32 * i;
-        sc[i] = qd < nq ? ld4(scale2 + qd * 4) : f4zero();
-        sh[i] = qd < nq ? ld4(shift2 + qd * 4) : f4zero();
-    }
-    for (long long g = (long long)blockIdx.x * (NT / 32) + w; g < G; g += (long long)gridDim.x * (NT / 32)) {
-        const float *gv = g3s + g * C3;
-        const int32_t *sp = selpos + g * C3;
-        const float *rows = y2 + g * ns * (long long)C2;
-        for (int c0 = 0; c0 < C3; c0 += 32) {
-            // this lane's (gradient, row) of channel c0 + lane; the warp then walks the 32 channels four at a time
-            const float my_g = c0 + lane < C3 ? __ldg(gv + c0 + lane) : 0.f;
-            const int my_r = c0 + lane < C3 ? __ldg(sp + c0 + lane) : 0;
-            unsigned live = __ballot_sync(0xffffffffu, my_g != 0.f);
-            while (live) {
-                int j[4];
-                float gj[4];
-                float4 y[4][2];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    j[u] = live ? __ffs(live) - 1 : -1;
-                    if (live) live &= live - 1;
-                    const int jj = j[u] < 0 ? 0 : j[u];
-                    gj[u] = __shfl_sync(0xffffffffu, my_g, jj);
-                    const int r = __shfl_sync(0xffffffffu, my_r, jj);
-                    if (j[u] < 0) gj[u] = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int qd = lane + 32 * i;
-                        y[u][i] = (j[u] >= 0 && qd < nq) ? ld4(rows + (long long)r * C2 + qd * 4) : f4zero();
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (j[u] < 0) continue;
-                    float *o = s_T + (c0 + j[u]) * C2;
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int qd = lane + 32 * i;
-                        if (qd < nq) {
-                            float4 a2;
-                            a2.x = fmaf(sc[i].x, y[u][i].x, sh[i].x); a2.y = fmaf(sc[i].y, y[u][i].y, sh[i].y);
-                            a2.z = fmaf(sc[i].z, y[u][i].z, sh[i].z); a2.w = fmaf(sc[i].w, y[u][i].w, sh[i].w);
-                            a2.x = fmaxf(a2.x, a2.x * slope); a2.y = fmaxf(a2.y, a2.y * slope);
-                            a2.z = fmaxf(a2.z, a2.z * slope); a2.w = fmaxf(a2.w, a2.w * slope);
-                            atomicAdd(o + qd * 4 + 0, gj[u] * a2.x);
-                            atomicAdd(o + qd * 4 + 1, gj[u] * a2.y);
-                            atomicAdd(o + qd * 4 + 2, gj[u] * a2.z);
-                            atomicAdd(o + qd * 4 + 3, gj[u] * a2.w);
-                        }
-                    }
-                }
-            }
-        }
-    }
-    __syncthreads();
-    for (int i = tid; i < C3 * C2; i += NT) {
-        const float v = s_T[i];
-        if (v != 0.f) atomicAdd(T + i, v);
-    }
-}
-
 // one warp per group; lanes over channel quads (C <= 256).  MASK: dyh holds the UNMASKED gradient dA and
 // relu'(bscale*y1 + shift) is applied here (y1 is gathered anyway).
 template <bool MASK>
@@ -928,26 +848,10 @@ extern "C" int pcl_sel_outer(const float *g3s, const int32_t *selpos, const floa
     PCL_REQUIRE(g3s && selpos && y2 && scale2 && shift2 && T, "pcl_sel_outer: null pointer");
     PCL_REQUIRE(C2 % 4 == 0 && C2 <= 256 && C3 >= 1 && ns >= 1, "pcl_sel_outer: bad shape");
     if (G == 0) return PCL_OK;
-    const size_t t_bytes = (size_t)C3 * C2 * sizeof(float);
-    if (t_bytes <= 200 * 1024 && C2 <= 256) {
-        // one warp per group (L1 serves the repeated rows of a group); T accumulated in shared memory
-        const bool big = t_bytes > 64 * 1024;           // one CTA per SM: give it 16 warps
-        auto kern = big ? sel_outer_group_kernel<512> : sel_outer_group_kernel<256>;
-        if (t_bytes > 40 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t_bytes);
-            if (e != cudaSuccess) {
-                set_error("pcl_sel_outer: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-                return (int)e;
-            }
-        }
-        const int wpc = big ? 16 : 8;
-        long long grid = ceil_div_ll(G, wpc);
-        const long long cap = (big ? 1 : (long long)(200 * 1024 / t_bytes < 4 ? 200 * 1024 / t_bytes : 4)) * kNumSMs;
-        if (grid > cap) grid = cap;
-        kern<<<(unsigned)grid, big ? 512 : 256, t_bytes, (cudaStream_t)stream>>>(g3s, selpos, y2, scale2, shift2, slope,
-                                                                               G, ns, C3, C2, T);
-        return check_launch("pcl_sel_outer");
-    }
+    // (Round 2 tried one warp per GROUP with T accumulated in shared memory, so that the repeated rows of a group
+    // would be L1 hits and DRAM would see each selected row once: 377 vs 266 us on the big branch — the chain
+    // selpos -> row -> shared atomics per channel is latency bound where this kernel keeps four groups of
+    // independent row gathers in flight per warp.  Dropped.)
     long long slices = (16LL * kNumSMs * 8) / C3;  // ~16 CTAs of 8 warps per SM in total
     if (slices < 1) slices = 1;
     if (slices > G) slices = G;

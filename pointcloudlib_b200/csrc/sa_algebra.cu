@@ -61,58 +61,86 @@ __global__ void __launch_bounds__(256) sa_bwd_prepare_kernel(const float *__rest
     }
 }
 
-// grid = C3 + 1: blocks 0..C3-1 write row c3 of dW3; the last block writes the BatchNorm-2 sums / means
-__global__ void __launch_bounds__(256) sa_bwd_finish_kernel(
+__device__ __forceinline__ double block_sum(double v, double *s_red) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) s_red[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_red[i];
+    return t;
+}
+
+// grid = C3 + C2: blocks 0..C3-1 write row c3 of dW3 (threads over columns); blocks C3.. handle one BatchNorm-2
+// channel n each (threads over the reduction index, so no thread walks a dependent chain of global loads)
+__global__ void __launch_bounds__(128) sa_bwd_finish_kernel(
     const float *__restrict__ W3, const double *__restrict__ Q, const double *__restrict__ tvec,
     const double *__restrict__ sums3, const float *__restrict__ sc3, const float *__restrict__ mu3,
     const float *__restrict__ gram, int ldg, const float *__restrict__ T, const float *__restrict__ constf,
     const float *__restrict__ sc2, const float *__restrict__ sh2, const float *__restrict__ mu2,
     const float *__restrict__ rs2, double invP, int C3, int C2, int algebraic, float *__restrict__ dW3,
     double *__restrict__ sums2, float *__restrict__ m1, float *__restrict__ m2) {
+    extern __shared__ double s_w[];   // W3[c, :]  (dW3 blocks)
+    __shared__ double s_red[4];
     const int tid = threadIdx.x;
     if ((int)blockIdx.x < C3) {
         const int c = blockIdx.x;
-        extern __shared__ double s_w[];   // W3[c, :]
-        for (int k = tid; k < C2; k += 256) s_w[k] = (double)W3[(long long)c * C2 + k];
+        for (int k = tid; k < C2; k += 128) s_w[k] = (double)W3[(long long)c * C2 + k];
         __syncthreads();
         const double t = tvec[c], a = (double)sc3[c] * sums3[c] * invP, mu = (double)mu3[c];
-        for (int j = tid; j < C2; j += 256) {
-            double wm = 0.0;
-            for (int k = 0; k < C2; ++k) wm += s_w[k] * (double)gram[(long long)k * ldg + j];   // (W3 . M2)[c, j]
+        for (int j = tid; j < C2; j += 128) {
+            double wm0 = 0.0, wm1 = 0.0, wm2 = 0.0, wm3 = 0.0;   // four independent chains: the loads pipeline
+            int k = 0;
+            for (; k + 3 < C2; k += 4) {
+                wm0 += s_w[k] * (double)gram[(long long)k * ldg + j];
+                wm1 += s_w[k + 1] * (double)gram[(long long)(k + 1) * ldg + j];
+                wm2 += s_w[k + 2] * (double)gram[(long long)(k + 2) * ldg + j];
+                wm3 += s_w[k + 3] * (double)gram[(long long)(k + 3) * ldg + j];
+            }
+            for (; k < C2; ++k) wm0 += s_w[k] * (double)gram[(long long)k * ldg + j];
+            const double wm = (wm0 + wm1) + (wm2 + wm3);            // (W3 . M2)[c, j]
             const double S2 = (double)gram[(long long)j * ldg + C2];
             dW3[(long long)c * C2 + j] = (float)((double)T[(long long)c * C2 + j] - a * S2 - t * (wm - mu * S2));
         }
         return;
     }
-    for (int n = tid; n < C2; n += 256) {
-        double s1 = sums2[n];
-        if (algebraic) {
-            double d2 = 0.0;
-            for (int k = 0; k < C2; ++k) d2 -= Q[(long long)k * C2 + n] * (double)gram[(long long)k * ldg + n];
-            for (int c = 0; c < C3; ++c) d2 += (double)W3[(long long)c * C2 + n] * (double)T[(long long)c * C2 + n];
-            d2 += (double)constf[n] * (double)gram[(long long)n * ldg + C2];
-            const double gamma = (double)sc2[n] / (double)rs2[n];
-            const double beta = (double)sh2[n] + (double)mu2[n] * (double)sc2[n];
-            sums2[C2 + n] = gamma != 0.0 ? (d2 - beta * s1) / gamma : 0.0;
-        }
-        m1[n] = (float)(s1 * invP);
-        m2[n] = (float)(sums2[C2 + n] * invP);
+    const int n = blockIdx.x - C3;
+    double s2v = sums2[C2 + n];
+    if (algebraic) {
+        double part = 0.0;
+        for (int k = tid; k < C2; k += 128) part -= Q[(long long)k * C2 + n] * (double)gram[(long long)k * ldg + n];
+        for (int c = tid; c < C3; c += 128) part += (double)W3[(long long)c * C2 + n] * (double)T[(long long)c * C2 + n];
+        double d2 = block_sum(part, s_red);
+        d2 += (double)constf[n] * (double)gram[(long long)n * ldg + C2];
+        const double gamma = (double)sc2[n] / (double)rs2[n];
+        const double beta = (double)sh2[n] + (double)mu2[n] * (double)sc2[n];
+        s2v = gamma != 0.0 ? (d2 - beta * sums2[n]) / gamma : 0.0;
+    }
+    if (tid == 0) {
+        if (algebraic) sums2[C2 + n] = s2v;
+        m1[n] = (float)(sums2[n] * invP);
+        m2[n] = (float)(s2v * invP);
     }
 }
 
-// dwm (C2, 2*C1) = [dW2 | dz2^T mask1]; W2 (C2, C1).  One block.
-__global__ void __launch_bounds__(256) sa_bwd_sums1_kernel(const float *__restrict__ W2, const float *__restrict__ dwm,
+// dwm (C2, 2*C1) = [dW2 | dz2^T mask1]; W2 (C2, C1).  grid = C1 (one BatchNorm-1 channel per block), threads over k.
+__global__ void __launch_bounds__(128) sa_bwd_sums1_kernel(const float *__restrict__ W2, const float *__restrict__ dwm,
                                                            const float *__restrict__ sc1, const float *__restrict__ sh1,
                                                            const float *__restrict__ mu1, const float *__restrict__ rs1,
                                                            double invP, int C2, int C1, double *__restrict__ sums1,
                                                            float *__restrict__ m1, float *__restrict__ m2) {
-    for (int n = threadIdx.x; n < C1; n += 256) {
-        double s0 = 0.0, d = 0.0;
-        for (int k = 0; k < C2; ++k) {
-            const double w = (double)W2[(long long)k * C1 + n];
-            s0 += w * (double)dwm[(long long)k * 2 * C1 + C1 + n];
-            d += w * (double)dwm[(long long)k * 2 * C1 + n];
-        }
+    __shared__ double s_red[4];
+    const int n = blockIdx.x;
+    double p0 = 0.0, pd = 0.0;
+    for (int k = threadIdx.x; k < C2; k += 128) {
+        const double w = (double)W2[(long long)k * C1 + n];
+        p0 += w * (double)dwm[(long long)k * 2 * C1 + C1 + n];
+        pd += w * (double)dwm[(long long)k * 2 * C1 + n];
+    }
+    const double s0 = block_sum(p0, s_red);
+    const double d = block_sum(pd, s_red);
+    if (threadIdx.x == 0) {
         const double gamma = (double)sc1[n] / (double)rs1[n];
         const double beta = (double)sh1[n] + (double)mu1[n] * (double)sc1[n];
         const double s1 = gamma != 0.0 ? (d - beta * s0) / gamma : 0.0;
@@ -147,7 +175,7 @@ extern "C" int pcl_sa_bwd_finish(const float *W3, const double *Q, const double 
                     m1 && m2,
                 "pcl_sa_bwd_finish: null pointer");
     PCL_REQUIRE(P >= 1 && C3 >= 1 && C2 >= 1 && C2 <= 4096 && ldg > C2, "pcl_sa_bwd_finish: bad shape");
-    sa_bwd_finish_kernel<<<C3 + 1, 256, C2 * sizeof(double), (cudaStream_t)stream>>>(
+    sa_bwd_finish_kernel<<<C3 + C2, 128, C2 * sizeof(double), (cudaStream_t)stream>>>(
         W3, Q, tvec, sums3, sc3, mu3, gram, ldg, T, constf, sc2, sh2, mu2, rs2, 1.0 / (double)P, C3, C2, algebraic, dW3,
         sums2, m1, m2);
     return check_launch("pcl_sa_bwd_finish");
@@ -158,7 +186,7 @@ extern "C" int pcl_sa_bwd_sums1(const float *W2, const float *dwm, const float *
                                 void *stream) {
     PCL_REQUIRE(W2 && dwm && sc1 && sh1 && mu1 && rs1 && sums1 && m1 && m2, "pcl_sa_bwd_sums1: null pointer");
     PCL_REQUIRE(P >= 1 && C2 >= 1 && C1 >= 1, "pcl_sa_bwd_sums1: bad shape");
-    sa_bwd_sums1_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(W2, dwm, sc1, sh1, mu1, rs1, 1.0 / (double)P, C2, C1, sums1, m1,
+    sa_bwd_sums1_kernel<<<C1, 128, 0, (cudaStream_t)stream>>>(W2, dwm, sc1, sh1, mu1, rs1, 1.0 / (double)P, C2, C1, sums1, m1,
                                                             m2);
     return check_launch("pcl_sa_bwd_sums1");
 }

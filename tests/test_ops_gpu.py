@@ -290,6 +290,8 @@ def test_pack_weight_is_the_3xtf32_split():
 @pytest.mark.parametrize("B,N,S,C,radii,nss", [
     (32, 4096, 512, 3, (0.1, 0.2, 0.4), (16, 32, 128)),        # config 2, SA1 (networks/cls/pointnet2.py:165-176)
     (32, 512, 128, 320, (0.2, 0.4, 0.8), (32, 64, 128)),       # config 2, SA2 (:178-190)
+    (4, 256, 32, 32, (0.3,), (4,)),                            # narrowest row the four-row staged writer takes (C = 32)
+    (3, 512, 40, 36, (0.2, 0.45), (8, 12)),                    # staged writer with a partial last load (C/4 = 9 lanes)
     (4, 1024, 100, 5, (0.4, 0.1), (12, 20)),                   # radii given in DESCENDING order, two of them
     (3, 300, 37, 0, (0.3, 0.3, 0.5), (8, 4, 16)),              # equal radii, no feature (W = 3)
     (2, 257, 9, 7, (0.05, 0.2, 0.9), (5, 7, 3)),               # ns*W not a multiple of 4: per-radius fallback

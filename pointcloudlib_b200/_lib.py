@@ -191,6 +191,25 @@ def check(rc: int, what: str = "") -> None:
         raise RuntimeError(f"libpcl_b200 {what}: {kind}: {msg}")
 
 
+# Host-fed inputs of a CUDA-graph capture: values that the reference draws on the HOST every step (PointConv's
+# random FPS start indices, np.random.randint at misc/pointconv_utils.py:88).  Code that runs under capture stages
+# them through a pinned buffer and registers a refill callback here; the trainer that captured the graph calls the
+# callbacks before every replay, so a replayed step draws fresh values exactly as an eager step does.
+GRAPH_HOST_FEEDS = []
+
+
+def host_feed(make_values, device):
+    """make_values() -> 1-D int32/float32 CPU tensor.  Eager: plain copy.  Under capture: pinned staging buffer +
+    a captured async copy, refilled by the registered callback before each replay."""
+    vals = make_values()
+    if not (device.type == "cuda" and torch.cuda.is_current_stream_capturing()):
+        return vals.to(device)
+    pinned = torch.empty_like(vals).pin_memory()
+    pinned.copy_(vals)
+    GRAPH_HOST_FEEDS.append(lambda: pinned.copy_(make_values()))
+    return pinned.to(device, non_blocking=True)
+
+
 def ptr(t):
     """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
     if t is None:

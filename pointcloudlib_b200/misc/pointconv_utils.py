@@ -22,7 +22,11 @@ def farthest_point_sample(xyz, npoint, start=None):
     `start` (B,) is given."""
     B, N, C = xyz.shape
     if start is None:
-        start = torch.from_numpy(np.random.randint(0, N, B, dtype="l")).to(xyz.device)
+        # drawn on the host every step like the reference; under CUDA-graph capture the draw is registered as a
+        # host feed (pointcloudlib_b200/_lib.py) so that every replay draws again
+        from .. import _lib
+        start = _lib.host_feed(lambda: torch.from_numpy(np.random.randint(0, N, B, dtype="l").astype(np.int32)),
+                               xyz.device)
     return F.fps_pointconv(xyz, npoint, start.to(torch.int32))
 
 

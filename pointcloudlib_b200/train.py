@@ -107,6 +107,7 @@ class Trainer:
         self._eager_steps = 0
         self._graph = None
         self._static = None
+        self._host_feeds = []
         self.graph_launches = 0     # own C-ABI launches captured in the graph (per step)
         self.graph_error = None
         self.allreduce_mode = "none (1 rank)"
@@ -204,12 +205,15 @@ class Trainer:
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         n0 = _lib.LAUNCHES
+        feeds0 = len(_lib.GRAPH_HOST_FEEDS)
         # thread_local: other threads (NCCL watchdog, clock sampler) may touch CUDA during the capture
         with torch.cuda.graph(g, capture_error_mode="thread_local"):
             self._static_loss = self._fwd_bwd(*self._static[0], labels=self._static[1])
             if self._split and not self._tail_fired:
                 self._ev_graph.record()
         self.graph_launches = _lib.LAUNCHES - n0
+        self._host_feeds = _lib.GRAPH_HOST_FEEDS[feeds0:]     # host-drawn inputs captured through pinned buffers
+        del _lib.GRAPH_HOST_FEEDS[feeds0:]
         self._graph = g
 
     def step(self, *inputs, labels):
@@ -222,6 +226,8 @@ class Trainer:
             try:
                 self._capture(inputs, labels)
             except Exception as e:  # keep training eagerly; bench.py reports graph_error
+                from . import _lib
+                _lib.GRAPH_HOST_FEEDS.clear()
                 self.graph_error = repr(e)
                 self.use_graph = False
                 self._graph = None
@@ -234,6 +240,11 @@ class Trainer:
         for s, t in zip(self._static[0], inputs):
             s.copy_(t, non_blocking=True)
         self._static[1].copy_(labels, non_blocking=True)
+        if self._host_feeds:
+            # the previous replay must have consumed its host-fed values before the pinned buffers are refilled
+            torch.cuda.current_stream().synchronize()
+            for refill in self._host_feeds:
+                refill()
         self._graph.replay()
         self.opt.step(grad_scale=self.reduce_gradients(replayed=True))
         return self._static_loss

@@ -202,3 +202,19 @@ def test_cuda_graph_step_equals_eager_step():
                  for b1, b0 in zip(m1.buffers(), m0.buffers()))
         assert rm <= 1e-3, (s, rm)
     assert t1.graph_error is None and t1._graph is not None and t1.graph_launches > 0
+
+
+def test_pointconv_step_captures_with_host_fed_fps_starts():
+    """PointConv draws its FPS start indices on the HOST every step (np.random.randint, pointconv_utils.py:88).
+    Under CUDA-graph capture they go through pinned staging buffers registered as host feeds and are redrawn before
+    every replay: the step captures (no eager fallback) and consecutive replays sample different centroids."""
+    from pointcloudlib_b200.networks.cls.pointconv import PointConvDensityClsSsg
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = PointConvDensityClsSsg(n_classes=40).to(DEV).train()
+    tr = Trainer(model, lr=1e-3, graph=True, graph_warmup=2)
+    xyz, _, lab = modelnet_batch(4, 1024, seed=12)
+    losses = [float(tr.step(xyz.to(DEV), labels=lab.to(DEV))) for _ in range(6)]
+    assert tr.graph_error is None and tr._graph is not None, tr.graph_error
+    assert len(tr._host_feeds) == 2                     # sa1 and sa2 sample; sa3 groups all points
+    assert all(np.isfinite(l) for l in losses)

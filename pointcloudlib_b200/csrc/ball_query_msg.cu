@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(NT) ball_query_msg_kernel(const BQMArgs a) {
     float *s_pts = reinterpret_cast<float *>(s_ctr + a.cpb);
     int *s_idx[R];
     {
-        int *p = reinterpret_cast<int *>(s_pts + ((3 * a.N + 3) & ~3));
+        int *p = reinterpret_cast<int *>(s_pts + 3 * ((a.N + 127) & ~127));
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             s_idx[r] = p;
@@ -178,6 +178,10 @@ __global__ void __launch_bounds__(NT) ball_query_msg_kernel(const BQMArgs a) {
     const int n_c = min(a.cpb, a.S - s0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *pb = a.xyz + (long long)b * a.N * 3;
+    {   // pad to a multiple of 128 points with coordinates no ball reaches (the scan then needs no bounds checks)
+        const int Npad = (a.N + 127) & ~127;
+        for (int i = 3 * a.N + tid; i < 3 * Npad; i += kMThreads) s_pts[i] = 1.0e18f;
+    }
     const uint32_t bytes = (uint32_t)a.N * 12u;
     const bool bulk = (bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(pb) & 15u) == 0;   // TMA: 16-byte granules
     if (bulk) {
@@ -223,29 +227,38 @@ __global__ void __launch_bounds__(NT) ball_query_msg_kernel(const BQMArgs a) {
             sidx[r] = s_idx[r] + cl * a.ns[r];
             open = true;
         }
+        const unsigned lt = (1u << lane) - 1u;
         for (int base = 0; base < a.N && open; base += 128) {
+            // the cloud is padded to a multiple of 128 points with far-away coordinates: no bounds checks in here
             float d[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int k = base + 32 * j + lane;
-                d[j] = 3.0e38f;
-                if (k < a.N) d[j] = sqdist3(cx, cy, cz, s_pts[3 * k], s_pts[3 * k + 1], s_pts[3 * k + 2]);   // ops.py:317-320
+                const float *p = s_pts + 3 * (base + 32 * j + lane);
+                d[j] = sqdist3(cx, cy, cz, p[0], p[1], p[2]);   // ops.py:317-320
             }
+            unsigned m[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                unsigned m = __ballot_sync(0xffffffffu, d[j] < a.r2[R - 1]);   // largest ball gates the rest
-                if (m == 0) continue;
+            for (int j = 0; j < 4; ++j) m[j] = __ballot_sync(0xffffffffu, d[j] < a.r2[R - 1]);   // largest ball gates the rest
+            if ((m[0] | m[1] | m[2] | m[3]) == 0) continue;
 #pragma unroll
-                for (int r = R - 1; r >= 0; --r) {
-                    const bool hit = d[j] < a.r2[r];                            // strict <, ops.py:320
-                    if (r != R - 1) m = __ballot_sync(0xffffffffu, hit);
-                    if (m == 0) break;                                          // nested: none in the smaller balls
-                    if (cnt[r] < a.ns[r]) {                                     // ops.py:313 loop condition
-                        if (cnt[r] == 0) first[r] = base + 32 * j + __ffs(m) - 1;
-                        const int pos = cnt[r] + __popc(m & ((1u << lane) - 1u));
-                        if (hit && pos < a.ns[r]) sidx[r][pos] = base + 32 * j + lane;
-                        cnt[r] += __popc(m);
+            for (int r = R - 1; r >= 0; --r) {
+                if (r != R - 1) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) m[j] = __ballot_sync(0xffffffffu, d[j] < a.r2[r]);   // strict <, ops.py:320
+                    if ((m[0] | m[1] | m[2] | m[3]) == 0) break;   // nested: none in the smaller balls either
+                }
+                if (cnt[r] < a.ns[r]) {   // ops.py:313 loop condition; hits are consumed in index order, 128 at a time
+                    const int ns = a.ns[r];
+                    if (cnt[r] == 0)
+                        first[r] = base + (m[0] ? __ffs(m[0]) - 1 : m[1] ? 31 + __ffs(m[1]) : m[2] ? 63 + __ffs(m[2]) : 95 + __ffs(m[3]));
+                    int at = cnt[r];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int pos = at + __popc(m[j] & lt);
+                        if (((m[j] >> lane) & 1u) && pos < ns) sidx[r][pos] = base + 32 * j + lane;
+                        at += __popc(m[j]);
                     }
+                    cnt[r] = at;
                 }
             }
             open = false;
@@ -293,7 +306,7 @@ bool bq_msg_supported(int B, int N, int S, int C, int use_xyz, int R, const floa
         if (r > 0 && !(radii[r] >= radii[r - 1])) return false;   // ascending radii = nested balls
         sum_ns += ns[r];
     }
-    if ((size_t)N * 12 + 16 + 8 * (16 + 4 * sum_ns) > 200 * 1024) return false;
+    if ((size_t)((N + 127) & ~127) * 12 + 16 + 8 * (16 + 4 * sum_ns) > 200 * 1024) return false;
     if (group) {
         const int W = (use_xyz ? 3 : 0) + C;
         if (W < 3) return false;                         // one row wrap per float4
@@ -328,7 +341,7 @@ static int launch_msg_r(BQMArgs a, cudaStream_t st, const char *what) {
     // multiply-high division is exact while n < 2^32 / d
     while (!wide && cpb > 1 && (long long)cpb * max_per4 * max_per4 >= (1ll << 32)) cpb >>= 1;
     auto smem_for = [&](int c) {
-        return (((size_t)a.N * 12 + 15) & ~(size_t)15) + (size_t)c * (16 + 4 * sum_ns) + (wide ? (size_t)(nt / 32) * 16 * W : 0);
+        return (size_t)((a.N + 127) & ~127) * 12 + (size_t)c * (16 + 4 * sum_ns) + (wide ? (size_t)(nt / 32) * 16 * W : 0);
     };
     while (cpb > 1 && smem_for(cpb) > 200 * 1024) cpb >>= 1;
     if (smem_for(cpb) > 227 * 1024 || (!wide && ((long long)cpb * max_per4 * max_per4 >= (1ll << 32) ||

@@ -27,8 +27,8 @@
 //     active at 3.8 TB/s), not memory bound.
 //   * Writer, narrow rows: ALL threads write the CTA's grouped rows as one flat float4 stream per radius;
 //     (row, channel) of a flat index come from two multiply-high divisions.
-//   * Scan-heavy launches (narrow rows, query only) run 512-thread CTAs: the staged cloud (48 KB at N = 4096) is
-//     shared by 16 warps, so four CTAs keep all 64 warp slots of an SM busy.
+//   * The scan consumes 128 points per step with branch-light bookkeeping (four ballots, popc prefixes, predicated
+//     slot stores; the cloud is padded with unreachable points so the loop has no bounds checks).
 // HBM traffic = read xyz/feat once (L2-resident per cloud), write idx + grouped tensors once.
 #include <stdlib.h>
 
@@ -332,10 +332,12 @@ static int launch_msg_r(BQMArgs a, cudaStream_t st, const char *what) {
     // wide rows: the four-row staged writer (128-bit loads and stores); else the flat float4 writer
     const bool wide = GROUP && a.use_xyz && a.feat && a.C % 4 == 0 && a.C >= 32 && a.C <= 384 && ns4 &&
                       (reinterpret_cast<uintptr_t>(a.feat) & 15u) == 0 && env_int("PCL_BQ_WIDE", 1) != 0;
-    // scan-heavy launches (narrow rows / query only): 512 threads share one staged cloud
-    const int nt = wide ? 256 : env_int("PCL_BQ_THREADS", 512);
-    // centroids per CTA: wide rows -> few (the writer is the work; many resident CTAs); else one per warp
-    int cpb = wide ? 4 : nt / 32;
+    // scan-heavy launches (narrow rows / query only): measured on config 2's SA1 shapes, 256 threads with one
+    // centroid per warp beat 512 threads sharing one staged cloud (three radii: 129 vs 140 us)
+    const int nt = wide ? 256 : env_int("PCL_BQ_THREADS", 256);
+    // centroids per CTA: wide rows -> few (the writer is the work; many resident CTAs: 8 when a centroid writes
+    // <= 64 rows, else 4); narrow rows / query only -> one per warp
+    int cpb = wide ? (sum_ns <= 64 ? 8 : 4) : nt / 32;
     cpb = env_int("PCL_BQ_CPB", cpb);
     while (cpb > 1 && (long long)a.B * ceil_div(a.S, cpb) < 2 * kNumSMs) cpb >>= 1;
     // multiply-high division is exact while n < 2^32 / d

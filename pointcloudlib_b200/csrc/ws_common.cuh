@@ -192,5 +192,80 @@ struct WProG3A2 {
     }
 };
 
+// ------------------------------------------------------------------------------------------
+// Epilogues, one output channel n per thread.  fetch() = the extra per-element operand.
+// ------------------------------------------------------------------------------------------
+struct WEpiBwdPar { float b, s, h, mu, rs; };
+__device__ __forceinline__ WEpiBwdPar load_bwd_par(const PclRowGemm &a, int n, bool act) {
+    WEpiBwdPar e = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (act) {
+        e.b = a.ebias ? __ldg(a.ebias + n) : 0.f;
+        e.s = __ldg(a.escale + n);
+        e.h = __ldg(a.eshift + n);
+        e.mu = __ldg(a.emean + n);
+        e.rs = __ldg(a.erstd + n);
+    }
+    return e;
+}
+struct WEpiStoreStats {
+    static constexpr bool kMaxMin = false, kFetch = false, kStats = true, kSrc = false;
+    using Par = int;
+    static __device__ __forceinline__ Par params(const PclRowGemm &, int, bool) { return 0; }
+    static __device__ __forceinline__ const float *fetch_ptr(const PclRowGemm &a, long long, int, int) { return a.W; }
+    static __device__ __forceinline__ void apply(const PclRowGemm &, const Par &, float &v, float &q, float) { q = v * v; }
+};
+struct WEpiStore {
+    static constexpr bool kMaxMin = false, kFetch = false, kStats = false, kSrc = false;
+    using Par = int;
+    static __device__ __forceinline__ Par params(const PclRowGemm &, int, bool) { return 0; }
+    static __device__ __forceinline__ const float *fetch_ptr(const PclRowGemm &a, long long, int, int) { return a.W; }
+    static __device__ __forceinline__ void apply(const PclRowGemm &, const Par &, float &, float &q, float) { q = 0.f; }
+};
+struct WEpiMaxMinStats {
+    static constexpr bool kMaxMin = true, kFetch = false, kStats = true, kSrc = false;
+    using Par = int;
+    static __device__ __forceinline__ Par params(const PclRowGemm &, int, bool) { return 0; }
+};
+__device__ __forceinline__ void bwd_act1(const PclRowGemm &a, const WEpiBwdPar &e, float &v, float &q, float y) {
+    v = (v + e.b) * (fmaf(e.s, y, e.h) > 0.f ? 1.f : a.eslope);
+    q = v * (y - e.mu) * e.rs;
+}
+struct WEpiBwdY {
+    static constexpr bool kMaxMin = false, kFetch = true, kStats = true, kSrc = false;
+    using Par = WEpiBwdPar;
+    static __device__ __forceinline__ Par params(const PclRowGemm &a, int n, bool act) { return load_bwd_par(a, n, act); }
+    static __device__ __forceinline__ const float *fetch_ptr(const PclRowGemm &a, long long p, int n, int) { return a.ey + p * a.N + n; }
+    static __device__ __forceinline__ void apply(const PclRowGemm &a, const Par &e, float &v, float &q, float y) { bwd_act1(a, e, v, q, y); }
+};
+// ey := U[src[p]] + vsign*V[p/ns]; the src index arrives by shuffle from a lane-distributed prefetch and
+// the V term is hoisted per 16-row block (ns % 16 == 0)
+struct WEpiBwdGather {
+    static constexpr bool kMaxMin = false, kFetch = true, kStats = true, kSrc = true;
+    using Par = WEpiBwdPar;
+    static __device__ __forceinline__ Par params(const PclRowGemm &a, int n, bool act) { return load_bwd_par(a, n, act); }
+    static __device__ __forceinline__ const float *fetch_ptr(const PclRowGemm &a, long long, int n, int src) {
+        return a.U + (long long)src * a.N + n;
+    }
+    static __device__ __forceinline__ void apply(const PclRowGemm &a, const Par &e, float &v, float &q, float y) { bwd_act1(a, e, v, q, y); }
+};
+
+// Last-layer backward with NO per-element epilogue operand in global memory (PCL_EPI_BWD_Y_MASK):
+//   v = relu'(z2) * (acc + ebias),  out = v,  stats[n] += sum v
+// with PCL_PRO_G3_A2: K = C3 + N, the routed max-gradient enters as the one-hot K block (scattered into a zeroed
+// operand tile, contracted with W3 by the tensor core), the dense part is -a2.Q with a2 = relu(bn2(y2)) staged by
+// THIS kernel's transform warps.  The ReLU mask of output element (p, n) is the sign of the A-operand element
+// (p, k = C3 + n) they just produced: they drop one byte per element into a shared-memory stash (256 x N bytes per
+// tile, two tiles) and the epilogue reads it back — the round-1 kernel re-read y2 (P x N floats) in its epilogue.
+// The second BatchNorm-backward sum (sum v * xhat) needs no pass at all: with a2 = mask*(gamma*xhat + beta) it
+// equals (sum_p dA2*a2 - beta*sum v)/gamma, and sum_p dA2*a2 follows from the Gram matrix, the column sums and
+// the routed outer product the step computes anyway (fused.py).
+struct WEpiBwdYMask {
+    static constexpr bool kMaxMin = false, kFetch = false, kStats = true, kSrc = false;
+    using Par = int;
+    static __device__ __forceinline__ Par params(const PclRowGemm &, int, bool) { return 0; }
+};
+template <class Epi> struct EpiTraits { static constexpr bool kMask = false; };
+template <> struct EpiTraits<WEpiBwdYMask> { static constexpr bool kMask = true; };
+
 }  // namespace ws
 }  // namespace pcl

@@ -35,3 +35,21 @@ for k, v in [r for r in rows if not own(r[0])][:40]:
 print("--- library / torch kernels by count")
 for k, v in sorted([r for r in tot.items() if not own(r[0])], key=lambda kv: -kv[1][0])[:25]:
     print(f"{v[0]:5d} {v[1]:9.1f} us  {k}")
+# --- which host lines launch the library / torch kernels (second eager step, CPU+CUDA activities with stacks)
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True) as prof:
+    tr.step(*inputs, labels=lab)
+    torch.cuda.synchronize()
+site = collections.defaultdict(lambda: [0, 0.0])
+for e in prof.events():
+    if e.device_type != torch.autograd.DeviceType.CPU or not e.kernels:
+        continue
+    ks = [k for k in e.kernels if not own(k.name)]
+    if not ks:
+        continue
+    fr = [s for s in (e.stack or []) if ("pointcloudlib_b200/" in s or "/compat/" in s or "bench.py" in s)]
+    where = fr[0].split("/root/repo/")[-1][:70] if fr else ("autograd engine (backward of torch ops)" if not e.stack else e.stack[0][-70:])
+    site[where][0] += len(ks)
+    site[where][1] += sum(k.duration for k in ks)
+print("--- library / torch launches by host call site")
+for k, v in sorted(site.items(), key=lambda kv: -kv[1][0])[:45]:
+    print(f"{v[0]:5d} {v[1]:9.1f} us  {k}")

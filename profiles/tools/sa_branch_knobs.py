@@ -17,7 +17,7 @@ new_xyz = F.gather_xyz(xyz, F.furthest_point_sample(xyz, 512))
 g = BallQueryGrouper(0.4, 128, True)
 def run():
     out = sa.sa_branch(g, seq, new_xyz, xyz, nrm); out.sum().backward()
-for mode, dbgs in ((2,(0,)), (3,(0,31,31+128,128,2+128))):
+for mode, dbgs in ((3,(2048, 0, 31, 1, 2, 4)),):
     fused.MODE = mode
     for dbg in dbgs:
         fused.WS_DBG = dbg

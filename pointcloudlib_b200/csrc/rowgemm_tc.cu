@@ -154,7 +154,9 @@ __global__ void __launch_bounds__(256, 2) rowgemm_tc_kernel(const PclRowGemm a) 
     uint32_t uses = 0, tiles_done = 0;
     const int dbg = a.c0 >> 16;  // profiling knobs (scratch/knobs.py): 1 no MMA, 2 no epilogue body, 4 no A loads, 8 no W
 
-    for (int pass = 0; pass < n_pass; ++pass) {
+    // channel passes: all of them in this CTA (gridDim.y == 1), or one per blockIdx.y when the row tiles alone
+    // cannot fill the GPU (few rows, many channels: the SA3 / feature-propagation / PointConv dense layers)
+    for (int pass = blockIdx.y; pass < n_pass; pass += gridDim.y) {
         const int n0 = pass * BN;
         // thread tid < 2*BN owns the fp64 accumulator of (stat = tid / BN, column = tid % BN)
         double acc_d = 0.0;
@@ -476,7 +478,15 @@ static int launch_tc(const PclRowGemm &a, cudaStream_t st) {
     const long long n_tiles = (a.P + 255) / 256;  // macro tiles of 2 x 128 rows
     long long grid = 2LL * kNumSMs;  // two persistent CTAs per SM
     if (grid > n_tiles) grid = n_tiles;
-    kern<<<(unsigned)grid, 256, smem, st>>>(a);
+    const int n_pass = a.N / BN;
+    dim3 g((unsigned)grid, 1, 1);
+    if (n_pass > 1 && n_tiles < 2LL * kNumSMs) {   // spread the channel passes over the idle SMs
+        g.y = (unsigned)n_pass;
+        long long gx = 2LL * kNumSMs / n_pass;
+        gx = gx < 1 ? 1 : gx;
+        g.x = (unsigned)(gx < n_tiles ? gx : n_tiles);
+    }
+    kern<<<g, 256, smem, st>>>(a);
     return check_launch("pcl_rowgemm(tcgen05)");
 }
 

@@ -86,7 +86,9 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int BN = a.N < MMA_M ? a.N : MMA_M;       // channels per pass
-    const int n_pass = a.N / BN;
+    // channel passes: all of them here (gridDim.y == 1) or exactly one per blockIdx.y (few row tiles, many channels)
+    const int pass0 = gridDim.y > 1 ? (int)blockIdx.y : 0;
+    const int n_pass = gridDim.y > 1 ? 1 : a.N / BN;
     const int nk = a.K / KC;
     const long long n_tiles = (a.P + TILE_ROWS - 1) / TILE_ROWS;
     const int my_tiles = blockIdx.x < n_tiles ? (int)((n_tiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
                 const int half = e >= per_half ? 1 : 0, r = e - half * per_half;
                 const int n = r / CPR, c = r % CPR;
                 woff[j] = 2 * C::A_BYTES + half * w_bytes + sw_off<KC>(n, c);
-                wptr[j] = Whi + (long long)half * a.N * a.ldw + (long long)(pass * BN + n) * a.ldw + c * 4;
+                wptr[j] = Whi + (long long)half * a.N * a.ldw + (long long)((pass0 + pass) * BN + n) * a.ldw + c * 4;
                 if (e < 2 * per_half) n_w = j + 1;
             }
         };
@@ -333,7 +335,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
             // ---- max/min and plain store epilogues: warp (q, h) owns rows [128h, 128h+128) of the tile ----
             int tl = 0;   // local tile counter across passes (accumulator buffer = tl & 1)
             for (int pass = 0; pass < n_pass; ++pass) {
-                const int n = pass * BN + ch;
+                const int n = (pass0 + pass) * BN + ch;
                 double acc_s = 0.0, acc_q = 0.0;
                 for (int lt = 0; lt < my_tiles; ++lt, ++tl) {
                     const int buf = tl & 1;
@@ -462,7 +464,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
                 if (kk >= E) mbar_wait(smem_u32(&s_eyempty[h][slot]), (uint32_t)(((kk / E) - 1) & 1));
                 const long long p = block_row0(kk) + lane;
                 const bool valid = lane < 16 && p < a.P && !(dbg & (2 | 64));
-                const int n0k = ((kk >> 3) / my_tiles) * BN;
+                const int n0k = (pass0 + (kk >> 3) / my_tiles) * BN;
                 if (Epi::kSrc && (kk & 7) == 0 && kk > 0) {   // the issue cursor enters a new tile
 #pragma unroll
                     for (int j = 0; j < 4; ++j) srcv[j] = srcn[j];
@@ -499,7 +501,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
             }
             double acc_s = 0.0, acc_q = 0.0;
             float fs = 0.f, fq = 0.f;
-            int n = ch;
+            int n = pass0 * BN + ch;
             typename Epi::Par par = Epi::params(a, n, act);
             for (int k = 0; k < total_blocks; ++k) {
                 const int bi = k & 7, tl = k >> 3, buf = tl & 1;
@@ -509,7 +511,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
                         atomicAdd(a.stats + a.N + n, acc_q);
                     }
                     acc_s = acc_q = 0.0;
-                    n = (tl / my_tiles) * BN + ch;
+                    n = (pass0 + tl / my_tiles) * BN + ch;
                     par = Epi::params(a, n, act);
                 }
                 if (q == 0 && !(dbg & 128)) issue_blk(k + E - 1);
@@ -653,7 +655,15 @@ static int launch_ws(const PclRowGemm &a, cudaStream_t st) {
     }
     const long long n_tiles = (a.P + TILE_ROWS - 1) / TILE_ROWS;
     const long long grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-    kern<<<(unsigned)grid, kThreadsWS, smem, st>>>(b);
+    const int n_pass = a.N / BN;
+    dim3 g((unsigned)grid, 1, 1);
+    if (n_pass > 1 && n_tiles < kNumSMs) {   // few row tiles: one channel pass per blockIdx.y
+        g.y = (unsigned)n_pass;
+        long long gx = kNumSMs / n_pass;
+        gx = gx < 1 ? 1 : gx;
+        g.x = (unsigned)(gx < n_tiles ? gx : n_tiles);
+    }
+    kern<<<g, kThreadsWS, smem, st>>>(b);
     return check_launch("pcl_rowgemm(ws)");
 }
 

@@ -23,6 +23,9 @@ from .fused import (EPI_BWD_Y, EPI_STORE, EPI_STORE_STATS, PRO_BN_ACT, PRO_BN_BW
                     pack_weight, rowgemm, wgrad)
 
 
+SPLIT_BWD = 1   # 0: data gradient through the fused BN_BWD -> BWD_Y row GEMM of the serial tcgen05 kernel (A/B runs)
+
+
 def _widths_ok(cin, chans):
     """Channel widths the row-GEMM tiles cover (N % 32 == 0, N <= 128 or N % 128 == 0; K % 16 == 0 past layer 1)."""
     ok_n = lambda n: n % 32 == 0 and (n <= 128 or n % 128 == 0)
@@ -155,8 +158,18 @@ class RowMLPFn(torch.autograd.Function):
                 Wt = pack_weight(Wm.t().contiguous())              # (Kin, C): da = dz . W
                 dprev = torch.empty((P, Kin), **f32)
                 sums = torch.zeros((2, Kin), **f64)
-                rowgemm(PRO_BN_BWD, EPI_BWD_Y, "mlp_b", W=Wt, P=P, N=Kin, ldw=Wt.shape[-1], out=dprev, stats=sums,
-                        ey=ys[l - 1], escale=psc, eshift=psh, emean=pmu, erstd=prs, eslope=slope, **dzkw)
+                if SPLIT_BWD:
+                    # da on the warp-specialised pipeline (plain store), then act' and the BatchNorm sums of the layer
+                    # below in one elementwise pass: the fused BWD_Y epilogue only exists on the serial round-1 kernel,
+                    # which is 2-3x slower than this pair (dense.py docstring)
+                    rowgemm(PRO_BN_BWD, EPI_STORE, "mlp_bs", W=Wt, P=P, N=Kin, ldw=Wt.shape[-1], out=dprev, **dzkw)
+                    da = dprev
+                    dprev = torch.empty((P, Kin), **f32)
+                    _lib.call("pcl_bn_act_backward", ptr(da), ptr(ys[l - 1]), ptr(psc), ptr(psh), ptr(pmu), ptr(prs),
+                              float(slope), P, Kin, ptr(dprev), ptr(sums), stream(dprev), key=("mlp_b_act", P, Kin))
+                else:
+                    rowgemm(PRO_BN_BWD, EPI_BWD_Y, "mlp_b", W=Wt, P=P, N=Kin, ldw=Wt.shape[-1], out=dprev, stats=sums,
+                            ey=ys[l - 1], escale=psc, eshift=psh, emean=pmu, erstd=prs, eslope=slope, **dzkw)
                 dyh = dprev
             else:
                 # first layer, narrow: dW_1 = dz_1^T . x on the mma.sync reduction kernel (BatchNorm backward in its

@@ -51,6 +51,7 @@ def shared_mlp_rows(h: torch.Tensor, seq: nn.Sequential) -> torch.Tensor:
 
 
 FUSED = os.environ.get("PCL_FUSED", "1") != "0"
+DENSE_MAX = os.environ.get("PCL_DENSE_MAX", "1") != "0"   # mlp_max on the dense row-GEMM engine (0: torch layers)
 
 
 def _fusable(grouper, seq, xyz):
@@ -104,6 +105,15 @@ def sa_branch(grouper, seq: nn.Sequential, new_xyz, xyz, feature) -> torch.Tenso
 
 def mlp_max(grouped: torch.Tensor, seq: nn.Sequential) -> torch.Tensor:
     """grouped (B,S,ns,Cin) -> (B,S,Cout): shared MLP then max over the ns neighbours."""
+    from . import dense
     B, S, ns, Cin = grouped.shape
-    h = shared_mlp_rows(grouped.reshape(B * S * ns, Cin), seq)
+    rows = grouped.reshape(B * S * ns, Cin)
+    tr = _triples(seq)
+    convs, bns, acts = [t[0] for t in tr], [t[1] for t in tr], [t[2] for t in tr]
+    if FUSED and DENSE_MAX and dense.supported(rows, convs, bns, acts):
+        # GroupAll levels (SA3: 643 -> 256 -> 512 -> 1024 on B*128 rows) and branches the fused stage does not cover:
+        # the stack as row GEMMs with BatchNorm / ReLU in their prologues and epilogues (dense.py)
+        h = dense.row_mlp(rows, convs, bns, acts)
+    else:
+        h = shared_mlp_rows(rows, seq)
     return torch.max(h.view(B, S, ns, -1), dim=2)[0]

@@ -108,6 +108,19 @@ constexpr int kTabQuads = 40;
 constexpr int kSlackBytes = 2 * WG_BLK + 1024;       // the 128-lane operand read past the last staged block
 constexpr int kSrcSlot = NPR * kTT * 4;              // gather-index slots of one chunk   // channel quads covered by a parameter table (160 channels)
 
+// advance every per-channel vector and row-major operand of a view by c0 channels (blocked mode)
+__device__ __forceinline__ void shift_channels(PclRowGemm &a, int c0) {
+    if (a.x0) a.x0 += c0;
+    if (a.x1) a.x1 += c0;
+    if (a.scale) a.scale += c0;
+    if (a.shift) a.shift += c0;
+    if (a.mean) a.mean += c0;
+    if (a.rstd) a.rstd += c0;
+    if (a.bscale) a.bscale += c0;
+    if (a.m1) a.m1 += c0;
+    if (a.m2) a.m2 += c0;
+}
+
 // one operand (L or R) of the transform: piece bookkeeping of this thread
 template <int NP, class Pro>
 struct Operand {
@@ -123,8 +136,23 @@ struct Operand {
 // reads), so one copy of the data is loaded, transformed and staged.
 template <int S, int LAG, bool SHARE, class ProL, class ProR>
 __global__ void __launch_bounds__(kWgThreads, 1)
-wgrad_ws_kernel(const PclRowGemm al, const PclRowGemm ar, long long P, int M, int N, float *__restrict__ out, int ldo) {
+wgrad_ws_kernel(const PclRowGemm al_, const PclRowGemm ar_, long long P, int M_, int N_, float *__restrict__ out_, int ldo) {
     constexpr int PD = S - LAG;   // chunks in flight ahead of the transform
+    // Blocked mode (gridDim.y * gridDim.z > 1, dense stacks with M > 128 or N > 160): CTA (x, y, z) reduces ITS slice
+    // of the rows into the 128 x 128 block (y, z) of OUT — the operand views are the caller's, advanced by the block's
+    // first channel (row strides unchanged).  RW = width of the R operand (its row stride stays ar.K).
+    PclRowGemm al = al_, ar = ar_;
+    int M = M_, N = N_, RW = ar_.K;
+    float *__restrict__ out = out_;
+    if (gridDim.y * gridDim.z > 1) {
+        const int m0 = (int)blockIdx.y * 128, n0 = (int)blockIdx.z * 128;
+        shift_channels(al, m0);
+        shift_channels(ar, n0);
+        M = M_ - m0 < 128 ? M_ - m0 : 128;
+        N = N_ - n0 < 128 ? N_ - n0 : 128;
+        RW = N;
+        out = out_ + (long long)m0 * ldo + n0;
+    }
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     __shared__ __align__(8) uint64_t s_full[S], s_free[S], s_done;
@@ -154,7 +182,7 @@ wgrad_ws_kernel(const PclRowGemm al, const PclRowGemm ar, long long P, int M, in
     for (int e = tid; e < 3 * kTabQuads; e += kWgThreads) {
         const int t = e / kTabQuads, qd = e % kTabQuads;
         s_tabL[t][qd] = (t < ProL::T && qd * 4 < M) ? ProL::table(al, qd * 4, t) : f4zero();
-        s_tabR[t][qd] = (t < ProR::T && qd * 4 < ar.K) ? ProR::table(ar, qd * 4, t) : f4zero();
+        s_tabR[t][qd] = (t < ProR::T && qd * 4 < RW) ? ProR::table(ar, qd * 4, t) : f4zero();
     }
     // constant pieces, written once per stage: zeros for channel quads past the operand width, and the
     // ones column of the Gram operand.  (The live pieces never touch these slots.)
@@ -165,10 +193,10 @@ wgrad_ws_kernel(const PclRowGemm al, const PclRowGemm ar, long long P, int M, in
             const bool isR = r >= WG_ROWS * qL;
             const int rr = isR ? r - WG_ROWS * qL : r;
             const int qd = rr % (isR ? qR : qL), row = rr / (isR ? qR : qL);
-            const int width = isR ? ar.K : M;
+            const int width = isR ? RW : M;
             if (qd * 4 >= width) {
                 const uint32_t o = sbase + s * stage_bytes + (isR ? 2 * l_tile : 0) + mn_off(row, qd);
-                const bool one = isR && ProR::kOnes && qd * 4 == ar.K;
+                const bool one = isR && ProR::kOnes && qd * 4 == RW;
                 sts4(o, one ? 0x3F800000u : 0u, 0u, 0u, 0u);
                 sts4(o + (isR ? r_tile : l_tile), 0u, 0u, 0u, 0u);
             }
@@ -192,7 +220,7 @@ wgrad_ws_kernel(const PclRowGemm al, const PclRowGemm ar, long long P, int M, in
         Operand<NPL, ProL> L;
         Operand<NPR, ProR> R;
         const int qL = 8 * MB, qR = 8 * NB;
-        const int liveL = (M + 3) / 4, liveR = (ar.K + 3) / 4;   // live quads per row
+        const int liveL = (M + 3) / 4, liveR = (RW + 3) / 4;   // live quads per row
         // live pieces are enumerated over [32 rows][live quads]
         L.n_live = 0;
 #pragma unroll
@@ -334,7 +362,7 @@ wgrad_ws_kernel(const PclRowGemm al, const PclRowGemm ar, long long P, int M, in
             }
             if (ProR::kOnes && rows_valid < WG_ROWS) {
                 // ragged last chunk: the pre-written ones column must be 0 for the rows past P
-                const int qd = ar.K / 4;
+                const int qd = RW / 4;
                 if (tid < WG_ROWS && tid >= rows_valid) sts4(st + 2 * l_tile + mn_off(tid, qd), 0u, 0u, 0u, 0u);
             }
             if (!(dbg & 32)) fence_proxy_async();
@@ -409,20 +437,28 @@ static int launch_wgrad_ws(const PclRowGemm &al, const PclRowGemm &ar, long long
                            int ldo, cudaStream_t st) {
     size_t stage, slack;
     int S;
-    wgrad_ws_geometry(M, N, SHARE, ProR::kSrc, stage, slack, S);
+    const bool blocked = M > 128 || N > 160;
+    wgrad_ws_geometry(blocked ? 128 : M, blocked ? 128 : N, SHARE, ProR::kSrc, stage, slack, S);
     if (S == 0) {
         set_error("pcl_wgrad(ws): M=%d N=%d does not fit three stages", M, N);
         return PCL_ERR_UNSUPPORTED;
     }
     const size_t smem = 1024 + S * stage + slack;
     const long long n_chunks = (P + WG_ROWS - 1) / WG_ROWS;
-    const long long grid = n_chunks < kNumSMs ? n_chunks : kNumSMs;
+    dim3 grid((unsigned)(n_chunks < kNumSMs ? n_chunks : kNumSMs), 1, 1);
+    if (blocked) {   // one 128 x 128 block of OUT per (y, z); the row slices share what is left of the SMs
+        grid.y = (unsigned)((M + 127) / 128);
+        grid.z = (unsigned)((N + 127) / 128);
+        long long gx = kNumSMs / (long long)(grid.y * grid.z);
+        gx = gx < 1 ? 1 : gx;
+        grid.x = (unsigned)(gx < n_chunks ? gx : n_chunks);
+    }
     cudaError_t e = cudaSuccess;
 #define PCL_LAUNCH(S_, LAG_)                                                                      \
     do {                                                                                          \
         auto kern = wgrad_ws_kernel<S_, LAG_, SHARE, ProL, ProR>;                                 \
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-        if (e == cudaSuccess) kern<<<(unsigned)grid, kWgThreads, smem, st>>>(al, ar, P, M, N, out, ldo); \
+        if (e == cudaSuccess) kern<<<grid, kWgThreads, smem, st>>>(al, ar, P, M, N, out, ldo); \
     } while (0)
     if (S == 6) PCL_LAUNCH(6, 2);
     else if (S == 4) PCL_LAUNCH(4, 2);
@@ -452,8 +488,14 @@ bool wgrad_ws_supported(const PclRowGemm &al, int pl, const PclRowGemm &ar, int 
                        (pl == PCL_PRO_BN_BWD && pr == PCL_PRO_BN_ACT) ||
                        (pl == PCL_PRO_BN_BWD && pr == PCL_PRO_GATHER_BN_ACT) ||
                        (pl == PCL_PRO_BN_BWD && pr == PCL_PRO_GATHER_BN_ACT_MASK);
-    if (!combo || M > 128 || N > 160 || M % 4 != 0 || P < 1) return false;
+    if (!combo || M % 4 != 0 || P < 1) return false;
     if (al.K % 4 != 0 || ar.K % 4 != 0 || al.K < M) return false;
+    if (M > 128 || N > 160) {
+        // blocked mode: the dense-stack pair only (R as wide as its row stride), whole 16-column groups per block
+        if (!(pl == PCL_PRO_BN_BWD && pr == PCL_PRO_BN_ACT) || N != ar.K || N % 16 != 0) return false;
+        M = 128;
+        N = 128;
+    }
     size_t stage, slack;
     int S;
     ws::wgrad_ws_geometry(M, N, ws::gram_shares(al, pl, ar, pr, M),

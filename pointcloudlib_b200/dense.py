@@ -58,6 +58,12 @@ def _wgrad_any(pro_l, kw_l, pro_r, kw_r, P, M, N, out, name):
     """dW (M,N) = L^T R.  The tcgen05 reduction kernels hold one accumulator tile (M <= 128 lanes, N <= 160 columns):
     wider LEFT operands are walked in 128-channel slices (same row stride K, pointers advanced by the slice offset);
     wider right operands take the mma.sync 3xTF32 kernel, which tiles both."""
+    if (pro_l == PRO_BN_BWD and pro_r == PRO_BN_ACT and N == kw_r["K"] and N % 16 == 0 and M % 4 == 0
+            and (M > 128 or N > 160) and fused.MODE == 3):
+        # one launch, blocked over (M / 128) x (N / 128) accumulator tiles with the row slices spread over what is left
+        # of the SMs (wgrad_ws.cu): the layers with few rows and many channels (SA3, the PointConv / FP heads)
+        wgrad(pro_l, kw_l, pro_r, kw_r, P, M, N, out, name=name)
+        return
     if N <= 160:
         for m0 in range(0, M, 128):
             kl = dict(kw_l)

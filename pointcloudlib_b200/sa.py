@@ -54,6 +54,17 @@ FUSED = os.environ.get("PCL_FUSED", "1") != "0"
 DENSE_MAX = os.environ.get("PCL_DENSE_MAX", "1") != "0"   # mlp_max on the dense row-GEMM engine (0: torch layers)
 
 
+BRANCH_STREAMS = os.environ.get("PCL_BRANCH_STREAMS", "1") != "0"   # 0: the branches of a level back to back on one stream
+_streams = {}
+
+
+def _branch_stream(device, n):
+    key = (device.index if device.index is not None else torch.cuda.current_device(), n)
+    if key not in _streams:
+        _streams[key] = torch.cuda.Stream(device=device)
+    return _streams[key]
+
+
 def _fusable(grouper, seq, xyz):
     from . import fused
     from .misc.ops import BallQueryGrouper
@@ -79,6 +90,23 @@ def sa_branches(groupers, mlps, new_xyz, xyz, feature):
             continue                                  # a single radius: sa_branch below
         res = F.ball_query_msg(new_xyz, xyz, [float(str(groupers[i].radius)) for i in chunk],
                                [groupers[i].n_samples for i in chunk])
+        if BRANCH_STREAMS and xyz.is_cuda:
+            # the radius branches are independent after the shared scan: one stream each (forked from / joined to the
+            # current stream, so the whole thing still captures into one CUDA graph; autograd replays the backward
+            # of each branch on its forward stream).  Every big kernel here is one persistent CTA per SM, so two of
+            # them never share an SM — what overlaps is the tail of one with the head of the next and the dozens of
+            # small launches (weight packing, BatchNorm parameters, the algebra kernels) with somebody's GEMM.
+            cur = torch.cuda.current_stream(xyz.device)
+            for n, (i, (idx, _cnt)) in enumerate(zip(chunk, res)):
+                st = _branch_stream(xyz.device, n)
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    outs[i] = fused.fused_sa_branch(xyz, new_xyz, feature, idx, mlps[i], slope=0.0)
+                    idx.record_stream(st)
+            for n, i in enumerate(chunk):
+                cur.wait_stream(_branch_stream(xyz.device, n))
+                outs[i].record_stream(cur)
+            continue
         for i, (idx, _cnt) in zip(chunk, res):
             outs[i] = fused.fused_sa_branch(xyz, new_xyz, feature, idx, mlps[i], slope=0.0)
     for i, (g, m) in enumerate(zip(groupers, mlps)):

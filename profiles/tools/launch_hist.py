@@ -24,7 +24,7 @@ for e in prof.events():
         n = e.name[:90]
         tot[n][0] += 1
         tot[n][1] += e.device_time
-own = lambda n: any(k in n for k in ("pcl::", "rowgemm", "wgrad", "fps_", "ball_query", "knn_", "gather", "maxpool", "sel_outer", "bn_param", "pack_weight", "sgd_momentum", "three_", "index_points", "density", "graph_feature", "edgeconv"))
+own = lambda n: any(k in n for k in ("bn_act", "bn_bwd", "sa_bwd", "sa_algebra", "interp", "square_distance", "ws2", "pcl::", "rowgemm", "wgrad", "fps_", "ball_query", "knn_", "gather", "maxpool", "sel_outer", "bn_param", "pack_weight", "sgd_momentum", "three_", "index_points", "density", "graph_feature", "edgeconv"))
 rows = sorted(tot.items(), key=lambda kv: -kv[1][1])
 n_all = sum(v[0] for v in tot.values()); t_all = sum(v[1] for v in tot.values())
 n_own = sum(v[0] for k, v in tot.items() if own(k)); t_own = sum(v[1] for k, v in tot.items() if own(k))

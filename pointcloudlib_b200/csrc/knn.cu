@@ -25,6 +25,14 @@ constexpr int kKnnWarps = 8;
 constexpr int kKnnThreads = 256;
 constexpr int kKnnTR = 128;  // references per chunk
 
+// One channel of two squared distances with Blackwell's packed fp32 pipe (FADD2 / FFMA2: two IEEE round-to-nearest
+// operations per instruction, bit-identical to the scalar __fsub_rn / __fmaf_rn pair, r + (-q) == r - q): the
+// distance loop is FP32-issue bound, this halves its instruction count.
+__device__ __forceinline__ void dist2(float2 &acc, float ra, float rb, float q) {
+    const float2 t = __fadd2_rn(make_float2(ra, rb), make_float2(-q, -q));
+    acc = __ffma2_rn(t, t, acc);
+}
+
 // Insert (d, id) into the warp-distributed ascending list after every element <= d.
 template <int R>
 __device__ __forceinline__ void list_insert(float (&ld)[R], int (&li)[R], float d, int id,
@@ -111,11 +119,11 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float *__restric
     }
 
     for (int r0 = 0; r0 < Nr; r0 += kKnnTR) {
-        float acc[QW][4];
+        float2 acc[QW][2];
 #pragma unroll
         for (int qi = 0; qi < QW; ++qi)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[qi][j] = 0.f;
+            for (int j = 0; j < 2; ++j) acc[qi][j] = make_float2(0.f, 0.f);
 
         for (int c0 = 0; c0 < C; c0 += CC) {
             __syncthreads();
@@ -139,15 +147,8 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float *__restric
 #pragma unroll
                 for (int qi = 0; qi < QW; ++qi) {
                     const float qv = sQ[cc][warp * QW + qi];
-                    float t;
-                    t = __fsub_rn(rv.x, qv);
-                    acc[qi][0] = __fmaf_rn(t, t, acc[qi][0]);
-                    t = __fsub_rn(rv.y, qv);
-                    acc[qi][1] = __fmaf_rn(t, t, acc[qi][1]);
-                    t = __fsub_rn(rv.z, qv);
-                    acc[qi][2] = __fmaf_rn(t, t, acc[qi][2]);
-                    t = __fsub_rn(rv.w, qv);
-                    acc[qi][3] = __fmaf_rn(t, t, acc[qi][3]);
+                    dist2(acc[qi][0], rv.x, rv.y, qv);
+                    dist2(acc[qi][1], rv.z, rv.w, qv);
                 }
             }
         }
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float *__restric
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int r = r0 + j * 32 + lane;
-                const float d = r < Nr ? acc[qi][j] : CUDART_INF_F;
+                const float d = r < Nr ? ((j & 1) ? acc[qi][j >> 1].y : acc[qi][j >> 1].x) : CUDART_INF_F;
                 list_offer<R>(ld[qi], li[qi], thr[qi], d, r0 + j * 32, km1, lane);
             }
         }
@@ -266,14 +267,14 @@ __global__ void __launch_bounds__(kKnnThreads) knn_tma_kernel(const float *__res
             li[qi][r] = 0;
         }
     }
-    float acc[QW][4];
+    float2 acc[QW][2];
     for (int it = 0; it < total; ++it) {
         const int s = it % NS, rc = it / nC, cb = it - rc * nC;
         if (cb == 0) {
 #pragma unroll
             for (int qi = 0; qi < QW; ++qi)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[qi][j] = 0.f;
+                for (int j = 0; j < 2; ++j) acc[qi][j] = make_float2(0.f, 0.f);
         }
         // stage (it + 2) % NS was last read in iteration it - 1, which every thread left through the barrier below
         if (tid == 0 && it + 2 < total) issue_refs(it + 2);
@@ -288,15 +289,8 @@ __global__ void __launch_bounds__(kKnnThreads) knn_tma_kernel(const float *__res
 #pragma unroll
             for (int qi = 0; qi < QW; ++qi) {
                 const float qv = Q_[cc * TQ + qi];
-                float t;
-                t = __fsub_rn(r0v, qv);
-                acc[qi][0] = __fmaf_rn(t, t, acc[qi][0]);
-                t = __fsub_rn(r1v, qv);
-                acc[qi][1] = __fmaf_rn(t, t, acc[qi][1]);
-                t = __fsub_rn(r2v, qv);
-                acc[qi][2] = __fmaf_rn(t, t, acc[qi][2]);
-                t = __fsub_rn(r3v, qv);
-                acc[qi][3] = __fmaf_rn(t, t, acc[qi][3]);
+                dist2(acc[qi][0], r0v, r1v, qv);
+                dist2(acc[qi][1], r2v, r3v, qv);
             }
         }
         if (cb == nC - 1) {
@@ -306,7 +300,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn_tma_kernel(const float *__res
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int r = r0 + j * 32 + lane;
-                    const float d = r < Nr ? acc[qi][j] : CUDART_INF_F;
+                    const float d = r < Nr ? ((j & 1) ? acc[qi][j >> 1].y : acc[qi][j >> 1].x) : CUDART_INF_F;
                     list_offer<R>(ld[qi], li[qi], thr[qi], d, r0 + j * 32, km1, lane);
                 }
             }

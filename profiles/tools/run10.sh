@@ -1,2 +1,2 @@
-for bs in 0 1 0 1; do PCL_BRANCH_STREAMS=$bs timeout 400 python bench.py --workload pointnet2_msg --steps 20 --warmup 5 --no-cpu-baseline 2>gpurun_out/bs$bs.err | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('branch streams $bs', d['ms_per_step'], d['value'], d['config']['cuda_graph'], d['config']['cuda_graph_error'])"; tail -2 gpurun_out/bs$bs.err; done
-PCL_BRANCH_STREAMS=1 timeout 600 python -m pytest tests/test_models_gpu.py tests/test_fullsize_gpu.py -q -x 2>&1 | tail -3
+timeout 600 python -m pytest tests/test_ops_gpu.py tests/test_ref_kernels_gpu.py -q -x -k "knn or nn or interp" 2>&1 | tail -4
+timeout 200 python profiles/tools/knn_one.py

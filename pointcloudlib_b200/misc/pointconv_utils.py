@@ -131,9 +131,18 @@ class WeightNet(Module):
 def _density_conv_tail(mod, B, S, new_points, grouped_xyz_norm, grouped_density):
     """pointconv_utils.py:384-397 (shared by the set-abstraction and interpolation modules)."""
     from .. import dense
-    from ..sa import FUSED
+    from ..sa import FUSED, BRANCH_STREAMS, _branch_stream
     convs, bns = list(mod.mlp_convs), list(mod.mlp_bns)
     rows = new_points.reshape(-1, new_points.shape[-1])      # (B*S*ns, 3+D): already channels-last
+    # WeightNet (3 -> 8 -> 8 -> 16 channels: cuDNN BatchNorm kernels that occupy a handful of SMs) is independent of the
+    # shared MLP: its own stream, forked here and joined before the product (autograd replays its backward there too)
+    side = None
+    if BRANCH_STREAMS and new_points.is_cuda:
+        cur = torch.cuda.current_stream(new_points.device)
+        side = _branch_stream(new_points.device, 0)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            weights_side = mod.weightnet(grouped_xyz_norm.permute(0, 3, 2, 1))
     if FUSED and dense.supported(rows, convs, bns, [mod.relu] * len(convs)):
         # the shared MLP of pointconv_utils.py:384-389 as tcgen05 row GEMMs (BatchNorm / ReLU fused in)
         h = dense.row_mlp(rows.contiguous(), convs, bns, [mod.relu] * len(convs))
@@ -142,8 +151,12 @@ def _density_conv_tail(mod, B, S, new_points, grouped_xyz_norm, grouped_density)
         new_points = new_points.permute(0, 3, 2, 1)  # [B, C+D, nsample, npoint]
         for i in range(len(mod.mlp_convs)):
             new_points = mod.relu(mod.mlp_bns[i](mod.mlp_convs[i](new_points)))
-    grouped_xyz = grouped_xyz_norm.permute(0, 3, 2, 1)
-    weights = mod.weightnet(grouped_xyz)
+    if side is not None:
+        cur.wait_stream(side)
+        weights = weights_side
+        weights.record_stream(cur)
+    else:
+        weights = mod.weightnet(grouped_xyz_norm.permute(0, 3, 2, 1))
     new_points = new_points * grouped_density.permute(0, 3, 2, 1)
     new_points = torch.matmul(new_points.permute(0, 3, 1, 2),
                               weights.permute(0, 3, 2, 1)).reshape(B, S, -1)

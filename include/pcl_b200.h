@@ -142,6 +142,21 @@ int pcl_graph_feature_backward(const float *dout, const int32_t *idx, int B, int
 /* ---- a15: compute_density (misc/pointconv_utils.py:174-184) -------------------------------- */
 int pcl_compute_density(const float *xyz, int B, int N, float bandwidth, float *out, void *stream);
 
+/* ---- a17 / a18: density-weighted contraction of a PointConv layer ---------------------------
+ * Reference: misc/pointconv_utils.py:392-394 and :321-323 (new_points * grouped_density, then
+ * matmul(new_points.permute(0,3,1,2), weights.permute(0,3,2,1)).reshape(B, S, -1)).
+ *   out[g, c*W + w] = sum_k h[g*ns + k, c] * dens[g*ns + k] * wts[b, w, k, s],   g = b*S + s
+ * h (B*S*ns, C) channels-last rows, dens (B*S*ns), wts read in place through its element strides
+ * (sw_b, sw_w, sw_k, sw_s) — the WeightNet output (B, W, ns, S) needs no permuted copy.  W == 16,
+ * C % 128 == 0, ns <= 256.  Backward: dh (B*S*ns, C), ddens (B*S*ns), dwts with the strides of wts. */
+int pcl_density_contract(const float *h, const float *dens, const float *wts, long long sw_b,
+                         long long sw_w, long long sw_k, long long sw_s, int B, int S, int ns, int C,
+                         int W, float *out, void *stream);
+int pcl_density_contract_backward(const float *dout, const float *h, const float *dens,
+                                  const float *wts, long long sw_b, long long sw_w, long long sw_k,
+                                  long long sw_s, int B, int S, int ns, int C, int W, float *dh,
+                                  float *ddens, float *dwts, void *stream);
+
 /* ---- a5 / a8: per-group shared MLP (1x1 conv -> BatchNorm(train) -> ReLU)* -> max, fused -----
  * Reference: PointNetModuleBase.execute, networks/cls/pointnet2.py:52-57 (dup
  * networks/seg/pointnet2_partseg.py:61-67), EdgeConv blocks networks/cls/dgcnn.py:72-111.

@@ -18,6 +18,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "pcl_b200.h")
 _lib = None
 
 c_int, c_float, c_void_p, c_size_t = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+c_longlong = ctypes.c_longlong
 P = c_void_p
 
 # name -> argtypes (all return int except pcl_last_error)
@@ -45,6 +46,10 @@ _SIGNATURES = {
     "pcl_graph_feature": [P, P, c_int, c_int, c_int, c_int, P, P],
     "pcl_graph_feature_backward": [P, P, c_int, c_int, c_int, c_int, P, P],
     "pcl_compute_density": [P, c_int, c_int, c_float, P, P],
+    "pcl_density_contract": [P, P, P, c_longlong, c_longlong, c_longlong, c_longlong, c_int, c_int, c_int, c_int, c_int,
+                             P, P],
+    "pcl_density_contract_backward": [P, P, P, P, c_longlong, c_longlong, c_longlong, c_longlong, c_int, c_int, c_int,
+                                      c_int, c_int, P, P, P, P],
     "pcl_sgd_momentum": [P, P, P, c_size_t, c_float, c_float, c_float, c_float, P],
     "pcl_pack_weight": [P, c_int, c_int, c_int, c_float, P, P],
 }

@@ -386,6 +386,47 @@ def compute_density(xyz, bandwidth: float):
     return out
 
 
+class _DensityContractFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, dens, weights, B, S, ns):
+        h, dens, weights = f32(h), f32(dens), weights.float()
+        C, W = h.shape[1], weights.shape[1]
+        out = torch.empty((B, S, C * W), dtype=torch.float32, device=h.device)
+        sb, sw, sk, ss = weights.stride()
+        check(lib().pcl_density_contract(ptr(h), ptr(dens), ptr(weights), sb, sw, sk, ss, B, S, ns, C, W, ptr(out),
+                                         stream(h)), "pcl_density_contract")
+        ctx.save_for_backward(h, dens, weights)
+        ctx.shape = (B, S, ns)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, dens, weights = ctx.saved_tensors
+        B, S, ns = ctx.shape
+        C, W = h.shape[1], weights.shape[1]
+        dout = f32(dout)
+        dh = torch.empty_like(h)
+        ddens = torch.empty_like(dens)
+        dw = torch.empty_strided(weights.shape, weights.stride(), dtype=torch.float32, device=h.device)
+        sb, sw, sk, ss = weights.stride()
+        check(lib().pcl_density_contract_backward(ptr(dout), ptr(h), ptr(dens), ptr(weights), sb, sw, sk, ss, B, S, ns,
+                                                  C, W, ptr(dh), ptr(ddens), ptr(dw), stream(h)),
+              "pcl_density_contract_backward")
+        return dh, ddens, dw, None, None, None
+
+
+def density_contract_supported(h, weights, ns) -> bool:
+    return bool(h.is_cuda and h.dim() == 2 and h.shape[1] % 128 == 0 and weights.dim() == 4
+                and weights.shape[1] == 16 and 1 <= ns <= 256)
+
+
+def density_contract(h, dens, weights, B: int, S: int, ns: int):
+    """misc/pointconv_utils.py:392-394 / :321-323 on channels-last rows: h (B*S*ns, C) shared-MLP output, dens
+    (B*S*ns,) grouped density scale, weights (B, 16, ns, S) WeightNet output (any strides) ->
+    (B, S, C*16) = matmul((h * dens) as (B,S,C,ns), weights as (B,S,ns,16)).reshape(B, S, -1)."""
+    return _DensityContractFn.apply(h, dens.reshape(-1), weights, int(B), int(S), int(ns))
+
+
 def sgd_momentum_(param, grad, buf, lr, momentum=0.9, weight_decay=0.0, grad_scale=1.0):
     """In-place SGD+momentum over a flat fp32 bucket (train_cls.py:72 optimizer.step)."""
     n = param.numel()

@@ -146,8 +146,10 @@ def _density_conv_tail(mod, B, S, new_points, grouped_xyz_norm, grouped_density)
     if FUSED and dense.supported(rows, convs, bns, [mod.relu] * len(convs)):
         # the shared MLP of pointconv_utils.py:384-389 as tcgen05 row GEMMs (BatchNorm / ReLU fused in)
         h = dense.row_mlp(rows.contiguous(), convs, bns, [mod.relu] * len(convs))
+        rows_out = h
         new_points = h.view(new_points.shape[0], new_points.shape[1], new_points.shape[2], -1).permute(0, 3, 2, 1)
     else:
+        rows_out = None
         new_points = new_points.permute(0, 3, 2, 1)  # [B, C+D, nsample, npoint]
         for i in range(len(mod.mlp_convs)):
             new_points = mod.relu(mod.mlp_bns[i](mod.mlp_convs[i](new_points)))
@@ -157,9 +159,15 @@ def _density_conv_tail(mod, B, S, new_points, grouped_xyz_norm, grouped_density)
         weights.record_stream(cur)
     else:
         weights = mod.weightnet(grouped_xyz_norm.permute(0, 3, 2, 1))
-    new_points = new_points * grouped_density.permute(0, 3, 2, 1)
-    new_points = torch.matmul(new_points.permute(0, 3, 1, 2),
-                              weights.permute(0, 3, 2, 1)).reshape(B, S, -1)
+    ns = grouped_density.shape[2]
+    if rows_out is not None and F.density_contract_supported(rows_out, weights, ns):
+        # x density, then the per-group (C x ns).(ns x 16) product, from the row matrix and the strided WeightNet
+        # output as they are (pcl_density_contract): no permuted copies around a batched matmul
+        new_points = F.density_contract(rows_out, grouped_density, weights, B, S, ns)
+    else:
+        new_points = new_points * grouped_density.permute(0, 3, 2, 1)
+        new_points = torch.matmul(new_points.permute(0, 3, 1, 2),
+                                  weights.permute(0, 3, 2, 1)).reshape(B, S, -1)
     new_points = mod.linear(new_points)
     new_points = mod.bn_linear(new_points.permute(0, 2, 1))
     return mod.relu(new_points)

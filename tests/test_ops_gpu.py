@@ -341,3 +341,30 @@ def test_group_backward_reaches_a_permuted_feature():
     base.grad = None
     out2.sum().backward()
     assert base.grad is not None and float(base.grad.abs().sum()) > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,S,ns,C", [(4, 64, 32, 128), (2, 16, 64, 256), (3, 1, 128, 1024), (2, 5, 7, 128)])
+def test_density_contract_matches_the_permute_matmul_form(B, S, ns, C):
+    """pcl_density_contract == misc/pointconv_utils.py:392-394 (x density, permute, matmul, reshape) and its autograd,
+    with the WeightNet output read in place (B, 16, ns, S)."""
+    torch.manual_seed(B * 100 + ns)
+    dev = "cuda"
+    h = torch.randn(B * S * ns, C, device=dev, requires_grad=True)
+    dens = (torch.rand(B, S, ns, 1, device=dev) + 0.5).requires_grad_(True)
+    wts = torch.randn(B, 16, ns, S, device=dev, requires_grad=True)
+    out = F.density_contract(h, dens, wts, B, S, ns)
+    go = torch.randn_like(out)
+    out.backward(go)
+    h64, d64, w64 = (t.detach().double().requires_grad_(True) for t in (h, dens, wts))
+    np_ = h64.view(B, S, ns, C).permute(0, 3, 2, 1)                     # (B, C, ns, S)
+    np_ = np_ * d64.permute(0, 3, 2, 1)
+    ref = torch.matmul(np_.permute(0, 3, 1, 2), w64.permute(0, 3, 2, 1)).reshape(B, S, -1)
+    ref.backward(go.double())
+    rel = lambda a, b: ((a.double() - b).norm() / b.norm().clamp_min(1e-30)).item()
+    assert rel(out, ref) <= 1e-5
+    assert rel(h.grad, h64.grad) <= 1e-5
+    assert rel(dens.grad, d64.grad) <= 1e-5
+    assert rel(wts.grad, w64.grad) <= 1e-5
+    with pytest.raises(RuntimeError):
+        F.density_contract(h[:, :100].contiguous(), dens, wts, B, S, ns)

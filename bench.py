@@ -492,6 +492,12 @@ def run_product_arm(args, wl: Workload):
     prof_steps = min(args.steps, 5)
     trainer_graph = trainer.use_graph
     trainer.use_graph = False
+    # the radius branches of a level run on one stream each in the timed region; here they run back to back on ONE
+    # stream, so an event pair brackets exactly one kernel (with the branch streams on, a small branch's launch is
+    # timed while another branch's persistent kernel holds the SMs and its duration means nothing)
+    from pointcloudlib_b200 import sa as _sa
+    branch_streams = _sa.BRANCH_STREAMS
+    _sa.BRANCH_STREAMS = False
     pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i in range(2):   # the eager path re-grows its allocator pool after the graph capture
         x, l = resident[i % n_slots]
@@ -507,6 +513,7 @@ def run_product_arm(args, wl: Workload):
     ms_prof = pe0.elapsed_time(pe1)
     kernel_stats = kt.summary()
     trainer.use_graph = trainer_graph
+    _sa.BRANCH_STREAMS = branch_streams
 
     # ---- timed region 2: end to end from pinned host buffers -------------------------------
     sync_all()
@@ -573,7 +580,8 @@ def run_product_arm(args, wl: Workload):
                 "instrumented_step_us": step_us,
                 "note": "dominant own kernel by total time; CUDA events on the launch stream around every own "
                         "launch, in an eager pass of the same step run right after the timed region (the timed "
-                        "region replays one CUDA graph per step, which events cannot subdivide); every kernel is "
+                        "region replays one CUDA graph per step, which events cannot subdivide), the radius branches "
+                        "serialised on one stream for this pass only; every kernel is "
                         "quoted against the measured HBM copy peak and, for the tcgen05 3xTF32 GEMMs, the TF32 "
                         "throughput measured here (issued flops = 3x logical); bound = the nearer ceiling; "
                         "traffic = dram read+write per launch from this round's ncu --set full capture "

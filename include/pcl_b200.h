@@ -190,6 +190,14 @@ int pcl_density_contract_backward(const float *dout, const float *h, const float
  *                          from global memory — relu' is the sign of the operand tile the prologue just staged
  *                          (A-operand element (p, C3 + n)), handed to the epilogue through shared memory; the caller
  *                          derives sum v*xhat algebraically
+ *     PCL_EPI_BWD_Y_MASK_ROUTED  the same output with the routed term in its SPARSE form: PCL_PRO_BN_ACT, K == N <= 128
+ *                          (W = the -Q^T block), x1 = W3 (C3, N) row-major, selpos = the (G, C3, 2) entry list of
+ *                          pcl_routed_sort (row | W3 offset, value; ordered by row inside each group).  Before a
+ *                          tile's MMAs start, the epilogue warps that own its tensor-memory accumulator write
+ *                          sum_e value_e * W3[channel_e, :] into the accumulator column of every row (fp32 FMAs, one
+ *                          tcgen05.st per row) and the MMAs accumulate -a2.Q on top: the K = C3 one-hot block of
+ *                          PCL_PRO_G3_A2 (more than half of that kernel's MMA and shared-memory traffic) is gone.
+ *                          x3 == 3, ns = 2^j in [1, 128], C3 % 32 == 0, ReLU.
  */
 /* Field notes: c0 / c1 are the widths of x0 / x1 for PCL_PRO_PLAIN2 only.  For every other prologue
  * c0 carries opt-in switches of the tcgen05 kernels and must be 0 in production: bit 15 routes the
@@ -212,7 +220,7 @@ enum { PCL_PRO_PLAIN2 = 0, PCL_PRO_BN_ACT = 1, PCL_PRO_GATHER_BN_ACT = 2, PCL_PR
        PCL_PRO_GATHER_BN_ACT_MASK = 6 /* pcl_wgrad R operand only (x3 == 3): [a1 | relu'] with a1 as
                                          PCL_PRO_GATHER_BN_ACT, K % 32 == 0, N = 2K <= 160 */ };
 enum { PCL_EPI_STORE = 0, PCL_EPI_STORE_STATS = 1, PCL_EPI_MAXMIN_STATS = 2, PCL_EPI_BWD_Y = 3,
-       PCL_EPI_BWD_GATHER = 4, PCL_EPI_BWD_Y_ROUTED = 5, PCL_EPI_BWD_Y_MASK = 6 };
+       PCL_EPI_BWD_GATHER = 4, PCL_EPI_BWD_Y_ROUTED = 5, PCL_EPI_BWD_Y_MASK = 6, PCL_EPI_BWD_Y_MASK_ROUTED = 7 };
 int pcl_rowgemm(const PclRowGemm *args, int prologue, int epilogue, int x3, void *stream);
 /* Weight operand of pcl_rowgemm: w (N,K) fp32, row stride ldi -> out (3, N, ld), ld = K rounded up to
  * 32, zero padded: [sign*w | tf32 hi | tf32 lo] with hi = rna_tf32(sign*w), lo = rna_tf32(sign*w - hi).
@@ -292,6 +300,13 @@ int pcl_sa_bwd_finish(const float *W3, const double *Q, const double *tvec, cons
                       int C2, int algebraic, float *dW3, double *sums2, float *m1, float *m2, void *stream);
 int pcl_sa_bwd_sums1(const float *W2, const float *dwm, const float *sc1, const float *sh1, const float *mu1,
                      const float *rs1, long long P, int C2, int C1, double *sums1, float *m1, float *m2, void *stream);
+/* Entry lists of the routed max-pool gradient for PCL_EPI_BWD_Y_MASK_ROUTED: per group g the C3 int32 pairs
+ * (((g*ns + selpos[g,c]) % 128) << 24 | c*N*4, bits of g3s[g,c]) ordered by row selpos (ties in channel order)
+ * -> ent (G, C3, 2).  The first word is the row inside the row GEMM's 128-row tile and the byte offset of row c of
+ * W3 (C3, N) fp32.  The reference has no counterpart (Jittor autograd of argmax, networks/cls/pointnet2.py:57).
+ * ns = 2^j <= 128, C3*N*4 <= 2^24. */
+int pcl_routed_sort(const int32_t *selpos, const float *g3s, long long G, int C3, int ns, int N, int32_t *ent,
+                    void *stream);
 
 /* ---- a7 / a8: fused EdgeConv (networks/cls/dgcnn.py:29-50 + :72-83,100-111) -------------------
  * W.[x_j - x_i ; x_i] = W1.x_j + (W2-W1).x_i  =>  y[i,j] = u[src[i,j]] + vsign*v[i] on per-point

@@ -763,6 +763,11 @@ extern "C" int pcl_rowgemm(const PclRowGemm *args, int prologue, int epilogue, i
                   "C3 %% 16 == 0, ReLU, ns = 2^j in [4, 256] (K=%d N=%d C3=%d ns=%d)", a.K, a.N, a.C3, a.ns);
         return PCL_ERR_UNSUPPORTED;
     }
+    if (epilogue == PCL_EPI_BWD_Y_MASK_ROUTED && !(x3 == 3 && rowgemm_ws_supported(a, prologue, epilogue))) {
+        set_error("pcl_rowgemm: PCL_EPI_BWD_Y_MASK_ROUTED needs x3 == 3, PCL_PRO_BN_ACT, K == N <= 128, N %% 32 == 0, "
+                  "C3 %% 32 == 0, ReLU, ns = 2^j <= 128, x1 / g3s / selpos (K=%d N=%d C3=%d ns=%d)", a.K, a.N, a.C3, a.ns);
+        return PCL_ERR_UNSUPPORTED;
+    }
     if (a.P == 0) return PCL_OK;
     cudaStream_t st = (cudaStream_t)stream;
     // x3: 0 = mma.sync TF32, 1 = mma.sync 3xTF32, 2 = tcgen05 3xTF32 (W = [raw | hi | lo] stacked)

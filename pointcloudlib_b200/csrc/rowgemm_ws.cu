@@ -30,6 +30,8 @@
 //     [act hi 256x64B | act lo | W hi BNx64B | W lo] (32 KB + 2*BN*64 B); the weight rows >= BN are
 //     not staged: the 128-lane read runs into whatever follows and only feeds accumulator lanes that
 //     nobody reads.  Accumulators: 2 x 256 TMEM columns.
+#include <type_traits>
+
 #include "ws_common.cuh"
 
 namespace pcl {
@@ -373,48 +375,53 @@ __global__ void __launch_bounds__(kThreadsWS, 1) rowgemm_ws_kernel(const PclRowG
                                     }
                                 }
                             }
-                        } else if constexpr (kMaskStash) {
-                            const float bias = act && a.ebias ? __ldg(a.ebias + n) : 0.f;
-                            const uint32_t ms = mstash + (uint32_t)buf * mstash_tile + (uint32_t)(h * 128 * a.N + (act ? ch : 0));
-                            for (int blk = 0; blk < 8; ++blk) {
-                                const long long pb = p0 + blk * 16;
-                                if (pb >= a.P) break;
-                                float v[16];
-                                tc_ld16(tbase + blk * 16, v);
-                                if (act) {
-                                    float *op = a.out + pb * a.N + n;
-#pragma unroll
-                                    for (int i = 0; i < 16; ++i) {
-                                        uint32_t m;
-                                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(m) : "r"(ms + (uint32_t)((blk * 16 + i) * a.N)));
-                                        if (pb + i < a.P) {
-                                            const float x = m ? v[i] + bias : 0.f;
-                                            if (!(dbg & 32)) op[(long long)i * a.N] = x;
-                                            fs += x;
-                                        }
-                                    }
-                                }
-                            }
                         } else {
+                            // Store epilogues (as in rowgemm_ws2.cu): the tensor-memory load of the NEXT 16-row block in
+                            // flight while this one is written, no per-row bounds checks on a full half tile, the
+                            // ReLU-mask bytes of a block fetched together before their first use.
+                            const float bias = kMaskStash && act && a.ebias ? __ldg(a.ebias + n) : 0.f;
+                            const uint32_t ms = mstash + (uint32_t)buf * mstash_tile + (uint32_t)(h * 128 * a.N + (act ? ch : 0));
                             const typename Epi::Par par = Epi::params(a, n, act);
-                            for (int blk = 0; blk < 8; ++blk) {
+                            const bool full = p0 + 128 <= a.P;
+                            float *orow = a.out + p0 * a.N + n;
+                            const long long ostep = a.N;
+                            auto process = [&](auto fullc, int blk, const uint32_t (&r)[16]) {
+                                constexpr bool kFull = decltype(fullc)::value;
+                                if (!act) return;
                                 const long long pb = p0 + blk * 16;
-                                if (pb >= a.P) break;
-                                float v[16];
-                                tc_ld16(tbase + blk * 16, v);
-                                if (act) {
-                                    float *op = a.out + pb * a.N + n;
+                                [[maybe_unused]] uint32_t m[16];
+                                if constexpr (kMaskStash) {
 #pragma unroll
-                                    for (int i = 0; i < 16; ++i) {
-                                        if (pb + i < a.P) {
-                                            float x = v[i], qq;
-                                            Epi::apply(a, par, x, qq, 0.f);
-                                            if (!(dbg & 32)) op[(long long)i * a.N] = x;
-                                            if (Epi::kStats) { fs += x; fq += qq; }
-                                        }
-                                    }
+                                    for (int i = 0; i < 16; ++i)
+                                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(m[i]) : "r"(ms + (uint32_t)((blk * 16 + i) * a.N)));
                                 }
-                            }
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) {
+                                    if (kFull || pb + i < a.P) {
+                                        float x = __uint_as_float(r[i]), qq = 0.f;
+                                        if constexpr (kMaskStash) x = m[i] ? x + bias : 0.f;
+                                        else Epi::apply(a, par, x, qq, 0.f);
+                                        if (!(dbg & 32)) *orow = x;
+                                        if (Epi::kStats) { fs += x; fq += qq; }
+                                    }
+                                    orow += ostep;
+                                }
+                            };
+                            auto drain = [&](auto fullc) {
+                                uint32_t ra[16], rb[16];
+                                tc_ld16_async(tbase, ra);
+#pragma unroll
+                                for (int blk = 0; blk < 8; blk += 2) {
+                                    tc_wait_ld16(ra);
+                                    tc_ld16_async(tbase + (blk + 1) * 16, rb);
+                                    process(fullc, blk, ra);
+                                    tc_wait_ld16(rb);
+                                    if (blk + 2 < 8) tc_ld16_async(tbase + (blk + 2) * 16, ra);
+                                    process(fullc, blk + 1, rb);
+                                }
+                            };
+                            if (full) drain(std::true_type{});
+                            else drain(std::false_type{});
                         }
                     }
                     tc_fence_before();
@@ -670,7 +677,9 @@ static int launch_ws(const PclRowGemm &a, cudaStream_t st) {
 }  // namespace ws
 
 // Shapes the warp-specialised kernel covers; everything else stays on rowgemm_tc_kernel.
+bool rowgemm_ws2_supported(const PclRowGemm &a, int pro, int epi);                 // rowgemm_ws2.cu
 bool rowgemm_ws_supported(const PclRowGemm &a, int pro, int epi) {
+    if (epi == PCL_EPI_BWD_Y_MASK_ROUTED) return rowgemm_ws2_supported(a, pro, epi);   // generation 4 only
     if (epi == PCL_EPI_BWD_Y_MASK) {
         // the ReLU mask comes from the staged operand: K == C3 + N, one pass, ReLU (slope 0); the one-hot scatter needs
         // whole groups inside a 256-row tile and at most 4 entries per transform thread
@@ -715,7 +724,8 @@ int rowgemm_ws2_dispatch(const PclRowGemm &a, int pro, int epi, cudaStream_t st)
 int rowgemm_ws_dispatch(const PclRowGemm &a, int pro, int epi, cudaStream_t st) {
     using namespace ws;
     // generation 4 (weights in tensor memory) where it applies; knob 2048 keeps generation 3
-    if (!((a.c0 >> 16) & 2048) && rowgemm_ws2_supported(a, pro, epi)) return rowgemm_ws2_dispatch(a, pro, epi, st);
+    if ((!((a.c0 >> 16) & 2048) || epi == PCL_EPI_BWD_Y_MASK_ROUTED) && rowgemm_ws2_supported(a, pro, epi))
+        return rowgemm_ws2_dispatch(a, pro, epi, st);
     if (pro == PCL_PRO_G3_A2 && epi == PCL_EPI_BWD_Y_MASK)
         return ws_mask_stages(a.N) == 4 ? launch_ws_s<16, WProG3A2, WEpiBwdYMask, 4>(a, st)
                                         : launch_ws_s<16, WProG3A2, WEpiBwdYMask, 3>(a, st);

@@ -19,7 +19,14 @@
 //   * epilogue warp set h (4 warps, one per TMEM lane quarter) owns accumulator h = the tiles of parity h.
 //   * PCL_PRO_G3_A2 (last-layer backward): the dense part (-Q^T, C2 <= 128 columns) is TMEM resident; the routed
 //     one-hot K block keeps generation 3's scheme — W3^T chunk staged in shared memory next to the scattered
-//     one-hot tile, both operands from shared memory.
+//     one-hot tile, both operands from shared memory (slower than generation 3: opt-in).
+//   * PCL_EPI_BWD_Y_MASK_ROUTED (last-layer backward, production): NO one-hot block.  The routed term
+//     sum_e g3s_e * W3[c3_e, :] of a row is a handful of fp32 FMAs; the epilogue warps that own accumulator h
+//     write it into tensor memory (tcgen05.st, one column = one row, entries pre-sorted by row) right after they
+//     have drained the previous tile of that accumulator, and every MMA of the tile accumulates on top of it.  K
+//     drops from C3 + C2 to C2, the ring holds activations only, W3 sits in shared memory once per CTA when it fits.
+#include <type_traits>
+
 #include "ws_common.cuh"
 
 namespace pcl {
@@ -39,6 +46,8 @@ constexpr int A_BYTES = TR * KC * 4;                 // 16 KB, one of hi / lo
 constexpr int kLagDefault = 2;
 constexpr int kWCol = 256;                           // first TMEM column of the resident weights
 constexpr int kSmemMax2 = 232448 - 512;
+constexpr int kEntMax = 512;                         // routed pre-load: entries of one tile
+constexpr int kEntBytes = kEntMax * 8;               // ... as (row | W3 offset, value) pairs, one buffer per epilogue warp set
 
 __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
                                                uint32_t accumulate) {
@@ -56,9 +65,16 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16])
         : "memory");
 }
 
+__device__ __forceinline__ void tc_st1(uint32_t taddr, float v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(__float_as_uint(v)) : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 template <class Pro, class Epi, int S, int kLag = kLagDefault>
 __global__ void __launch_bounds__(kThreads2, 1) rowgemm_ws2_kernel(const PclRowGemm a) {
     constexpr bool kMaskStash = EpiTraits<Epi>::kMask;
+    constexpr bool kRouted = EpiTraits<Epi>::kRouted;   // routed term pre-loaded into the accumulator
+    constexpr bool kW3Smem = EpiTraits<Epi>::kW3Smem;   // ... with W3 (C3 x N fp32) in shared memory, else read through L2
     // instruction descriptor: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), both K-major, N>>3, M>>4
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TR >> 3) << 17) |
                                ((uint32_t)(MMA_M >> 4) << 24);
@@ -131,6 +147,15 @@ __global__ void __launch_bounds__(kThreads2, 1) rowgemm_ws2_kernel(const PclRowG
     // (one-hot: the 128-lane read of the staged W lo runs (128 - BN) rows past the last stage)
     const uint32_t mstash = sbase + S * stage_bytes + (Pro::kOneHot ? (uint32_t)((MMA_M - BN) * KC * 4) : 0u);
     const uint32_t mstash_tile = (uint32_t)(TR * a.N);
+    const uint32_t w3s = mstash + 2 * mstash_tile;        // kRouted && a.c1: W3 (C3, N) fp32, once per CTA
+    if (kRouted && kW3Smem) {
+        const int n4 = a.C3 * a.N / 4;
+        for (int e = tid; e < n4; e += kThreads2) {
+            const float4 v = ld4(a.x1 + 4 * e);
+            sts4(w3s + 16u * (uint32_t)e, __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+        }
+        __syncthreads();
+    }
 
     if (warp < kTW) {
         // ============================ TRANSFORM warps ============================
@@ -256,7 +281,7 @@ __global__ void __launch_bounds__(kThreads2, 1) rowgemm_ws2_kernel(const PclRowG
             const uint32_t st = sbase + s * stage_bytes;
             const int k0 = c_kc * KC;
             if (kMaskStash && c_kc == 0 && c_lt >= 2)   // the epilogue has drained this tile's stash buffer (tile c_lt - 2)
-                mbar_wait(smem_u32(&s_accempty[c_lt & 1]), (uint32_t)(((c_lt >> 1) - 1) & 1));
+                mbar_wait(smem_u32(&s_accempty[c_lt & 1]), (uint32_t)(((c_lt >> 1) - (kRouted ? 0 : 1)) & 1));
             if (Pro::kOneHot && k0 < kbase) {
                 // routed one-hot chunk: per (group, channel) ONE row carries g3s; everything else is 0.
                 // Zero the tile, then scatter the (128/ns)*32 entries.
@@ -340,12 +365,110 @@ __global__ void __launch_bounds__(kThreads2, 1) rowgemm_ws2_kernel(const PclRowG
         const int n = q * 32 + lane;
         const bool act = n < BN;
         double acc_s = 0.0, acc_q = 0.0;
+        // kRouted: routed term of local tile lt -> accumulator h.  Entries of the tile = its (128 / ns) groups x C3 pairs
+        // (row_in_tile << 24 | byte offset of W3 row c3, value) from pcl_routed_sort, ordered by row.  Lane = output
+        // channel: a row's entries are summed in a register (fp32 FMAs) and written with ONE tcgen05.st into the
+        // row's accumulator column.  The entry list of tile lt + 2 (1-4 KB, streamed from HBM once) is cp.async'ed into
+        // the warp set's buffer BEFORE tile lt is drained, so its latency hides behind the drain; the four warps of
+        // the set read it back with broadcast 128-bit loads, 16 W3 values in flight per thread.
+        const uint32_t ebuf = w3s + (kW3Smem ? (uint32_t)(a.C3 * a.N * 4) : 0u) + (uint32_t)h * kEntBytes;
+        auto set_barrier = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + h) : "memory"); };
+        auto tile_entries = [&](int lt, const int2 *&ep) {
+            const long long p0 = (blockIdx.x + (long long)lt * gridDim.x) * TR;
+            const long long rows = a.P - p0 < TR ? a.P - p0 : TR;
+            ep = reinterpret_cast<const int2 *>(a.selpos) + (p0 >> a.reserved) * a.C3;
+            return (int)(rows >> a.reserved) * a.C3;
+        };
+        auto fetch_entries = [&](int lt) {   // this warp's share of tile lt's entry list -> the set's buffer
+            if (lt < my_tiles) {
+                const int2 *ep;
+                const int n16 = tile_entries(lt, ep) / 2;          // 16-byte pieces (two entries each)
+                for (int e = q * 32 + lane; e < n16; e += 128)
+                    cp_async16_zfill(ebuf + 16u * (uint32_t)e, reinterpret_cast<const int4 *>(ep) + e, true);
+            }
+            cp_async_commit();
+        };
+        long long prof[6] = {0, 0, 0, 0, 0, 0};   // knob 16384: cycles in {entry wait, zero fill, entry loop, accfull wait, drain, tiles}
+        const bool profiling = kRouted && (dbg & 16384);
+        auto preload = [&](int lt) {
+            long long t0 = profiling ? clock64() : 0;
+            cp_async_wait<0>();
+            set_barrier();                                   // every warp's share of the list has landed
+            if (profiling) { const long long t1 = clock64(); prof[0] += t1 - t0; t0 = t1; }
+            if (q * 32 >= BN || lt >= my_tiles) return;
+            const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * TR);
+            const int2 *ep;
+            const int nE = tile_entries(lt, ep);
+            {
+                uint32_t z[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) z[i] = 0u;
+#pragma unroll
+                for (int blk = 0; blk < TR / 16; ++blk) tc_st16(tb + blk * 16, z);
+                tc_wait_st();
+            }
+            if (profiling) { const long long t1 = clock64(); prof[1] += t1 - t0; t0 = t1; }
+            const uint32_t wl = w3s + 4u * (uint32_t)n;
+            const char *wg = reinterpret_cast<const char *>(a.x1 + n);
+            uint32_t cur = 0xFFFFFFFFu;                      // row whose sum is being built (none yet)
+            float sum = 0.f;
+            // 16 entries per step: their (row | offset, value) pairs by 8 broadcast 128-bit reads of the set's buffer, then
+            // the 16 W3 values in flight together, then the sums.  (A deeper software pipeline — entries two steps and W3
+            // values one step ahead — was measured SLOWER, 599 vs 536 us at P = 2M: the step is bound by the latency of
+            // shared-memory reads queued behind the transform warps' and the tensor core's traffic, ~450 cycles each,
+            // and the rotating register sets spilled.)
+            for (int e0 = 0; e0 < nE; e0 += 16) {
+                uint32_t ee[16];
+                float vv[16], w[16];
+#pragma unroll
+                for (int u = 0; u < 16; u += 2) {
+                    uint32_t x0, x1, x2, x3;
+                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
+                                 : "r"(ebuf + 8u * (uint32_t)(e0 + u)));
+                    ee[u] = x0; vv[u] = __uint_as_float(x1);
+                    ee[u + 1] = x2; vv[u + 1] = __uint_as_float(x3);
+                }
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const uint32_t off = ee[u] & 0xFFFFFFu;
+                    if (kW3Smem) {
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w[u]) : "r"(wl + off));
+                    } else {
+                        w[u] = __ldg(reinterpret_cast<const float *>(wg + off));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const uint32_t row = ee[u] >> 24;
+                    const bool nw = row != cur;              // warp-uniform
+                    if (nw && cur != 0xFFFFFFFFu && !(dbg & 128)) tc_st1(tb + cur, sum);
+                    sum = fmaf(vv[u], w[u], nw ? 0.f : sum);
+                    cur = row;
+                }
+            }
+            if (cur != 0xFFFFFFFFu) tc_st1(tb + cur, sum);
+            tc_wait_st();
+            if (profiling) prof[2] += clock64() - t0;
+        };
+        if (kRouted) {   // the first tile of this accumulator; from then on each tile's drain is followed by the next preload
+            fetch_entries(h);
+            preload(h);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s_accempty[h]));
+        }
         for (int lt = h; lt < my_tiles; lt += 2) {
             const long long p0 = (blockIdx.x + (long long)lt * gridDim.x) * TR;
             const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * TR);
             float fs = 0.f, fq = 0.f;
+            if (kRouted) {
+                set_barrier();            // the set is done reading the buffer (the pre-load that ended the last turn)
+                fetch_entries(lt + 2);
+            }
+            long long tp = profiling ? clock64() : 0;
             while (!mbar_try_wait(smem_u32(&s_accfull[h]), (uint32_t)((lt >> 1) & 1))) __nanosleep(64);
             tc_fence_after();
+            if (profiling) { const long long t1 = clock64(); prof[3] += t1 - tp; tp = t1; }
             if (!(dbg & 2)) {
                 if constexpr (Epi::kMaxMin) {
                     const int ns = a.ns, sh = a.reserved;
@@ -372,56 +495,65 @@ __global__ void __launch_bounds__(kThreads2, 1) rowgemm_ws2_kernel(const PclRowG
                             mx = -3.402823466e38f; mn = 3.402823466e38f; imx = 0; imn = 0;
                         }
                     }
-                } else if constexpr (kMaskStash) {
-                    const float bias = act && a.ebias ? __ldg(a.ebias + n) : 0.f;
-                    const uint32_t ms = mstash + (uint32_t)h * mstash_tile + (uint32_t)(act ? n : 0);
-                    for (int blk = 0; blk < 8; ++blk) {
-                        const long long pb = p0 + blk * 16;
-                        if (pb >= a.P) break;
-                        float v[16];
-                        tc_ld16(tbase + blk * 16, v);
-                        if (act) {
-                            float *op = a.out + pb * a.N + n;
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                uint32_t m;
-                                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(m) : "r"(ms + (uint32_t)((blk * 16 + i) * a.N)));
-                                if (pb + i < a.P) {
-                                    const float x = m ? v[i] + bias : 0.f;
-                                    if (!(dbg & 32)) op[(long long)i * a.N] = x;
-                                    fs += x;
-                                }
-                            }
-                        }
-                    }
                 } else {
+                    // Store epilogues.  The accumulator comes out of tensor memory 16 rows at a time, the load of the NEXT
+                    // block in flight while this one is written; a full tile (all but the last) takes the path without
+                    // per-row bounds checks; the ReLU-mask bytes of a block are fetched together before their first use.
+                    const float bias = kMaskStash && act && a.ebias ? __ldg(a.ebias + n) : 0.f;
+                    const uint32_t ms = mstash + (uint32_t)h * mstash_tile + (uint32_t)(act ? n : 0);
                     const typename Epi::Par par = Epi::params(a, n, act);
-                    for (int blk = 0; blk < 8; ++blk) {
+                    const bool full = p0 + TR <= a.P;
+                    float *orow = a.out + p0 * a.N + n;
+                    const long long ostep = a.N;
+                    auto process = [&](auto fullc, int blk, const uint32_t (&r)[16]) {
+                        constexpr bool kFull = decltype(fullc)::value;
+                        if (!act) return;
                         const long long pb = p0 + blk * 16;
-                        if (pb >= a.P) break;
-                        float v[16];
-                        tc_ld16(tbase + blk * 16, v);
-                        if (act) {
-                            float *op = a.out + pb * a.N + n;
+                        [[maybe_unused]] uint32_t m[16];
+                        if constexpr (kMaskStash) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                if (pb + i < a.P) {
-                                    float x = v[i], qq;
-                                    Epi::apply(a, par, x, qq, 0.f);
-                                    if (!(dbg & 32)) op[(long long)i * a.N] = x;
-                                    if (Epi::kStats) { fs += x; fq += qq; }
-                                }
-                            }
+                            for (int i = 0; i < 16; ++i)
+                                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(m[i]) : "r"(ms + (uint32_t)((blk * 16 + i) * a.N)));
                         }
-                    }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            if (kFull || pb + i < a.P) {
+                                float x = __uint_as_float(r[i]), qq = 0.f;
+                                if constexpr (kMaskStash) x = m[i] ? x + bias : 0.f;
+                                else Epi::apply(a, par, x, qq, 0.f);
+                                if (!(dbg & 32)) *orow = x;
+                                if (Epi::kStats) { fs += x; fq += qq; }
+                            }
+                            orow += ostep;
+                        }
+                    };
+                    auto drain = [&](auto fullc) {
+                        uint32_t ra[16], rb[16];
+                        tc_ld16_async(tbase, ra);
+#pragma unroll
+                        for (int blk = 0; blk < TR / 16; blk += 2) {
+                            tc_wait_ld16(ra);
+                            tc_ld16_async(tbase + (blk + 1) * 16, rb);
+                            process(fullc, blk, ra);
+                            tc_wait_ld16(rb);
+                            if (blk + 2 < TR / 16) tc_ld16_async(tbase + (blk + 2) * 16, ra);
+                            process(fullc, blk + 1, rb);
+                        }
+                    };
+                    if (full) drain(std::true_type{});
+                    else drain(std::false_type{});
                 }
             }
+            if (profiling) { prof[4] += clock64() - tp; prof[5] += 1; }
+            if (kRouted) preload(lt + 2);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_accempty[h]));
             acc_s += (double)fs;
             acc_q += (double)fq;
         }
+        if (profiling && blockIdx.x == 0 && warp == kTW && lane == 0)
+            for (int i = 0; i < 6; ++i) reinterpret_cast<long long *>(a.gmin)[i] = prof[i];
         if (Epi::kStats && act && my_tiles > h) {
             atomicAdd(a.stats + n, acc_s);
             if (!kMaskStash) atomicAdd(a.stats + a.N + n, acc_q);
@@ -432,7 +564,8 @@ __global__ void __launch_bounds__(kThreads2, 1) rowgemm_ws2_kernel(const PclRowG
         const uint32_t wh0 = tmem + kWCol, wl0 = tmem + kWCol + (uint32_t)Kd;
         for (int lt = 0; lt < my_tiles; ++lt) {
             const int buf = lt & 1;
-            if (lt >= 2) mbar_wait_spin(smem_u32(&s_accempty[buf]), (uint32_t)(((lt >> 1) - 1) & 1));
+            if (kRouted) mbar_wait_spin(smem_u32(&s_accempty[buf]), (uint32_t)((lt >> 1) & 1));   // drained AND pre-loaded
+            else if (lt >= 2) mbar_wait_spin(smem_u32(&s_accempty[buf]), (uint32_t)(((lt >> 1) - 1) & 1));
             tc_fence_after();
             const uint32_t d = tmem + (uint32_t)(buf * TR);
             for (int kc = 0; kc < nk; ++kc, ++c) {
@@ -460,7 +593,7 @@ __global__ void __launch_bounds__(kThreads2, 1) rowgemm_ws2_kernel(const PclRowG
                         if (dbg & 1) break;
                         const uint64_t adv = (uint64_t)(ks * 2);
                         const uint32_t col = kk + (uint32_t)(ks * 8);   // one TMEM column per TF32 element of the K step
-                        tc_mma_tf32_ts(d, wh0 + col, dXlo + adv, IDESC, (kc > 0 || ks > 0) ? 1u : 0u);
+                        tc_mma_tf32_ts(d, wh0 + col, dXlo + adv, IDESC, (kRouted || kc > 0 || ks > 0) ? 1u : 0u);
                         tc_mma_tf32_ts(d, wl0 + col, dXhi + adv, IDESC, 1u);
                         tc_mma_tf32_ts(d, wh0 + col, dXhi + adv, IDESC, 1u);
                     }
@@ -488,9 +621,23 @@ static int pick_stages(int N, bool onehot, bool mask) {
     return 0;
 }
 
+// PCL_EPI_BWD_Y_MASK_ROUTED: W3 (C3 x N fp32) goes to shared memory when at least 4 ring stages still fit beside it
+// and the mask stash; otherwise the epilogue warps read its rows through L2 and the ring keeps up to 6 stages.
+static void routed_plan(int N, int C3, int &S, bool &w3_smem) {
+    const size_t w3 = (size_t)C3 * N * 4;
+    for (S = 6; S >= 4; --S)
+        if (smem_need(S, N, false, true) + w3 + 2 * kEntBytes <= (size_t)kSmemMax2) { w3_smem = true; return; }
+    w3_smem = false;
+    for (S = 6; S >= 3; --S)
+        if (smem_need(S, N, false, true) + 2 * kEntBytes <= (size_t)kSmemMax2) return;
+    S = 0;
+}
+
 template <class Pro, class Epi, int S, int LAG = kLagDefault>
 static int launch2(const PclRowGemm &a, cudaStream_t st) {
-    const size_t smem = smem_need(S, a.N, Pro::kOneHot, EpiTraits<Epi>::kMask);
+    const size_t smem = smem_need(S, a.N, Pro::kOneHot, EpiTraits<Epi>::kMask) +
+                        (EpiTraits<Epi>::kRouted && EpiTraits<Epi>::kW3Smem ? (size_t)a.C3 * a.N * 4 : 0) +
+                        (EpiTraits<Epi>::kRouted ? 2 * (size_t)kEntBytes : 0);
     auto kern = rowgemm_ws2_kernel<Pro, Epi, S, LAG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
@@ -524,7 +671,8 @@ bool rowgemm_ws2_supported(const PclRowGemm &a, int pro, int epi) {
                        (pro == PCL_PRO_GATHER_BN_ACT && epi == PCL_EPI_STORE_STATS) ||
                        (pro == PCL_PRO_GATHER_BN_ACT && epi == PCL_EPI_MAXMIN_STATS) ||
                        (pro == PCL_PRO_BN_BWD && epi == PCL_EPI_STORE) ||
-                       (pro == PCL_PRO_G3_A2 && epi == PCL_EPI_BWD_Y_MASK);
+                       (pro == PCL_PRO_G3_A2 && epi == PCL_EPI_BWD_Y_MASK) ||
+                       (pro == PCL_PRO_BN_ACT && epi == PCL_EPI_BWD_Y_MASK_ROUTED);
     if (!combo || a.N > ws2::MMA_M || a.N % 32 != 0 || a.K % ws2::KC != 0 || a.P < 1) return false;
     // the last-layer backward works here (parity tests pass with knob 512) but is SLOWER than generation 3 (1.10 vs
     // 0.84 ms at P = 2M): with the W3^T chunk staged next to the one-hot tile only 3 stages fit, i.e. one chunk of
@@ -541,6 +689,16 @@ bool rowgemm_ws2_supported(const PclRowGemm &a, int pro, int epi) {
         if (!(a.ns == 16 || a.ns == 32 || a.ns == 64 || a.ns == 128)) return false;
         if (a.P % a.ns != 0 || a.reserved < 0) return false;
     }
+    if (epi == PCL_EPI_BWD_Y_MASK_ROUTED) {
+        // whole groups inside a 128-row tile, 32-entry batches inside one group, the mask is the sign of operand (p, n)
+        if (a.K != a.N || a.C3 % 32 != 0 || a.C3 < 32 || a.reserved < 0 || a.reserved > 7 || a.P % a.ns != 0) return false;
+        if (!a.selpos || !a.x1 || a.slope != 0.f || a.eslope != 0.f) return false;
+        if ((long long)(ws2::TR >> a.reserved) * a.C3 > ws2::kEntMax) return false;   // a tile's entry list fits its buffer
+        int S;
+        bool w3s;
+        ws2::routed_plan(a.N, a.C3, S, w3s);
+        return S >= 3;
+    }
     return ws2::pick_stages(a.N, pro == PCL_PRO_G3_A2, epi == PCL_EPI_BWD_Y_MASK) >= 3;
 }
 
@@ -548,6 +706,24 @@ int rowgemm_ws2_dispatch(const PclRowGemm &a, int pro, int epi, cudaStream_t st)
     using namespace ws2;
     if (pro == PCL_PRO_BN_ACT && epi == PCL_EPI_MAXMIN_STATS && ((a.c0 >> 16) & 4096)) return launch2<WProBnAct, WEpiMaxMinStats, 6, 3>(a, st);
     if (pro == PCL_PRO_BN_ACT && epi == PCL_EPI_MAXMIN_STATS && ((a.c0 >> 16) & 8192)) return launch2<WProBnAct, WEpiMaxMinStats, 6, 4>(a, st);
+    if (pro == PCL_PRO_BN_ACT && epi == PCL_EPI_BWD_Y_MASK_ROUTED) {
+        int S;
+        bool w3s;
+        routed_plan(a.N, a.C3, S, w3s);
+        if (w3s) switch (S) {
+            case 6: return launch2<WProBnAct, WEpiBwdYMaskRouted, 6>(a, st);
+            case 5: return launch2<WProBnAct, WEpiBwdYMaskRouted, 5>(a, st);
+            case 4: return launch2<WProBnAct, WEpiBwdYMaskRouted, 4>(a, st);
+        }
+        else switch (S) {
+            case 6: return launch2<WProBnAct, WEpiBwdYMaskRoutedG, 6>(a, st);
+            case 5: return launch2<WProBnAct, WEpiBwdYMaskRoutedG, 5>(a, st);
+            case 4: return launch2<WProBnAct, WEpiBwdYMaskRoutedG, 4>(a, st);
+            case 3: return launch2<WProBnAct, WEpiBwdYMaskRoutedG, 3>(a, st);
+        }
+        set_error("pcl_rowgemm(ws2): no ring fits the routed last-layer backward");
+        return PCL_ERR_UNSUPPORTED;
+    }
 #define PCL_WS2(P_, E_, PRO_, EPI_) \
     if (pro == P_ && epi == E_) return launch2_any<PRO_, EPI_>(a, st)
     PCL_WS2(PCL_PRO_BN_ACT, PCL_EPI_MAXMIN_STATS, WProBnAct, WEpiMaxMinStats);

@@ -151,6 +151,70 @@ __global__ void __launch_bounds__(128) sa_bwd_sums1_kernel(const float *__restri
     }
 }
 
+
+// Routed max-pool gradient of one group, ordered by row (pcl_routed_sort): entry (group g, channel c3) lands on row
+// selpos[g, c3] of the group.  Output: int2 pairs (row inside the row GEMM's 128-row tile << 24 | byte offset of row c3
+// of the (C3, N) fp32 matrix W3, value bits) — the form the consuming kernel uses without further arithmetic.  The last-layer-backward row GEMM (PCL_EPI_BWD_Y_MASK_ROUTED) walks a tile's entries
+// in row order and sums each row's contributions before ONE write into the accumulator, so it needs them sorted by
+// row; ties keep channel order (deterministic sums).  One warp per group: counting sort over the ns rows —
+// histogram (shared-memory atomics: counts only), warp scan, then a stable rank per 32-channel block from
+// __match_any_sync + a per-row running offset the block's first lane of each row advances.
+constexpr int kSortWarps = 8;
+__global__ void __launch_bounds__(kSortWarps * 32) routed_sort_kernel(const int32_t *__restrict__ selpos,
+                                                                      const float *__restrict__ g3s, long long G, int C3,
+                                                                      int ns, int N, int2 *__restrict__ ent) {
+    __shared__ int s_start[kSortWarps][256];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long g = (long long)blockIdx.x * kSortWarps + w;
+    if (g >= G) return;
+    int *st = s_start[w];
+    int sh = 0;
+    while ((1 << sh) < ns) ++sh;
+    for (int r = lane; r < ns; r += 32) st[r] = 0;
+    __syncwarp();
+    const int32_t *sp = selpos + g * C3;
+    for (int c = lane; c < C3; c += 32) atomicAdd(&st[sp[c]], 1);
+    __syncwarp();
+    // exclusive scan of the ns <= 256 counts: lane owns rows [8*lane, 8*lane + 8)
+    int cnt[8], tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int r = lane * 8 + j;
+        cnt[j] = r < ns ? st[r] : 0;
+        tot += cnt[j];
+    }
+    int pre = tot;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += t;
+    }
+    pre -= tot;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int r = lane * 8 + j;
+        if (r < ns) st[r] = pre;
+        pre += cnt[j];
+    }
+    __syncwarp();
+    for (int c0 = 0; c0 < C3; c0 += 32) {
+        const int c = c0 + lane;
+        const bool ok = c < C3;
+        const int row = ok ? sp[c] : -1 - lane;                      // idle lanes: distinct keys nobody matches
+        const unsigned m = __match_any_sync(0xffffffffu, row);
+        const int before = __popc(m & ((1u << lane) - 1u));
+        int pos = 0;
+        if (ok) pos = st[row] + before;
+        __syncwarp();
+        if (ok && before == 0) st[row] += __popc(m);
+        __syncwarp();
+        if (ok) {   // row inside the 128-row tile of the row GEMM | byte offset of row c of W3 (C3, N) fp32; the value
+            const int row_t = (int)(((g << sh) + row) & 127);
+            ent[g * C3 + pos] = make_int2((row_t << 24) | (c * N * 4), __float_as_int(g3s[g * C3 + c]));
+        }
+    }
+}
+
 }  // namespace pcl
 
 using namespace pcl;
@@ -189,4 +253,16 @@ extern "C" int pcl_sa_bwd_sums1(const float *W2, const float *dwm, const float *
     sa_bwd_sums1_kernel<<<C1, 128, 0, (cudaStream_t)stream>>>(W2, dwm, sc1, sh1, mu1, rs1, 1.0 / (double)P, C2, C1, sums1, m1,
                                                             m2);
     return check_launch("pcl_sa_bwd_sums1");
+}
+
+extern "C" int pcl_routed_sort(const int32_t *selpos, const float *g3s, long long G, int C3, int ns, int N, int32_t *ent,
+                               void *stream) {
+    PCL_REQUIRE(selpos && g3s && ent, "pcl_routed_sort: null pointer");
+    PCL_REQUIRE(G >= 0 && C3 >= 1 && N >= 1 && (long long)C3 * N * 4 <= (1 << 24) && ns >= 1 && ns <= 128 &&
+                    (ns & (ns - 1)) == 0,
+                "pcl_routed_sort: bad shape (ns = 2^j <= 128, C3*N*4 <= 2^24)");
+    if (G == 0) return PCL_OK;
+    routed_sort_kernel<<<(unsigned)((G + kSortWarps - 1) / kSortWarps), kSortWarps * 32, 0, (cudaStream_t)stream>>>(
+        selpos, g3s, G, C3, ns, N, reinterpret_cast<int2 *>(ent));
+    return check_launch("pcl_routed_sort");
 }

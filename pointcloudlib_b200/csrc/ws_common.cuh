@@ -76,6 +76,24 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// tcgen05.ld without the wait (the registers are valid only after tc_wait_ld16 on the same array)
+__device__ __forceinline__ void tc_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+// the "+r" operands tie every later use of the array to this wait
+__device__ __forceinline__ void tc_wait_ld16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ void cp_async16_zfill(uint32_t sdst, const void *gsrc, bool valid) {
     const int n = valid ? 16 : 0;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst), "l"(gsrc), "r"(n));
@@ -264,8 +282,14 @@ struct WEpiBwdYMask {
     using Par = int;
     static __device__ __forceinline__ Par params(const PclRowGemm &, int, bool) { return 0; }
 };
-template <class Epi> struct EpiTraits { static constexpr bool kMask = false; };
-template <> struct EpiTraits<WEpiBwdYMask> { static constexpr bool kMask = true; };
+// PCL_EPI_BWD_Y_MASK_ROUTED (rowgemm_ws2.cu only): WEpiBwdYMask with the routed term pre-loaded into the tensor-memory
+// accumulator by the epilogue warps (sorted entry lists, pcl_routed_sort) instead of a one-hot K block.
+struct WEpiBwdYMaskRouted : WEpiBwdYMask {};    // W3 in shared memory
+struct WEpiBwdYMaskRoutedG : WEpiBwdYMask {};   // W3 rows through L2 (too large to sit beside the ring)
+template <class Epi> struct EpiTraits { static constexpr bool kMask = false, kRouted = false, kW3Smem = false; };
+template <> struct EpiTraits<WEpiBwdYMask> { static constexpr bool kMask = true, kRouted = false, kW3Smem = false; };
+template <> struct EpiTraits<WEpiBwdYMaskRouted> { static constexpr bool kMask = true, kRouted = true, kW3Smem = true; };
+template <> struct EpiTraits<WEpiBwdYMaskRoutedG> { static constexpr bool kMask = true, kRouted = true, kW3Smem = false; };
 
 }  // namespace ws
 }  // namespace pcl

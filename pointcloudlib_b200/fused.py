@@ -24,7 +24,8 @@ from . import _lib
 from ._lib import lib, ptr, stream
 
 PRO_PLAIN2, PRO_BN_ACT, PRO_GATHER_BN_ACT, PRO_BN_BWD, PRO_G3_A2, PRO_BN_ACT_ONES, PRO_GATHER_BN_ACT_MASK = range(7)
-EPI_STORE, EPI_STORE_STATS, EPI_MAXMIN_STATS, EPI_BWD_Y, EPI_BWD_GATHER, EPI_BWD_Y_ROUTED, EPI_BWD_Y_MASK = range(7)
+(EPI_STORE, EPI_STORE_STATS, EPI_MAXMIN_STATS, EPI_BWD_Y, EPI_BWD_GATHER, EPI_BWD_Y_ROUTED, EPI_BWD_Y_MASK,
+ EPI_BWD_Y_MASK_ROUTED) = range(8)
 
 _PTR_FIELDS = ("W", "x0", "x1", "U", "V", "scale", "shift", "mean", "rstd", "bscale", "m1", "m2",
                "g3s", "src", "selpos", "out", "gmax", "gmin", "amax", "amin", "stats", "ebias",
@@ -73,6 +74,7 @@ def _bind():
         "pcl_sa_bwd_prepare": [P, P, P, P, P, L, I, I, P, P, P, P, P],
         "pcl_sa_bwd_finish": [P, P, P, P, P, P, P, I, P, P, P, P, P, P, L, I, I, I, P, P, P, P, P],
         "pcl_sa_bwd_sums1": [P, P, P, P, P, P, L, I, I, P, P, P, P],
+        "pcl_routed_sort": [P, P, L, I, I, I, P, P],
     }
     for name, argtypes in sigs.items():
         fn = getattr(l, name)
@@ -85,7 +87,7 @@ SIGNATURE_NAMES = ("pcl_rowgemm", "pcl_wgrad", "pcl_gather_stats", "pcl_bn_param
                    "pcl_maxpool_finalize", "pcl_maxpool_backward", "pcl_sel_outer",
                    "pcl_gather_bn_backward", "pcl_gather_maxmin", "pcl_gather_bn_backward_routed",
                    "pcl_gather_bn_backward_masked", "pcl_bn_act_forward", "pcl_bn_act_backward", "pcl_bn_bwd_apply",
-                   "pcl_sa_bwd_prepare", "pcl_sa_bwd_finish", "pcl_sa_bwd_sums1")
+                   "pcl_sa_bwd_prepare", "pcl_sa_bwd_finish", "pcl_sa_bwd_sums1", "pcl_routed_sort")
 
 
 def _args(**kw):
@@ -94,7 +96,10 @@ def _args(**kw):
     keep = []
     for k, v in kw.items():
         if k in _PTR_FIELDS:
-            if v is not None:
+            if isinstance(v, tuple):                      # (tensor, element offset): a column block of a packed weight
+                keep.append(v[0])
+                setattr(a, k, ptr(v[0]) + v[1] * v[0].element_size())
+            elif v is not None:
                 keep.append(v)
                 setattr(a, k, ptr(v))
         else:
@@ -127,6 +132,11 @@ def pack_weight(w: torch.Tensor, sign: float = 1.0) -> torch.Tensor:
 DEBUG = None   # tests: a dict that FusedSAFn.forward fills with its routing state (selpos, y2, U, V, src, BN vectors)
 DEFER_MASK1 = 1  # 0: layer-2 backward row GEMM on the round-1 kernel (gathered epilogue operand) for A/B runs
 MASK_STASH = 1   # 0: last-layer backward row GEMM on the round-1 kernel (re-reads y2 in its epilogue) for A/B runs
+# last-layer backward, routed term: 1 = entry lists summed into the tensor-memory accumulator where a tile carries at most
+# 4 entries per output channel (measured faster there, profiles/r02/sa_b3_ab_r02.txt), 2 = wherever supported,
+# 0 = always the one-hot K block (PCL_PRO_G3_A2)
+ROUTED_PRELOAD = int(__import__("os").environ.get("PCL_ROUTED_PRELOAD", "1"))
+PROF_BUF = None   # profiling (knob 16384 of rowgemm_ws2.cu): a 64-byte CUDA tensor that receives phase cycle counters
 WS_DBG = 0   # profiling knobs of rowgemm_ws.cu (scratch/ws_branch_knobs.py); 0 in production
 WS_FETCH_EPI = 0   # 1: also route the BWD_Y / BWD_GATHER epilogues to rowgemm_ws.cu (slower today)
 
@@ -287,9 +297,20 @@ class FusedSAFn(torch.autograd.Function):
             # -- da2 -> dyhat2 on the warp-specialised kernel: the routed gradient enters as a one-hot K block, the
             # ReLU mask comes from the operand tile the kernel stages itself; its epilogue reads nothing of size
             # (P, C2) and accumulates sum(dyhat2) only
-            rowgemm(PRO_G3_A2, EPI_BWD_Y_MASK, "sa_b3", W=Wb, g3s=g3s, selpos=selpos, C3=C3, ns=ns, x0=y2,
-                    scale=sc2, shift=sh2, slope=0.0, P=P, K=C3 + C2, N=C2, ldw=ld, out=dyh2,
-                    stats=sums2, ebias=constf, eslope=0.0)
+            if (ROUTED_PRELOAD and C3 % 32 == 0 and ns <= 128 and (128 // ns) * C3 <= 512
+                    and (ROUTED_PRELOAD > 1 or (128 // ns) * C3 <= 4 * C2)):
+                # the routed term as sorted entry lists that the kernel's epilogue warps sum into the tensor-memory
+                # accumulator before the tile's MMAs (-a2.Q, K = C2) run: no one-hot K block
+                ent = torch.empty((G, C3, 2), dtype=torch.int32, device=dev)
+                _lib.call("pcl_routed_sort", ptr(selpos), ptr(g3s), G, C3, ns, C2, ptr(ent), stream(g3s),
+                          key=("sa_routed_sort", G, C3))
+                rowgemm(PRO_BN_ACT, EPI_BWD_Y_MASK_ROUTED, "sa_b3", x0=y2, W=(Wb, C3), x1=W3f, selpos=ent,
+                        C3=C3, ns=ns, scale=sc2, shift=sh2, slope=0.0, P=P, K=C2, N=C2, ldw=ld, out=dyh2,
+                        stats=sums2, ebias=constf, eslope=0.0, gmin=PROF_BUF)
+            else:
+                rowgemm(PRO_G3_A2, EPI_BWD_Y_MASK, "sa_b3", W=Wb, g3s=g3s, selpos=selpos, C3=C3, ns=ns, x0=y2,
+                        scale=sc2, shift=sh2, slope=0.0, P=P, K=C3 + C2, N=C2, ldw=ld, out=dyh2,
+                        stats=sums2, ebias=constf, eslope=0.0)
             # -- dW3, and sum_p dyhat2*xhat2 without a pass: a2 = mask*(gamma2*xhat2 + beta2)  =>
             #   sum_p dA2*mask*xhat2 = (sum_p dA2*a2 - beta2 * sum_p dyhat2) / gamma2,   dA2 = -a2.Q + R.W3 + const
             #   sum_p dA2[p,n]*a2[p,n] = -sum_k Q[k,n] M2[k,n] + sum_c3 W3[c3,n] T[c3,n] + const[n] S2[n]

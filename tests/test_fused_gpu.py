@@ -344,3 +344,70 @@ def test_row_mlp_matches_reference_sequence(P, cin, chans, slope, bias):
         np.testing.assert_allclose(bn.running_mean.cpu().numpy(), rbn.running_mean.float().numpy(), rtol=1e-3, atol=1e-4)
         np.testing.assert_allclose(bn.running_var.cpu().numpy(), rbn.running_var.float().numpy(), rtol=2e-3, atol=1e-4)
     assert _rel(xd.grad, x64.grad) <= 5e-3
+
+
+def test_routed_sort_orders_each_group_by_row_keeping_channel_order():
+    """pcl_routed_sort: (G, C3) pairs (row in the 128-row tile << 24 | c3*N*4, g3s bits) ordered by row, ties in
+    channel order."""
+    import ctypes
+    from pointcloudlib_b200 import _lib
+    fused._bind()
+    gen = torch.Generator().manual_seed(3)
+    for G, C3, ns, N in [(37, 128, 128, 96), (64, 64, 16, 32), (5, 256, 64, 128), (9, 32, 1, 64)]:
+        selpos = torch.randint(0, ns, (G, C3), generator=gen, dtype=torch.int32)
+        g3s = torch.randn(G, C3, generator=gen)
+        sp, gv = selpos.to(DEV), g3s.to(DEV)
+        ent = torch.empty((G, C3, 2), dtype=torch.int32, device=DEV)
+        _lib.call("pcl_routed_sort", _lib.ptr(sp), _lib.ptr(gv), G, C3, ns, N, _lib.ptr(ent), _lib.stream(gv))
+        key = selpos.long() * 65536 + torch.arange(C3).view(1, C3)
+        skey, order = torch.sort(key, dim=1, stable=True)
+        row_t = (torch.arange(G).view(G, 1) * ns + skey // 65536) % 128
+        want = row_t * 2 ** 24 + (skey % 65536) * N * 4
+        got = ent.cpu()
+        assert torch.equal(got[..., 0].long() & 0xFFFFFFFF, want)
+        assert torch.equal(got[..., 1].contiguous().view(torch.float32), torch.gather(g3s, 1, order))
+
+
+@pytest.mark.parametrize("B,N,S,r,ns,C,chans", [
+    (2, 1024, 128, 0.4, 128, 3, (64, 96, 128)),      # W3 in shared memory, one group per tile
+    (4, 1024, 128, 0.2, 32, 3, (64, 64, 128)),       # four groups per tile
+    (3, 300, 50, 0.1, 16, 5, (32, 32, 64)),          # ragged: P = 2400 rows, last tile holds 6 of 8 groups
+    (4, 512, 64, 0.4, 64, 320, (128, 128, 256)),     # W3 (128 KB) stays in L2
+])
+def test_last_layer_backward_routed_preload_equals_one_hot_block(B, N, S, r, ns, C, chans):
+    """The two forms of the routed max-pool term in the last-layer backward — entry lists summed into the
+    tensor-memory accumulator by the epilogue warps (PCL_EPI_BWD_Y_MASK_ROUTED, fp32 FMAs) and the one-hot K block
+    contracted by the tensor core (PCL_PRO_G3_A2, 3xTF32) — give the same gradients."""
+    xyz, nrm, _ = modelnet_batch(B, N, seed=7)
+    g = torch.Generator().manual_seed(11)
+    feat = nrm if C == 3 else torch.randn(B, N, C, generator=g)
+    seq = _mlp(chans, 3 + C).train()
+    xd = xyz.to(DEV)
+    new_xyz = F.gather_xyz(xd, F.furthest_point_sample(xd, S))
+    grouper = BallQueryGrouper(r, ns, True)
+    grads, old = [], fused.ROUTED_PRELOAD
+    gout = None
+    try:
+        for flag in (2, 0):
+            fused.ROUTED_PRELOAD = flag
+            seq_d = copy.deepcopy(seq).to(DEV)
+            fd = feat.to(DEV).requires_grad_(True)
+            with _lib_timer() as kt:
+                out = sa.sa_branch(grouper, seq_d, new_xyz, xd, fd)
+                if gout is None:
+                    gout = torch.randn(out.shape, generator=g).to(DEV)
+                out.backward(gout)
+                torch.cuda.synchronize()
+            tags = {k[1][0]: (int(k[1][1]), int(k[1][2])) for k in kt.summary() if k[0] == "pcl_rowgemm" and k[1]}
+            assert tags["sa_b3"] == ((fused.PRO_BN_ACT, fused.EPI_BWD_Y_MASK_ROUTED) if flag
+                                     else (fused.PRO_G3_A2, fused.EPI_BWD_Y_MASK))
+            grads.append([p.grad.clone() for p in seq_d.parameters()] + [fd.grad.clone()])
+    finally:
+        fused.ROUTED_PRELOAD = old
+    for a, b in zip(*grads):
+        assert _rel(a, b) <= 2e-4, f"rel-L2 {_rel(a, b):.3e}"
+
+
+def _lib_timer():
+    from pointcloudlib_b200 import _lib
+    return _lib.KernelTimer()

@@ -280,7 +280,11 @@ __global__ void __launch_bounds__(kThreads2, 1) rowgemm_ws2_kernel(const PclRowG
             const int s = c % S;
             const uint32_t st = sbase + s * stage_bytes;
             const int k0 = c_kc * KC;
-            if (kMaskStash && c_kc == 0 && c_lt >= 2)   // the epilogue has drained this tile's stash buffer (tile c_lt - 2)
+            // the epilogue has drained this tile's stash buffer (tile c_lt - 2).  kRouted: phase 0 of the barrier is the
+            // pre-load of the accumulator's first tile and EVERY tile waits for its phase in order — a parity wait only
+            // tells neighbouring phases apart (a K = 32 transform that skipped the wait at tiles 0 / 1 reached tile 2
+            // while phase 0 was still open, passed, and overwrote tile 0's mask)
+            if (kMaskStash && c_kc == 0 && (kRouted || c_lt >= 2))
                 mbar_wait(smem_u32(&s_accempty[c_lt & 1]), (uint32_t)(((c_lt >> 1) - (kRouted ? 0 : 1)) & 1));
             if (Pro::kOneHot && k0 < kbase) {
                 // routed one-hot chunk: per (group, channel) ONE row carries g3s; everything else is 0.

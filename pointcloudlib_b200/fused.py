@@ -347,6 +347,8 @@ class FusedSAFn(torch.autograd.Function):
             m1_2 = (sums2[0] / P).float().contiguous()
             m2_2 = (sums2[1] / P).float().contiguous()
 
+        if DEBUG is not None:
+            DEBUG.update(dyh2=dyh2, sums2=sums2)
         # ---- layer 2 backward -----------------------------------------------------------------
         dz2kw = dict(x0=dyh2, x1=y2, mean=mu2, rstd=rs2, bscale=sc2, m1=m1_2, m2=m2_2, K=C2)
         a1kw = dict(U=U, V=V, src=src, ns=ns, vsign=-1.0, scale=sc1, shift=sh1, slope=slope, K=C1)

@@ -411,3 +411,37 @@ def test_last_layer_backward_routed_preload_equals_one_hot_block(B, N, S, r, ns,
 def _lib_timer():
     from pointcloudlib_b200 import _lib
     return _lib.KernelTimer()
+
+
+@pytest.mark.parametrize("preload", [0, 2])
+@pytest.mark.parametrize("r,ns,chans", [(0.1, 16, (32, 32, 64)), (0.2, 32, (64, 64, 128))])
+def test_small_radius_branches_at_the_bench_shape(r, ns, chans, preload):
+    """BASELINE config 2, SA1 radii 0.1 / 0.2 at full size (B=32, N=4096, S=512: P = 262,144 / 524,288 rows, every
+    persistent CTA walks several row tiles) against the float64 reference sequence, with both forms of the routed
+    term in the last-layer backward.  Small balls pad their groups with copies of the first neighbour, so many rows
+    of a group are identical and the max has exact ties."""
+    B, N, S, C = 32, 4096, 512, 3
+    xyz, nrm, _ = modelnet_batch(B, N, seed=1)
+    seq = _mlp(chans, 3 + C).train()
+    ref_seq = copy.deepcopy(seq).double()
+    fidx = oracle.fps(xyz.numpy(), S)
+    new_xyz = torch.from_numpy(oracle.index_points(xyz.numpy(), fidx))
+    ridx, _ = oracle.ball_query(new_xyz.numpy(), xyz.numpy(), float(str(r)), ns)
+    grouped = torch.from_numpy(oracle.group(new_xyz.numpy(), xyz.numpy(), nrm.numpy(), ridx)).double()
+    ref = _ref64(ref_seq, grouped)
+    gen = torch.Generator().manual_seed(5)
+    gout = torch.randn(ref.shape, generator=gen)
+    ref.backward(gout.double())
+    seq_d = copy.deepcopy(seq).to(DEV)
+    old = fused.ROUTED_PRELOAD
+    fused.ROUTED_PRELOAD = preload
+    try:
+        out = sa.sa_branch(BallQueryGrouper(r, ns, True), seq_d, new_xyz.to(DEV), xyz.to(DEV), nrm.to(DEV))
+        out.backward(gout.to(DEV))
+        torch.cuda.synchronize()
+    finally:
+        fused.ROUTED_PRELOAD = old
+    scale = ref.abs().max().item()
+    assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= 1e-3 * scale
+    worst = {n: _rel(p.grad, q.grad) for (n, p), (_, q) in zip(seq_d.named_parameters(), ref_seq.named_parameters())}
+    assert max(worst.values()) <= 2e-3, worst

@@ -558,6 +558,10 @@ def run_product_arm(args, wl: Workload):
         if fl_issued:
             k["tf32_issued_TFLOPs"] = fl_issued / (mean_ms * 1e-3) / 1e12   # the 3xTF32 split issues 3x the algorithmic flops
             k["tensor_frac"] = k["tf32_issued_TFLOPs"] / tf32_peak
+        if fl and not fl_issued:
+            # CUDA-core kernels (kNN distances, routed outer product): logical fp32 flops against the FP32 FFMA rate
+            # measured in this run — the ceiling that actually bounds the kNN kernel, whose distances never touch HBM
+            k["fp32_frac"] = k["TFLOPs"] / cpeaks["fp32_tflops"]
         if by:
             k["bound"] = "tensor" if k.get("tensor_frac", 0.0) > k["hbm_frac"] else "hbm"
         tr = traffic_db.get("|".join([name] + (k["key"] or [])))
@@ -573,6 +577,7 @@ def run_product_arm(args, wl: Workload):
                 "frac": top.get("tensor_frac") if tensor_bound else top.get("hbm_frac"),
                 "traffic": traffic_db.get("|".join([str(top["call"])] + (top["key"] or []))),
                 "peak_source": peak_src, "hbm_frac": top.get("hbm_frac"), "tensor_frac": top.get("tensor_frac"),
+                "fp32_frac": top.get("fp32_frac"),
                 "compute_peaks": cpeaks,
                 "algorithmic_bytes_per_launch": int(top.get("algorithmic_MB", 0) * 1e6),
                 "mean_launch_us": top["mean_us"], "share_of_step": top["share_of_step"],
@@ -583,7 +588,9 @@ def run_product_arm(args, wl: Workload):
                         "region replays one CUDA graph per step, which events cannot subdivide), the radius branches "
                         "serialised on one stream for this pass only; every kernel is "
                         "quoted against the measured HBM copy peak and, for the tcgen05 3xTF32 GEMMs, the TF32 "
-                        "throughput measured here (issued flops = 3x logical); bound = the nearer ceiling; "
+                        "throughput measured here (issued flops = 3x logical); bound = the nearer of those two ceilings; "
+                        "fp32_frac = logical flops against the measured FP32 FFMA rate for the CUDA-core kernels "
+                        "(the kNN distance kernel is bound there, not by HBM); "
                         "traffic = dram read+write per launch from this round's ncu --set full capture "
                         "(profiles/ncu_traffic_r02.json) or null",
                 "kernels": kernels[:32]}

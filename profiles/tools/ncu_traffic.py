@@ -8,16 +8,18 @@ col = {h: i for i, h in enumerate(hdr)}
 def val(r, name):
     v, u = float(r[col[name]]), units[col[name]]
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
-MAP = [  # (substrings of the kernel name, key in bench.py's table)
-    (("rowgemm_ws_kernel", "WProGatherBnAct", "WEpiStoreStats"), "pcl_rowgemm|sa_l2|2|1|2097152|64|96"),
-    (("rowgemm_ws_kernel", "WProBnAct", "WEpiMaxMinStats"), "pcl_rowgemm|sa_l3|1|2|2097152|96|128"),
+MAP = [  # (substrings of the kernel name, key in bench.py's table); generation 4 (rowgemm_ws2_kernel) serves these shapes
+    (("rowgemm_ws2_kernel", "WProGatherBnAct", "WEpiStoreStats"), "pcl_rowgemm|sa_l2|2|1|2097152|64|96"),
+    (("rowgemm_ws2_kernel", "WProBnAct", "WEpiMaxMinStats"), "pcl_rowgemm|sa_l3|1|2|2097152|96|128"),
+    (("rowgemm_ws2_kernel", "WProBnAct", "WEpiBwdYMaskRouted"), "pcl_rowgemm|sa_b3|1|7|2097152|96|96"),
     (("rowgemm_ws_kernel", "WProG3A2", "WEpiBwdYMask"), "pcl_rowgemm|sa_b3|4|6|2097152|224|96"),
-    (("rowgemm_ws_kernel", "WProBnBwd", "WEpiStore,"), "pcl_rowgemm|sa_b2|3|0|2097152|96|64"),
+    (("rowgemm_ws2_kernel", "WProBnBwd", "WEpiStore"), "pcl_rowgemm|sa_b2|3|0|2097152|96|64"),
     (("wgrad_ws_kernel", "GBnAct, ws::GBnActOnes"), "pcl_wgrad|sa_gram|2097152|96|97"),
     (("wgrad_ws_kernel", "GBnBwd", "GGatherBnActMask"), "pcl_wgrad|sa_dw2|2097152|96|128"),
     (("sel_outer_group_kernel",), "pcl_sel_outer|sa_sel_outer|16384|128|96"),
     (("gather_bn_backward_kernel<1>",), "pcl_gather_bn_backward_masked|sa_b1_scatter|2097152|64"),
     (("gather_stats_kernel",), "pcl_gather_stats|sa_gather_stats|2097152|64"),
+    (("routed_sort_kernel",), "pcl_routed_sort|sa_routed_sort|16384|128"),
 ]
 out, lines = {}, []
 want = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",

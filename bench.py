@@ -343,6 +343,36 @@ def load_ncu_traffic():
         return {}
 
 
+def device_time_us(fn, reps=10, warm=3):
+    """Mean device time of fn() in us.  The reps are captured into ONE CUDA graph and replayed: a 50 us kernel behind
+    ~100 us of Python / ctypes / allocator work per call would otherwise be timed at the host's launch rate (seen: the
+    same ball-query kernels at 51 us on one box and 139 us on another).  Falls back to an eager event pair when fn
+    cannot be captured."""
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        b0.record()
+        g.replay()
+        b1.record()
+    except Exception:
+        torch.cuda.synchronize()
+        b0.record()
+        for _ in range(reps):
+            fn()
+        b1.record()
+    torch.cuda.synchronize()
+    return 1e3 * b0.elapsed_time(b1) / reps
+
+
 def reference_kernels_block(dev, peak):
     """The reference's OWN CUDA kernels (misc/ops.py:124-234, :291-330, :429-552, compiled unmodified into
     oracle/_ref/libref_kernels.so, launched with the reference's configuration: grid = B, block =
@@ -379,7 +409,7 @@ def reference_kernels_block(dev, peak):
     temp = torch.empty(32, 4096, device=dev)
     idx = torch.empty(32, 512, dtype=torch.int32, device=dev)
     t_ref = timeit(lambda: lib.ref_fps(xyz.data_ptr(), 32, 4096, 512, bs, temp.data_ptr(), idx.data_ptr(), st), 2)
-    t_own = timeit(lambda: PF.furthest_point_sample(xyz, 512), 10)
+    t_own = device_time_us(lambda: PF.furthest_point_sample(xyz, 512), 10)
     same = bool(torch.equal(idx, PF.furthest_point_sample(xyz, 512)))
     rows.append({"op": "furthest_point_sample", "shape": "B=32 N=4096 M=512 (C2 SA1)", "reference_us": t_ref,
                  "own_us": t_own, "speedup": t_ref / t_own, "idx_equal": same, "reference_block": bs})
@@ -392,7 +422,7 @@ def reference_kernels_block(dev, peak):
         rcnt = torch.zeros(B, S, dtype=torch.int32, device=dev)
         t_ref = timeit(lambda: lib.ref_ball_query(cen.data_ptr(), pts.data_ptr(), B, N, S, float(r), ns, bs,
                                                   ridx.data_ptr(), rcnt.data_ptr(), st), 2)
-        t_own = timeit(lambda: PF.ball_query(cen, pts, r, ns), 10)
+        t_own = device_time_us(lambda: PF.ball_query(cen, pts, r, ns), 10)
         oidx, ocnt = PF.ball_query(cen, pts, r, ns)
         rows.append({"op": "ball_query", "shape": f"B={B} N={N} S={S} r={r} ns={ns} (C2 {tag})", "reference_us": t_ref,
                      "own_us": t_own, "speedup": t_ref / t_own,
@@ -406,11 +436,12 @@ def reference_kernels_block(dev, peak):
         torch.cuda.synchronize()
         t_ref = timeit(lambda: lib.ref_knn(x.data_ptr(), x.data_ptr(), 32, C, 1024, 1024, 20, tmp.data_ptr(),
                                            kidx.data_ptr()), 3)
-        t_own = timeit(lambda: PF.knn(x, x, 20), 10)
+        t_own = device_time_us(lambda: PF.knn(x, x, 20), 10)
         rows.append({"op": "knn", "shape": f"B=32 C={C} N=1024 k=20 (C3)", "reference_us": t_ref, "own_us": t_own,
                      "speedup": t_ref / t_own, "idx_equal": bool(torch.equal(kidx, PF.knn(x, x, 20)))})
     return {"what": "the reference's own kernels compiled for sm_100a (oracle/_ref) vs libpcl_b200, CUDA events, "
-                    "same inputs; ball_query rows time the QUERY only on both sides", "rows": rows}
+                    "same inputs (own kernels: 10 launches replayed as one CUDA graph, so the host's launch rate does not enter); "
+                    "ball_query rows time the QUERY only on both sides", "rows": rows}
 
 
 # --------------------------------------------------------------------------------------------
@@ -608,16 +639,7 @@ def run_product_arm(args, wl: Workload):
     cen2 = PF.gather_xyz(cen1, PF.furthest_point_sample(cen1, 128))
     feat2 = torch.randn(32, 512, 320, device=dev)
 
-    def timeit(fn, reps=10):
-        for _ in range(3):
-            fn()
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b0.record()
-        for _ in range(reps):
-            fn()
-        b1.record()
-        torch.cuda.synchronize()
-        return 1e3 * b0.elapsed_time(b1) / reps
+    timeit = device_time_us
 
     levels = [(cen1, xyz0, nrm0, (0.1, 0.2, 0.4), (16, 32, 128)), (cen2, cen1, feat2, (0.2, 0.4, 0.8), (32, 64, 128))]
     for cen, pts, feat, radii, nss in levels:

@@ -162,7 +162,10 @@ wgrad_ws_kernel(const PclRowGemm al_, const PclRowGemm ar_, long long P, int M_,
     const int Npad = (N + 15) & ~15;
     const int MB = (M + 31) / 32, NB = (Npad + 31) / 32;
     const uint32_t l_tile = SHARE ? 0u : MB * WG_BLK, r_tile = NB * WG_BLK;
-    const uint32_t stage_bytes = 2 * (l_tile + r_tile);   // [L hi | L lo | R hi | R lo]
+    // [L hi | L lo | R hi | R lo].  Mask variant: the 0/1 block has no lo part, so the lo tile holds the a1 blocks only
+    // and the L_hi x R_lo product is issued over those columns alone (8 KB less per stage, a sixth of the MMA work)
+    const int NBlo = MaskTrait<ProR>::value ? (RW + 31) / 32 : NB;
+    const uint32_t stage_bytes = 2 * l_tile + r_tile + (uint32_t)NBlo * WG_BLK;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
@@ -198,7 +201,7 @@ wgrad_ws_kernel(const PclRowGemm al_, const PclRowGemm ar_, long long P, int M_,
                 const uint32_t o = sbase + s * stage_bytes + (isR ? 2 * l_tile : 0) + mn_off(row, qd);
                 const bool one = isR && ProR::kOnes && qd * 4 == RW;
                 sts4(o, one ? 0x3F800000u : 0u, 0u, 0u, 0u);
-                sts4(o + (isR ? r_tile : l_tile), 0u, 0u, 0u, 0u);
+                if (!isR || qd < 8 * NBlo) sts4(o + (isR ? r_tile : l_tile), 0u, 0u, 0u, 0u);
             }
         }
         fence_proxy_async();
@@ -250,8 +253,9 @@ wgrad_ws_kernel(const PclRowGemm al_, const PclRowGemm ar_, long long P, int M_,
         // issue of chunk k also cp.asyncs (4 bytes, private slot per thread) the indices chunk k + PD will
         // need, so they arrive with a whole pipeline depth of lead time instead of a dependent register load
         static_assert(!ProL::kSrc, "gathered L operands are not implemented");
-        const uint32_t src_base = sbase + S * stage_bytes + kSlackBytes;   // [PD + 1][NPR][256] ints
-        auto src_slot = [&](int k, int i) { return src_base + (uint32_t)((((k % (PD + 1)) * NPR + i) * kTT + tid) * 4); };
+        const uint32_t src_base = sbase + S * stage_bytes + kSlackBytes;   // [PD + 1][live pieces per thread][kTT] ints
+        const int npr_live = (WG_ROWS * liveR + kTT - 1) / kTT;
+        auto src_slot = [&](int k, int i) { return src_base + (uint32_t)((((k % (PD + 1)) * npr_live + i) * kTT + tid) * 4); };
         int i_c = 0;
         auto issue_next = [&]() {
             if (i_c < total) {
@@ -394,6 +398,9 @@ wgrad_ws_kernel(const PclRowGemm al_, const PclRowGemm ar_, long long P, int M_,
         // instruction descriptor: D=F32, A=B=TF32, both MN-major (bits 15,16), N>>3, M=128>>4
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                ((uint32_t)(Npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const int Nlo = MaskTrait<ProR>::value ? NBlo * 32 : Npad;   // columns of the R lo tile
+        const uint32_t idesc_lo = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                  ((uint32_t)(Nlo >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         for (int cc = 0; cc < total; ++cc) {
             const int s = cc % S;
             if (!(dbg & 64)) mbar_wait_spin(smem_u32(&s_full[s]), (uint32_t)((cc / S) & 1));
@@ -408,7 +415,7 @@ wgrad_ws_kernel(const PclRowGemm al_, const PclRowGemm ar_, long long P, int M_,
                 const uint64_t dLhi = SHARE ? dRhi : umma_desc_mn(st + o, WG_BLK, 512);
                 const uint64_t dLlo = SHARE ? dRlo : umma_desc_mn(st + l_tile + o, WG_BLK, 512);
                 tc_mma_tf32(tmem, dLlo, dRhi, idesc, (cc > 0 || kg > 0) ? 1u : 0u);
-                tc_mma_tf32(tmem, dLhi, dRlo, idesc, 1u);
+                tc_mma_tf32(tmem, dLhi, dRlo, idesc_lo, 1u);
                 tc_mma_tf32(tmem, dLhi, dRhi, idesc, 1u);
             }
             if (!(dbg & 256)) tc_commit(smem_u32(&s_free[s]));
@@ -421,24 +428,36 @@ wgrad_ws_kernel(const PclRowGemm al_, const PclRowGemm ar_, long long P, int M_,
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
 }
 
-static void wgrad_ws_geometry(int M, int N, bool share, bool gather, size_t &stage, size_t &slack, int &S) {
+// r_width: channels of the R operand that are loaded (its row stride); mask: [a1 | relu'] right operand (no lo tile for
+// the 0/1 block).  LAG = 1 where it buys a deeper prefetch: PD = S - LAG chunks in flight.
+static void wgrad_ws_geometry(int M, int N, int r_width, bool share, bool gather, bool mask, bool lag1, size_t &stage,
+                              size_t &slack, int &S, int &LAG) {
     const int Npad = (N + 15) & ~15;
     const int MB = share ? 0 : (M + 31) / 32, NB = (Npad + 31) / 32;
-    stage = (size_t)2 * (MB + NB) * WG_BLK;
-    // operand over-read + the gather-index slots (PD + 1 chunks: PD = S - 2, or 2 at S = 3)
+    const int NBlo = mask ? (r_width + 31) / 32 : NB;
+    stage = (size_t)(2 * MB + NB + NBlo) * WG_BLK;
+    const int live_r = (r_width + 3) / 4;
+    const size_t slot = (size_t)((WG_ROWS * live_r + kTT - 1) / kTT) * kTT * 4;   // gather indices of one chunk
+    // operand over-read + the gather-index slots (PD + 1 chunks)
     const size_t total = 232448 - 4096 - 1024 - kSlackBytes;   // static: barriers + parameter tables
-    auto fits = [&](int s_, int pd) { return stage * s_ + (gather ? (size_t)(pd + 1) * kSrcSlot : 0) <= total; };
-    S = fits(6, 4) ? 6 : (fits(4, 2) ? 4 : (fits(3, 2) ? 3 : 0));
-    slack = (size_t)kSlackBytes + (gather ? (size_t)((S == 6 ? 4 : 2) + 1) * kSrcSlot : 0);
+    auto fits = [&](int s_, int pd) { return stage * s_ + (gather ? (size_t)(pd + 1) * slot : 0) <= total; };
+    S = 0;
+    LAG = 2;
+    if (fits(6, lag1 ? 5 : 4)) S = 6, LAG = lag1 ? 1 : 2;
+    else if (fits(4, lag1 ? 3 : 2)) S = 4, LAG = lag1 ? 1 : 2;
+    else if (fits(3, 2)) S = 3, LAG = 1;
+    slack = (size_t)kSlackBytes + (gather ? (size_t)(S - LAG + 1) * slot : 0);
 }
 
 template <bool SHARE, class ProL, class ProR>
 static int launch_wgrad_ws(const PclRowGemm &al, const PclRowGemm &ar, long long P, int M, int N, float *out,
                            int ldo, cudaStream_t st) {
     size_t stage, slack;
-    int S;
+    int S, LAG;
     const bool blocked = M > 128 || N > 160;
-    wgrad_ws_geometry(blocked ? 128 : M, blocked ? 128 : N, SHARE, ProR::kSrc, stage, slack, S);
+    const bool lag1 = ((al.c0 >> 16) & 1024) != 0;   // knob: one more chunk in flight, the refill waits on the MMAs just issued
+    wgrad_ws_geometry(blocked ? 128 : M, blocked ? 128 : N, blocked ? 128 : ar.K, SHARE, ProR::kSrc, MaskTrait<ProR>::value,
+                      lag1, stage, slack, S, LAG);
     if (S == 0) {
         set_error("pcl_wgrad(ws): M=%d N=%d does not fit three stages", M, N);
         return PCL_ERR_UNSUPPORTED;
@@ -460,7 +479,9 @@ static int launch_wgrad_ws(const PclRowGemm &al, const PclRowGemm &ar, long long
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
         if (e == cudaSuccess) kern<<<grid, kWgThreads, smem, st>>>(al, ar, P, M, N, out, ldo); \
     } while (0)
-    if (S == 6) PCL_LAUNCH(6, 2);
+    if (S == 6 && LAG == 1) PCL_LAUNCH(6, 1);
+    else if (S == 6) PCL_LAUNCH(6, 2);
+    else if (S == 4 && LAG == 1) PCL_LAUNCH(4, 1);
     else if (S == 4) PCL_LAUNCH(4, 2);
     else PCL_LAUNCH(3, 1);
 #undef PCL_LAUNCH
@@ -490,16 +511,18 @@ bool wgrad_ws_supported(const PclRowGemm &al, int pl, const PclRowGemm &ar, int 
                        (pl == PCL_PRO_BN_BWD && pr == PCL_PRO_GATHER_BN_ACT_MASK);
     if (!combo || M % 4 != 0 || P < 1) return false;
     if (al.K % 4 != 0 || ar.K % 4 != 0 || al.K < M) return false;
-    if (M > 128 || N > 160) {
+    const bool blocked = M > 128 || N > 160;
+    if (blocked) {
         // blocked mode: the dense-stack pair only (R as wide as its row stride), whole 16-column groups per block
         if (!(pl == PCL_PRO_BN_BWD && pr == PCL_PRO_BN_ACT) || N != ar.K || N % 16 != 0) return false;
         M = 128;
         N = 128;
     }
     size_t stage, slack;
-    int S;
-    ws::wgrad_ws_geometry(M, N, ws::gram_shares(al, pl, ar, pr, M),
-                          pr == PCL_PRO_GATHER_BN_ACT || pr == PCL_PRO_GATHER_BN_ACT_MASK, stage, slack, S);
+    int S, LAG;
+    ws::wgrad_ws_geometry(M, N, blocked ? 128 : ar.K, ws::gram_shares(al, pl, ar, pr, M),
+                          pr == PCL_PRO_GATHER_BN_ACT || pr == PCL_PRO_GATHER_BN_ACT_MASK,
+                          pr == PCL_PRO_GATHER_BN_ACT_MASK, false, stage, slack, S, LAG);
     return S != 0;
 }
 

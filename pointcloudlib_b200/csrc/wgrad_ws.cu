@@ -428,6 +428,382 @@ wgrad_ws_kernel(const PclRowGemm al_, const PclRowGemm ar_, long long P, int M_,
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// wgrad_tl_kernel — the L operand in TENSOR memory (round 2).
+//
+// wgrad_ws_kernel takes BOTH operands of OUT += L^T.R from shared memory, and since both change every 32-row chunk
+// its ring moves ~208 KB per chunk of sa_dw2 (cp.async 32, read-back 32, hi / lo stores 56, tensor-core operand reads
+// 88) — 1625 cycles at 128 B/clk, twice the chunk's HBM time.  Here the 128-lane side never becomes a shared-memory
+// operand: L = BatchNorm-backward(x0, x1) is per-channel affine, so a thread that owns ONE channel (= one TMEM lane)
+// reads its 16 rows of the raw chunk (landed by its own 4-byte cp.asyncs in a compact row-major buffer), applies
+// A*x0 + B*x1 + C with the three constants in registers, splits hi / lo and writes 16 + 16 tensor-memory columns
+// (tcgen05.st); the MMAs take A from TMEM (TS form, `UTCHMMA tmem, gdesc, tmem`) and only the R tile from shared
+// memory.  Per chunk: cp.async 32, L read-back 24, R read-back 8, R stores 24, operand reads 40 = 128 KB.
+//   warps 0-3   L transform: lane quarter q = warp, thread = channel 32q + lane, all 32 rows of the chunk
+//   warps 4-14  R transform: wgrad_ws_kernel's piece scheme over 352 threads (gather, BatchNorm + ReLU, mask block)
+//   warp 15     MMA issuer;  16 warps -> 128 registers per thread (17 would be allocated as 20: 96)
+//   TMEM (512 columns): [0,128) accumulator, [128 + 64 s, +32) L hi and (+32, +64) L lo of ring stage s
+// L must be PCL_PRO_BN_BWD (M <= 128 channels, row stride al.K); R one of the gathered prologues.
+//
+// STATUS: correct (tests/test_fused_gpu.py runs it against the default kernel) and OPT-IN (knob 4096).  It moves 2.5x
+// fewer bytes through shared memory and keeps 3 instead of 2 chunks of HBM rows in flight, yet runs at the SAME speed
+// as wgrad_ws_kernel (716-748 vs 736 us at P = 2M; 845 us with 8 L + 7 R warps) — as did every other variant tried
+// (deeper prefetch, V rows a chunk ahead, smaller stages).  What all of them share is that EVERY transform warp touches
+// EVERY 32-row chunk, so a chunk cannot take less than one warp's latency chain through it (wait for the copy ->
+// shared-memory round trip -> math -> stores / tcgen05.wait::st -> arrive -> wait for the stage -> next copies, ~3 k
+// cycles), whatever the bandwidths are.  The way out is warp groups that OWN whole chunks (group g takes chunks g, g + G,
+// ...), so G chains overlap; this kernel's thread-per-channel L path is the piece that makes that affordable in
+// registers.  DESIGN.md section 9.
+constexpr int kLW = 4, kRWp = 11;
+constexpr int kRT = kRWp * 32;                          // R transform threads
+constexpr int kTlThreads = (kLW + kRWp + 1) * 32;       // 512
+constexpr int NPR_TL = (128 / 4 * WG_ROWS + kRT - 1) / kRT;   // max R pieces per thread and chunk (R width <= 128)
+
+template <int S, int LAG, int DL, class ProR>
+__global__ void __launch_bounds__(kTlThreads, 1)
+wgrad_tl_kernel(const PclRowGemm al, const PclRowGemm ar, long long P, int M, int N, float *__restrict__ out, int ldo) {
+    constexpr int PD = S - LAG;
+    constexpr bool kMask = MaskTrait<ProR>::value;
+    const int RW = ar.K;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    __shared__ __align__(8) uint64_t s_full[S], s_free[S], s_done;
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(16) float4 s_tabR[3][kTabQuads];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Npad = (N + 15) & ~15;
+    const int MB = (M + 31) / 32, NB = (Npad + 31) / 32;
+    const int NBlo = kMask ? (RW + 31) / 32 : NB;
+    const uint32_t l_raw = MB * WG_BLK;                   // one raw L tensor of a chunk: [32 rows][32 MB channels]
+    const uint32_t r_tile = NB * WG_BLK;
+    const uint32_t stage_bytes = r_tile + (uint32_t)NBlo * WG_BLK;   // R ring stage: [R hi | R lo]
+    // The raw L chunks land in their OWN ring of DL slots ([x0 raw | x1 raw], 2 l_raw bytes each) behind the R ring: a
+    // thread copies and reads back only its own elements, so a slot is reusable as soon as its thread has read it — no
+    // barrier — and the depth of the HBM prefetch (DL chunks) is no longer tied to the [hi | lo] operand stages.
+    const uint32_t lring = sbase + S * stage_bytes;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(smem_u32(&s_full[s]), kLW + kRWp);
+            mbar_init(smem_u32(&s_free[s]), 1);
+        }
+        mbar_init(smem_u32(&s_done), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int e = tid; e < 3 * kTabQuads; e += kTlThreads) {
+        const int t = e / kTabQuads, qd = e % kTabQuads;
+        s_tabR[t][qd] = (t < ProR::T && qd * 4 < RW) ? ProR::table(ar, qd * 4, t) : f4zero();
+    }
+    {   // constant R pieces, written once per stage: zeros for channel quads past the operand width
+        const int qR = 8 * NB;
+        for (int e = tid; e < S * WG_ROWS * qR; e += kTlThreads) {
+            const int s = e / (WG_ROWS * qR), r = e % (WG_ROWS * qR);
+            const int qd = r % qR, row = r / qR;
+            if (qd * 4 >= RW) {
+                const uint32_t o = sbase + s * stage_bytes + mn_off(row, qd);
+                sts4(o, 0u, 0u, 0u, 0u);
+                if (qd < 8 * NBlo) sts4(o + r_tile, 0u, 0u, 0u, 0u);
+            }
+        }
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const int dbg = al.c0 >> 16;
+
+    const long long n_chunks = (P + WG_ROWS - 1) / WG_ROWS;
+    const long long per = (n_chunks + gridDim.x - 1) / gridDim.x;
+    const long long c_begin = blockIdx.x * per;
+    const long long c_end = n_chunks < c_begin + per ? n_chunks : c_begin + per;
+    const int total = c_end > c_begin ? (int)(c_end - c_begin) : 0;
+
+    if (warp < kLW) {
+        // ============================ L transform: thread = channel ============================
+        const int q = warp & 3;
+        const int ch = q * 32 + lane;
+        const bool act = ch < M;
+        float cA = 0.f, cB = 0.f, cC = 0.f;               // dz = cA*x0 + cB*x1 + cC  (GBnBwd::table, one channel)
+        if (act) {
+            const float mu = __ldg(al.mean + ch), rs = __ldg(al.rstd + ch), bs = __ldg(al.bscale + ch);
+            const float m1 = __ldg(al.m1 + ch), m2 = __ldg(al.m2 + ch);
+            cA = bs;
+            cB = -bs * rs * m2;
+            cC = -fmaf(cB, mu, bs * m1);
+        }
+        const uint32_t rowstep = (uint32_t)MB * 128u;      // bytes per raw row
+        const uint32_t base_off = 4u * (uint32_t)ch;
+        const float *gp = al.x0 + c_begin * WG_ROWS * al.K + ch;
+        const long long d1 = al.x1 - al.x0;
+        int i_c = 0;
+        auto issue_next = [&]() {
+            if (i_c < total && act && !(dbg & 4)) {
+                const uint32_t st = lring + (uint32_t)(i_c % DL) * 2u * l_raw + base_off;
+                const long long left = P - (c_begin + i_c) * WG_ROWS;
+#pragma unroll
+                for (int j = 0; j < WG_ROWS; ++j) {
+                    const int nb = j < left ? 4 : 0;
+                    const float *g = j < left ? gp + (long long)j * al.K : al.x0;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(st + j * rowstep), "l"(g), "r"(nb));
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(st + l_raw + j * rowstep),
+                                 "l"(j < left ? g + d1 : al.x0), "r"(nb));
+                }
+            }
+            if (i_c < total) {
+                gp += (long long)WG_ROWS * al.K;
+                ++i_c;
+            }
+            cp_async_commit();
+        };
+        for (int j = 0; j < DL - 1; ++j) issue_next();
+        for (int cc = 0; cc < total; ++cc) {
+            const int s = cc % S;
+            const uint32_t st = lring + (uint32_t)(cc % DL) * 2u * l_raw + base_off;
+            const long long left = P - (c_begin + cc) * WG_ROWS;
+            cp_async_wait<DL - 2>();
+            // the tensor-memory buffer of ring stage s is free once the MMAs of chunk cc - S have retired
+            if (cc >= S) mbar_wait(smem_u32(&s_free[s]), (uint32_t)(((cc / S) - 1) & 1));
+            tc_fence_after();
+            if (act) {
+                const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + 128u + (uint32_t)(s * 64);
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    float d[16], y[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(d[j]) : "r"(st + (16 * hf + j) * rowstep));
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y[j]) : "r"(st + l_raw + (16 * hf + j) * rowstep));
+                    }
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float v = 16 * hf + j < left ? fmaf(cA, d[j], fmaf(cB, y[j], cC)) : 0.f;   // rows past P: nothing
+                        hi[j] = __float_as_uint(v) & 0xFFFFE000u;
+                        lo[j] = __float_as_uint(v - __uint_as_float(hi[j]));
+                    }
+                    tc_st16(ta + 16u * hf, hi);
+                    tc_st16(ta + 32u + 16u * hf, lo);
+                }
+                tc_wait_st();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s_full[s]));
+            issue_next();   // into the slot this thread has just read (chunk cc + DL - 1)
+        }
+        cp_async_wait<0>();
+        // ---- epilogue: TMEM accumulator -> atomics on OUT ----
+        if (total > 0) {
+            mbar_wait(smem_u32(&s_done), 0);
+            tc_fence_after();
+            for (int c0 = 0; c0 < Npad; c0 += 16) {
+                float v[16];
+                tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                if (act) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < N) atomicAdd(out + (long long)ch * ldo + c0 + j, v[j]);
+                }
+            }
+        }
+    } else if (warp < kLW + kRWp) {
+        // ============================ R transform (pieces, as wgrad_ws_kernel) ============================
+        const int tr = tid - kLW * 32;
+        Operand<NPR_TL, ProR> R;
+        const int liveR = (RW + 3) / 4;
+        R.n_live = 0;
+#pragma unroll
+        for (int i = 0; i < NPR_TL; ++i) {
+            const int e = tr + kRT * i;
+            R.row[i] = e / liveR;
+            R.kq[i] = e % liveR;
+            R.off[i] = mn_off(R.row[i] & 31, R.kq[i]);
+            R.offm[i] = kMask ? mn_off(R.row[i] & 31, R.kq[i] + liveR) : 0u;
+            R.gp[i] = nullptr;
+            if (e < WG_ROWS * liveR) R.n_live = i + 1;
+        }
+        static_assert(ProR::kSrc && !ProR::kTwo, "wgrad_tl_kernel: gathered single-tensor R operands only");
+        const uint32_t src_base = lring + (uint32_t)DL * 2u * l_raw + kSlackBytes;   // [PD + 1][live pieces per thread][kRT] ints
+        const int npr_live = (WG_ROWS * liveR + kRT - 1) / kRT;
+        auto src_slot = [&](int k, int i) { return src_base + (uint32_t)((((k % (PD + 1)) * npr_live + i) * kRT + tr) * 4); };
+        int i_c = 0;
+        // sidx: gather indices of the chunk about to be issued, read from their slots at the TOP of the iteration next
+        // to the raw-piece reads (the two shared-memory round trips overlap); the first PD chunks take them from global
+        auto issue_next = [&](const int (&sidx)[NPR_TL]) {
+            if (i_c < total) {
+                const uint32_t st = sbase + (i_c % S) * stage_bytes;
+                const long long c = c_begin + i_c;
+                const long long left = P - c * WG_ROWS;
+                const int rows_valid = left < WG_ROWS ? (int)left : WG_ROWS;
+#pragma unroll
+                for (int i = 0; i < NPR_TL; ++i) {
+                    if (i < R.n_live && !(dbg & 4)) {
+                        const bool ok = R.row[i] < rows_valid;
+                        const int sx = i_c < PD ? (ok ? __ldg(ar.src + c * WG_ROWS + R.row[i]) : 0) : sidx[i];
+                        const float *g = ProR::ptr(ar, sx, R.kq[i] * 4);
+                        const long long pn = (c + PD) * WG_ROWS + R.row[i];   // indices for chunk i_c + PD
+                        const bool okn = i_c + PD < total && pn < P;
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(src_slot(i_c + PD, i)),
+                                     "l"(ar.src + (okn ? pn : 0)), "r"(okn ? 4 : 0));
+                        cp_async16_zfill(st + R.off[i], ok ? g : ar.scale, ok);
+                    }
+                }
+                ++i_c;
+            }
+            cp_async_commit();
+        };
+        {
+            const int none[NPR_TL] = {};
+            for (int j = 0; j < PD; ++j) issue_next(none);
+        }
+        // the centre rows V come straight from global memory (L2): loaded ONE CHUNK AHEAD
+        float4 rvN[NPR_TL];
+        auto prefetch_v = [&](int cc) {
+            const long long c = c_begin + cc;
+            const long long left = P - c * WG_ROWS;
+#pragma unroll
+            for (int i = 0; i < NPR_TL; ++i) {
+                rvN[i] = f4zero();
+                if (i < R.n_live && ar.V != nullptr && cc < total && R.row[i] < left)
+                    rvN[i] = ld4(ar.V + group_of(ar, c * WG_ROWS + R.row[i]) * ar.K + R.kq[i] * 4);
+            }
+        };
+        prefetch_v(0);
+        for (int cc = 0; cc < total; ++cc) {
+            const uint32_t st = sbase + (cc % S) * stage_bytes;
+            const long long c = c_begin + cc;
+            const long long left = P - c * WG_ROWS;
+            const int rows_valid = left < WG_ROWS ? (int)left : WG_ROWS;
+            cp_async_wait<PD - 1>();
+            float4 r0[NPR_TL], rv[NPR_TL];
+            int sidx[NPR_TL];
+            const int nr = (dbg & 16) ? 0 : R.n_live;
+#pragma unroll
+            for (int i = 0; i < NPR_TL; ++i) {
+                r0[i] = f4zero();
+                rv[i] = rvN[i];
+                sidx[i] = 0;
+                if (i < nr) r0[i] = lds4(st + R.off[i]);
+                if (i < R.n_live && i_c >= PD && i_c < total)
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(sidx[i]) : "r"(src_slot(i_c, i)));
+            }
+            prefetch_v(cc + 1);
+#pragma unroll
+            for (int i = 0; i < NPR_TL; ++i) {
+                if (i < nr) {
+                    const uint32_t o = st + R.off[i];
+                    const float4 t[3] = {s_tabR[0][R.kq[i]], s_tabR[1][R.kq[i]], s_tabR[2][R.kq[i]]};
+                    float4 v = ProR::finish(ar, r0[i], f4zero(), t, rv[i]);
+                    if (R.row[i] >= rows_valid) v = f4zero();
+                    const float x[4] = {v.x, v.y, v.z, v.w};
+                    uint32_t hi[4], lo[4];
+                    split_tf32_trunc<4>(x, hi, lo);
+                    sts4(o, hi[0], hi[1], hi[2], hi[3]);
+                    sts4(o + r_tile, lo[0], lo[1], lo[2], lo[3]);
+                    if (kMask)   // relu'(z) == (a1 > 0)
+                        sts4(st + R.offm[i], v.x > 0.f ? 0x3F800000u : 0u, v.y > 0.f ? 0x3F800000u : 0u,
+                             v.z > 0.f ? 0x3F800000u : 0u, v.w > 0.f ? 0x3F800000u : 0u);
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s_full[cc % S]));
+            if (cc >= LAG && i_c < total) mbar_wait(smem_u32(&s_free[(cc - LAG) % S]), (uint32_t)(((cc - LAG) / S) & 1));
+            issue_next(sidx);
+        }
+        cp_async_wait<0>();
+    } else if (lane == 0) {
+        // ============================ MMA issuer ============================
+        // D = F32, A = TF32 from tensor memory (K-major), B = TF32 MN-major (bit 16), N >> 3, M = 128 >> 4
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(Npad >> 3) << 17) |
+                               ((uint32_t)(128 >> 4) << 24);
+        const int Nlo = kMask ? NBlo * 32 : Npad;
+        const uint32_t idesc_lo = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(Nlo >> 3) << 17) |
+                                  ((uint32_t)(128 >> 4) << 24);
+        for (int cc = 0; cc < total; ++cc) {
+            const int s = cc % S;
+            mbar_wait_spin(smem_u32(&s_full[s]), (uint32_t)((cc / S) & 1));
+            tc_fence_after();
+            const uint32_t st = sbase + s * stage_bytes;
+            const uint32_t ahi = tmem + 128u + (uint32_t)(s * 64), alo = ahi + 32u;
+#pragma unroll
+            for (int kg = 0; kg < 4; ++kg) {
+                if (dbg & 1) break;
+                const uint32_t o = kg * 1024;   // 8 rows = two 4-row groups of 512 B
+                const uint64_t dRhi = umma_desc_mn(st + o, WG_BLK, 512);
+                const uint64_t dRlo = umma_desc_mn(st + r_tile + o, WG_BLK, 512);
+                tc_mma_tf32_ts(tmem, alo + kg * 8, dRhi, idesc, (cc > 0 || kg > 0) ? 1u : 0u);
+                tc_mma_tf32_ts(tmem, ahi + kg * 8, dRlo, idesc_lo, 1u);
+                tc_mma_tf32_ts(tmem, ahi + kg * 8, dRhi, idesc, 1u);
+            }
+            tc_commit(smem_u32(&s_free[s]));
+        }
+        if (total > 0) tc_commit(smem_u32(&s_done));
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// rings of the tensor-memory-L kernel: S stages [R hi | R lo], DL slots [x0 raw | x1 raw], gather-index slots; 128 + 64 S
+// TMEM columns.  The operand over-read slack sits behind the L ring (the R tile's last stage is followed by it).
+static bool wgrad_tl_plan(int M, int N, int r_width, bool mask, int &S, int &DL, size_t &smem) {
+    const int Npad = (N + 15) & ~15;
+    const int MB = (M + 31) / 32, NB = (Npad + 31) / 32, NBlo = mask ? (r_width + 31) / 32 : NB;
+    const size_t rstage = (size_t)(NB + NBlo) * WG_BLK, lslot = (size_t)2 * MB * WG_BLK;
+    const int live_r = (r_width + 3) / 4;
+    const size_t slot = (size_t)((WG_ROWS * live_r + kRT - 1) / kRT) * kRT * 4;
+    const size_t total = 232448 - 4096 - 1024 - kSlackBytes;
+    const int cand[4][2] = {{4, 6}, {4, 4}, {3, 6}, {3, 4}};   // (S, DL): LAG = 2 / PD = 2 at S = 4, LAG = 1 / PD = 2 at S = 3
+    for (auto &c : cand) {
+        if (rstage * c[0] + lslot * c[1] + 3 * slot <= total) {
+            S = c[0];
+            DL = c[1];
+            smem = 1024 + rstage * S + lslot * DL + kSlackBytes + 3 * slot;
+            return true;
+        }
+    }
+    return false;
+}
+
+template <class ProR>
+static int launch_wgrad_tl(const PclRowGemm &al, const PclRowGemm &ar, long long P, int M, int N, float *out, int ldo,
+                           cudaStream_t st) {
+    size_t smem = 0;
+    int S = 0, DL = 0;
+    if (!wgrad_tl_plan(M, N, ar.K, MaskTrait<ProR>::value, S, DL, smem)) {
+        set_error("pcl_wgrad(tl): M=%d N=%d does not fit", M, N);
+        return PCL_ERR_UNSUPPORTED;
+    }
+    const long long n_chunks = (P + WG_ROWS - 1) / WG_ROWS;
+    const unsigned grid = (unsigned)(n_chunks < kNumSMs ? n_chunks : kNumSMs);
+    cudaError_t e = cudaSuccess;
+#define PCL_LAUNCH_TL(S_, LAG_, DL_)                                                              \
+    do {                                                                                          \
+        auto kern = wgrad_tl_kernel<S_, LAG_, DL_, ProR>;                                         \
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+        if (e == cudaSuccess) kern<<<grid, kTlThreads, smem, st>>>(al, ar, P, M, N, out, ldo);    \
+    } while (0)
+    if (S == 4 && DL == 6) PCL_LAUNCH_TL(4, 2, 6);
+    else if (S == 4) PCL_LAUNCH_TL(4, 2, 4);
+    else if (DL == 6) PCL_LAUNCH_TL(3, 1, 6);
+    else PCL_LAUNCH_TL(3, 1, 4);
+#undef PCL_LAUNCH_TL
+    if (e != cudaSuccess) {
+        set_error("pcl_wgrad(tl): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    return check_launch("pcl_wgrad(tl)");
+}
+
 // r_width: channels of the R operand that are loaded (its row stride); mask: [a1 | relu'] right operand (no lo tile for
 // the 0/1 block).  LAG = 1 where it buys a deeper prefetch: PD = S - LAG chunks in flight.
 static void wgrad_ws_geometry(int M, int N, int r_width, bool share, bool gather, bool mask, bool lag1, size_t &stage,
@@ -531,6 +907,14 @@ int wgrad_ws_dispatch(const PclRowGemm &al, int pl, const PclRowGemm &ar, int pr
     using namespace ws;
 #define PCL_WS(L_, R_, PL_, PR_) \
     if (pl == L_ && pr == R_) return launch_wgrad_ws<false, PL_, PR_>(al, ar, P, M, N, out, ldo, st)
+    if (pl == PCL_PRO_BN_BWD && (pr == PCL_PRO_GATHER_BN_ACT || pr == PCL_PRO_GATHER_BN_ACT_MASK) && M <= 128 && N <= 160 &&
+        ar.K <= 128 && ((al.c0 >> 16) & 4096)) {   // opt-in (knob 4096): measured on par with wgrad_ws_kernel, see the header above
+        size_t smem;
+        int S_, DL_;
+        if (wgrad_tl_plan(M, N, ar.K, pr == PCL_PRO_GATHER_BN_ACT_MASK, S_, DL_, smem))
+            return pr == PCL_PRO_GATHER_BN_ACT_MASK ? launch_wgrad_tl<GGatherBnActMask>(al, ar, P, M, N, out, ldo, st)
+                                                    : launch_wgrad_tl<GGatherBnAct>(al, ar, P, M, N, out, ldo, st);
+    }
     if (gram_shares(al, pl, ar, pr, M)) return launch_wgrad_ws<true, GBnAct, GBnActOnes>(al, ar, P, M, N, out, ldo, st);
     PCL_WS(PCL_PRO_BN_ACT, PCL_PRO_BN_ACT_ONES, GBnAct, GBnActOnes);
     PCL_WS(PCL_PRO_BN_BWD, PCL_PRO_BN_ACT, GBnBwd, GBnAct);

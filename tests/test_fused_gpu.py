@@ -445,3 +445,30 @@ def test_small_radius_branches_at_the_bench_shape(r, ns, chans, preload):
     assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= 1e-3 * scale
     worst = {n: _rel(p.grad, q.grad) for (n, p), (_, q) in zip(seq_d.named_parameters(), ref_seq.named_parameters())}
     assert max(worst.values()) <= 2e-3, worst
+
+
+def test_weight_gradient_with_the_left_operand_in_tensor_memory():
+    """wgrad_tl_kernel (opt-in, knob 4096): dz2^T.[a1 | mask1] with the BatchNorm-backward operand written to tensor
+    memory by thread-per-channel transform warps (TS-form MMAs) == the default shared-memory kernel."""
+    B, N, S, C = 8, 4096, 512, 3
+    xyz, nrm, _ = modelnet_batch(B, N, seed=3)
+    xd, nd = xyz.to(DEV), nrm.to(DEV)
+    new_xyz = F.gather_xyz(xd, F.furthest_point_sample(xd, S))
+    for r, ns, chans in [(0.4, 128, (64, 96, 128)), (0.2, 32, (64, 64, 128)), (0.1, 16, (32, 32, 64))]:
+        seq = _mlp(chans, 3 + C).train()
+        gen = torch.Generator().manual_seed(9)
+        gout, grads = None, []
+        try:
+            for knob in (0, 4096):
+                fused.WS_DBG = knob
+                seq_d = copy.deepcopy(seq).to(DEV)
+                out = sa.sa_branch(BallQueryGrouper(r, ns, True), seq_d, new_xyz, xd, nd)
+                if gout is None:
+                    gout = torch.randn(out.shape, generator=gen).to(DEV)
+                out.backward(gout)
+                torch.cuda.synchronize()
+                grads.append([p.grad.clone() for p in seq_d.parameters()])
+        finally:
+            fused.WS_DBG = 0
+        for a, b in zip(*grads):
+            assert _rel(a, b) <= 2e-4, f"ns={ns}: rel-L2 {_rel(a, b):.3e}"

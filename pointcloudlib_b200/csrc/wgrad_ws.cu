@@ -753,6 +753,343 @@ wgrad_tl_kernel(const PclRowGemm al, const PclRowGemm ar, long long P, int M, in
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// wgrad_own_kernel — warp groups that OWN whole chunks (round 2).
+//
+// In wgrad_ws_kernel / wgrad_tl_kernel every transform warp touches every 32-row chunk, so a chunk cannot take less than
+// one warp's latency chain through it (~3 k cycles), whatever the bandwidths are.  Here the CTA is G = 4 groups of 4
+// warps (one warp per tensor-memory lane quarter); group g takes the chunks g, g + G, ... of the CTA's row range and does
+// EVERYTHING for them: lands the raw rows (its own [R hi | R lo | x0 raw | x1 raw] buffer, 48 KB), writes the L operand
+// to its tensor-memory buffer (thread = channel, as wgrad_tl_kernel), builds the R tile in shared memory (pieces over
+// its 128 threads), meets at a named barrier, and its first lane issues the chunk's 12 MMAs and commits to the group's
+// mbarrier.  There is no MMA warp and no full / free ring: G latency chains overlap, and inside a group the HBM copies
+// of chunk k + 1's L rows are issued as soon as chunk k's have been read back (the R rows come from L2 and are issued
+// when the MMAs of chunk k have retired, since they land in the operand tile itself).
+//   TMEM (512 columns): [0,128) accumulator (zeroed once; every MMA accumulates), [128 + 64 g, +32) L hi, (+32, +64) L lo
+// L must be PCL_PRO_BN_BWD (M <= 128); R a gathered prologue of at most 64 channels (4 pieces per thread).
+constexpr int kOwnG = 4;
+constexpr int kOwnThreads = kOwnG * 128;                // 512: 16 warps -> 128 registers per thread
+constexpr int NPR_OWN = (64 / 4 * WG_ROWS + 127) / 128;   // R pieces per thread and chunk
+
+template <class ProR>
+__global__ void __launch_bounds__(kOwnThreads, 1)
+wgrad_own_kernel(const PclRowGemm al, const PclRowGemm ar, long long P, int M, int N, float *__restrict__ out, int ldo) {
+    constexpr bool kMask = MaskTrait<ProR>::value;
+    constexpr int G = kOwnG;
+    const int RW = ar.K;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    __shared__ __align__(8) uint64_t s_mdone[G];
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(16) float4 s_tabR[3][kTabQuads];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = warp >> 2, q = warp & 3, tg = tid & 127;   // group, TMEM lane quarter, thread inside the group
+    const int Npad = (N + 15) & ~15;
+    const int MB = (M + 31) / 32, NB = (Npad + 31) / 32;
+    const int NBlo = kMask ? (RW + 31) / 32 : NB;
+    const uint32_t l_raw = MB * WG_BLK, r_tile = NB * WG_BLK, r_lo = (uint32_t)NBlo * WG_BLK;
+    const uint32_t r_raw = (uint32_t)(WG_ROWS * ((RW + 3) / 4) * 16);   // gathered rows as landed: [row][quad] 16-byte pieces
+    const uint32_t gbytes = r_tile + r_lo + 2 * l_raw + r_raw;   // [R hi | R lo | x0 raw | x1 raw | R raw] of one group
+    const uint32_t gb = sbase + (uint32_t)g * gbytes;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int i = 0; i < G; ++i) mbar_init(smem_u32(&s_mdone[i]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int e = tid; e < 3 * kTabQuads; e += kOwnThreads) {
+        const int t = e / kTabQuads, qd = e % kTabQuads;
+        s_tabR[t][qd] = (t < ProR::T && qd * 4 < RW) ? ProR::table(ar, qd * 4, t) : f4zero();
+    }
+    {   // constant R pieces of this group's tile, written once: zeros for channel quads past the operand width
+        const int qR = 8 * NB;
+        for (int e = tg; e < WG_ROWS * qR; e += 128) {
+            const int qd = e % qR, row = e / qR;
+            if (qd * 4 >= RW) {
+                const uint32_t o = gb + mn_off(row, qd);
+                sts4(o, 0u, 0u, 0u, 0u);
+                if (qd < 8 * NBlo) sts4(o + r_tile, 0u, 0u, 0u, 0u);
+            }
+        }
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    if (g == 0) {   // the accumulator starts at zero: every MMA of every group accumulates
+        uint32_t z[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) z[i] = 0u;
+        for (int c0 = 0; c0 < 128; c0 += 16) tc_st16(tlane + c0, z);
+        tc_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const long long n_chunks = (P + WG_ROWS - 1) / WG_ROWS;
+    const long long per = (n_chunks + gridDim.x - 1) / gridDim.x;
+    const long long c_begin = blockIdx.x * per;
+    const long long c_end = n_chunks < c_begin + per ? n_chunks : c_begin + per;
+    const int total = c_end > c_begin ? (int)(c_end - c_begin) : 0;
+    const int mine = total > g ? (total - g + G - 1) / G : 0;   // chunks g, g + G, ... of the CTA's range
+
+    // ---- L side: thread = channel ----
+    const int ch = q * 32 + lane;
+    const bool act = ch < M;
+    float cA = 0.f, cB = 0.f, cC = 0.f;                    // dz = cA*x0 + cB*x1 + cC  (GBnBwd::table, one channel)
+    if (act) {
+        const float mu = __ldg(al.mean + ch), rs = __ldg(al.rstd + ch), bs = __ldg(al.bscale + ch);
+        const float m1 = __ldg(al.m1 + ch), m2 = __ldg(al.m2 + ch);
+        cA = bs;
+        cB = -bs * rs * m2;
+        cC = -fmaf(cB, mu, bs * m1);
+    }
+    const uint32_t rowstep = (uint32_t)MB * 128u;
+    const uint32_t lbuf = gb + r_tile + r_lo + 4u * (uint32_t)ch;
+    const long long d1 = al.x1 - al.x0;
+    // raw rows of this group's k-th chunk: 16-byte pieces over the group's 128 threads (a thread copies other elements
+    // than the ones it reads back by channel, hence the group barrier after the wait)
+    const int lq = M / 4;                                  // 16-byte pieces per row (M % 4 == 0)
+    const int n_lp = WG_ROWS * lq;                         // pieces per tensor and chunk
+    const int lr0 = tg / lq, lc0 = tg % lq, lrs = 128 / lq, lcs = 128 % lq;   // piece e = tg + 128 i -> (row, quad), incrementally
+    auto issue_L = [&](int k) {
+        if (k < mine) {
+            const long long row0 = (c_begin + g + (long long)k * G) * WG_ROWS;
+            const long long left = P - row0;
+            int r = lr0, c4 = lc0;
+            for (int e = tg; e < n_lp; e += 128, r += lrs, c4 += lcs) {
+                if (c4 >= lq) { c4 -= lq; ++r; }
+                const bool ok = r < left;
+                const float *p0 = al.x0 + (ok ? (row0 + r) * al.K + 4 * c4 : 0);
+                const uint32_t dst = gb + r_tile + r_lo + (uint32_t)r * rowstep + 16u * (uint32_t)c4;
+                cp_async16_zfill(dst, p0, ok);
+                cp_async16_zfill(dst + l_raw, ok ? p0 + d1 : al.x0, ok);
+            }
+        }
+        cp_async_commit();
+    };
+    // ---- R side: pieces over the group's 128 threads ----
+    const int liveR = (RW + 3) / 4;
+    int prow[NPR_OWN], pkq[NPR_OWN];
+    uint32_t poff[NPR_OWN], poffm[NPR_OWN];
+    int n_live = 0;
+#pragma unroll
+    for (int i = 0; i < NPR_OWN; ++i) {
+        const int e = tg + 128 * i;
+        prow[i] = e / liveR;
+        pkq[i] = e % liveR;
+        poff[i] = mn_off(prow[i] & 31, pkq[i]);
+        poffm[i] = kMask ? mn_off(prow[i] & 31, pkq[i] + liveR) : 0u;
+        if (e < WG_ROWS * liveR) n_live = i + 1;
+    }
+    const uint32_t rraw = gb + r_tile + r_lo + 2 * l_raw + 16u * (uint32_t)tg;   // piece e = tg + 128 i at 16 e bytes
+    {
+    }
+    // 128 % liveR == 0: every piece of a thread has the same channel quad -> its two table entries live in registers
+    const bool same_kq = 128 % liveR == 0;
+    static_assert(ProR::T == 2, "wgrad_own_kernel: BatchNorm + activation R prologues (scale, shift tables)");
+    __syncthreads();   // (the table was written above by other threads)
+    const float4 tab0 = s_tabR[0][pkq[0]], tab1 = s_tabR[1][pkq[0]];
+    // (The centre-row pieces fetched two chunks ahead with the indices — one float4 per thread when ns % 32 == 0 — were
+    // measured slower, 587 vs 553 us: the kernel sits at the 128-register limit and anything more spills.)
+    int srcN[NPR_OWN];
+    auto prefetch_R = [&](int k) {   // gather indices of the k-th own chunk (registers)
+        const long long row0 = (c_begin + g + (long long)k * G) * WG_ROWS;
+#pragma unroll
+        for (int i = 0; i < NPR_OWN; ++i) {
+            srcN[i] = 0;
+            const long long p = row0 + prow[i];
+            if (i < n_live && k < mine && p < P) srcN[i] = __ldg(ar.src + p);
+        }
+    };
+    auto issue_R = [&](int k, const int (&sx)[NPR_OWN]) {   // gathered rows straight into the R hi tile
+        if (k < mine) {
+            const long long row0 = (c_begin + g + (long long)k * G) * WG_ROWS;
+#pragma unroll
+            for (int i = 0; i < NPR_OWN; ++i) {
+                if (i < n_live) {
+                    const bool ok = row0 + prow[i] < P;
+                    cp_async16_zfill(rraw + 2048u * (uint32_t)i, ok ? ProR::ptr(ar, sx[i], pkq[i] * 4) : ar.scale, ok);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(Npad >> 3) << 17) |
+                           ((uint32_t)(128 >> 4) << 24);
+    const int Nlo = kMask ? NBlo * 32 : Npad;
+    const uint32_t idesc_lo = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(Nlo >> 3) << 17) |
+                              ((uint32_t)(128 >> 4) << 24);
+    const uint32_t ahi = tmem + 128u + (uint32_t)(g * 64), alo = ahi + 32u;
+
+    const bool profiling = ((al.c0 >> 16) & 16384) && al.gmin != nullptr;   // knob: phase cycle counters of thread 0 of CTA 0
+    long long prof[6] = {0, 0, 0, 0, 0, 0};   // {copy wait, L, R, barrier, MMA wait, chunks}
+    issue_L(0);
+    prefetch_R(0);
+    {
+        int s0[NPR_OWN];
+#pragma unroll
+        for (int i = 0; i < NPR_OWN; ++i) s0[i] = srcN[i];
+        issue_R(0, s0);
+    }
+    prefetch_R(1);
+    for (int k = 0; k < mine; ++k) {
+        const long long row0 = (c_begin + g + (long long)k * G) * WG_ROWS;
+        const long long left = P - row0;
+        long long t0 = profiling ? clock64() : 0;
+        cp_async_wait<0>();                       // this thread's pieces of chunk k (L rows, gathered R rows)
+        asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");   // every thread's pieces of the raw L rows have landed
+        if (profiling) { const long long t1 = clock64(); prof[0] += t1 - t0; t0 = t1; }
+        // the MMAs of chunk k - 1 have retired: the tensor-memory buffer and the R tile are free (they ran while this
+        // group waited for the copies of chunk k)
+        if (k > 0) mbar_wait(smem_u32(&s_mdone[g]), (uint32_t)((k - 1) & 1));
+        tc_fence_after();
+        if (profiling) { const long long t1 = clock64(); prof[4] += t1 - t0; t0 = t1; }
+        // ---- L: read back, A*x0 + B*x1 + C, hi / lo -> tensor memory ----
+        if (act) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                float d[16], y[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(d[j]) : "r"(lbuf + (16 * hf + j) * rowstep));
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y[j]) : "r"(lbuf + l_raw + (16 * hf + j) * rowstep));
+                }
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float v = 16 * hf + j < left ? fmaf(cA, d[j], fmaf(cB, y[j], cC)) : 0.f;   // rows past P: nothing
+                    hi[j] = __float_as_uint(v) & 0xFFFFE000u;
+                    lo[j] = __float_as_uint(v - __uint_as_float(hi[j]));
+                }
+                tc_st16(tlane + 128u + (uint32_t)(g * 64 + 16 * hf), hi);
+                tc_st16(tlane + 128u + (uint32_t)(g * 64 + 32 + 16 * hf), lo);
+            }
+        }
+        // the group's threads have all read their channels before anyone refills the raw buffer
+        asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
+        issue_L(k + 1);                           // HBM rows of the next own chunk
+        if (profiling) { const long long t1 = clock64(); prof[1] += t1 - t0; t0 = t1; }
+        // ---- R: gathered pieces (this thread's own, from the landing buffer) + centre rows, then the next gather goes out,
+        // then BatchNorm + ReLU, hi / lo (+ mask block) into the operand tile.  (Requesting these before the L phase, so
+        // that their round trips run behind it, was measured slower: 701 vs 553 us, the extra live registers spill.) ----
+        float4 rv[NPR_OWN], r0[NPR_OWN];
+#pragma unroll
+        for (int i = 0; i < NPR_OWN; ++i) {
+            rv[i] = r0[i] = f4zero();
+            if (i < n_live) {
+                r0[i] = lds4(rraw + 2048u * (uint32_t)i);
+                if (ar.V != nullptr && prow[i] < left) rv[i] = ld4(ar.V + group_of(ar, row0 + prow[i]) * ar.K + pkq[i] * 4);
+            }
+        }
+        {
+            int sx[NPR_OWN];
+#pragma unroll
+            for (int i = 0; i < NPR_OWN; ++i) sx[i] = srcN[i];
+            // (the landing pieces are consumed once their values are in registers: order the refill behind the reads)
+            asm volatile("" ::"f"(r0[0].x), "f"(r0[NPR_OWN - 1].w) : "memory");
+            issue_R(k + 1, sx);
+            prefetch_R(k + 2);
+        }
+#pragma unroll
+        for (int i = 0; i < NPR_OWN; ++i) {
+            if (i < n_live) {
+                const uint32_t o = gb + poff[i];
+                const float4 t[3] = {same_kq ? tab0 : s_tabR[0][pkq[i]], same_kq ? tab1 : s_tabR[1][pkq[i]], f4zero()};
+                float4 v = ProR::finish(ar, r0[i], f4zero(), t, rv[i]);
+                if (prow[i] >= left) v = f4zero();
+                const float x[4] = {v.x, v.y, v.z, v.w};
+                uint32_t hi[4], lo[4];
+                split_tf32_trunc<4>(x, hi, lo);
+                sts4(o, hi[0], hi[1], hi[2], hi[3]);
+                sts4(o + r_tile, lo[0], lo[1], lo[2], lo[3]);
+                if (kMask)   // relu'(z) == (a1 > 0)
+                    sts4(gb + poffm[i], v.x > 0.f ? 0x3F800000u : 0u, v.y > 0.f ? 0x3F800000u : 0u,
+                         v.z > 0.f ? 0x3F800000u : 0u, v.w > 0.f ? 0x3F800000u : 0u);
+            }
+        }
+        // ---- the group meets; its first lane issues the chunk's MMAs ----
+        fence_proxy_async();
+        tc_wait_st();
+        tc_fence_before();
+        if (profiling) { const long long t1 = clock64(); prof[2] += t1 - t0; t0 = t1; }
+        asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
+        if (profiling) { prof[3] += clock64() - t0; prof[5] += 1; }
+        if (tg == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int kg = 0; kg < 4; ++kg) {
+                const uint32_t o = kg * 1024;   // 8 rows = two 4-row groups of 512 B
+                const uint64_t dRhi = umma_desc_mn(gb + o, WG_BLK, 512);
+                const uint64_t dRlo = umma_desc_mn(gb + r_tile + o, WG_BLK, 512);
+                tc_mma_tf32_ts(tmem, alo + kg * 8, dRhi, idesc, 1u);
+                tc_mma_tf32_ts(tmem, ahi + kg * 8, dRlo, idesc_lo, 1u);
+                tc_mma_tf32_ts(tmem, ahi + kg * 8, dRhi, idesc, 1u);
+            }
+            tc_commit(smem_u32(&s_mdone[g]));
+        }
+    }
+    if (mine > 0) mbar_wait(smem_u32(&s_mdone[g]), (uint32_t)((mine - 1) & 1));
+    if (profiling && blockIdx.x == 0 && tid == 0)
+        for (int i = 0; i < 6; ++i) reinterpret_cast<long long *>(al.gmin)[i] = prof[i];
+    cp_async_wait<0>();
+    tc_fence_before();
+    __syncthreads();                              // every group's MMAs have retired
+    tc_fence_after();
+    // ---- epilogue: TMEM accumulator -> atomics on OUT (16-column blocks spread over the groups) ----
+    if (total > 0) {
+        for (int c0 = g * 16; c0 < Npad; c0 += 16 * G) {
+            float v[16];
+            tc_ld16(tlane + (uint32_t)c0, v);
+            if (act) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < N) atomicAdd(out + (long long)ch * ldo + c0 + j, v[j]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+static bool wgrad_own_fits(int M, int N, int r_width, bool mask, size_t &smem) {
+    const int Npad = (N + 15) & ~15;
+    const int MB = (M + 31) / 32, NB = (Npad + 31) / 32, NBlo = mask ? (r_width + 31) / 32 : NB;
+    smem = 1024 + (size_t)kOwnG * ((size_t)(NB + NBlo + 2 * MB) * WG_BLK + (size_t)WG_ROWS * ((r_width + 3) / 4) * 16);
+    return r_width <= 64 && M <= 128 && M % 4 == 0 && Npad <= 128 && smem <= (size_t)(232448 - 2048);
+}
+
+template <class ProR>
+static int launch_wgrad_own(const PclRowGemm &al, const PclRowGemm &ar, long long P, int M, int N, float *out, int ldo,
+                            cudaStream_t st) {
+    size_t smem = 0;
+    if (!wgrad_own_fits(M, N, ar.K, MaskTrait<ProR>::value, smem)) {
+        set_error("pcl_wgrad(own): M=%d N=%d K_r=%d does not fit", M, N, ar.K);
+        return PCL_ERR_UNSUPPORTED;
+    }
+    const long long n_chunks = (P + WG_ROWS - 1) / WG_ROWS;
+    const unsigned grid = (unsigned)(n_chunks < kNumSMs ? n_chunks : kNumSMs);
+    auto kern = wgrad_own_kernel<ProR>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("pcl_wgrad(own): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    kern<<<grid, kOwnThreads, smem, st>>>(al, ar, P, M, N, out, ldo);
+    return check_launch("pcl_wgrad(own)");
+}
+
 // rings of the tensor-memory-L kernel: S stages [R hi | R lo], DL slots [x0 raw | x1 raw], gather-index slots; 128 + 64 S
 // TMEM columns.  The operand over-read slack sits behind the L ring (the R tile's last stage is followed by it).
 static bool wgrad_tl_plan(int M, int N, int r_width, bool mask, int &S, int &DL, size_t &smem) {
@@ -907,6 +1244,13 @@ int wgrad_ws_dispatch(const PclRowGemm &al, int pl, const PclRowGemm &ar, int pr
     using namespace ws;
 #define PCL_WS(L_, R_, PL_, PR_) \
     if (pl == L_ && pr == R_) return launch_wgrad_ws<false, PL_, PR_>(al, ar, P, M, N, out, ldo, st)
+    if (pl == PCL_PRO_BN_BWD && (pr == PCL_PRO_GATHER_BN_ACT || pr == PCL_PRO_GATHER_BN_ACT_MASK) &&
+        !((al.c0 >> 16) & (2048 | 4096))) {
+        size_t smem;   // chunk-owning warp groups (default where the shape fits; knob 2048 / 4096: the other two kernels)
+        if (wgrad_own_fits(M, N, ar.K, pr == PCL_PRO_GATHER_BN_ACT_MASK, smem))
+            return pr == PCL_PRO_GATHER_BN_ACT_MASK ? launch_wgrad_own<GGatherBnActMask>(al, ar, P, M, N, out, ldo, st)
+                                                    : launch_wgrad_own<GGatherBnAct>(al, ar, P, M, N, out, ldo, st);
+    }
     if (pl == PCL_PRO_BN_BWD && (pr == PCL_PRO_GATHER_BN_ACT || pr == PCL_PRO_GATHER_BN_ACT_MASK) && M <= 128 && N <= 160 &&
         ar.K <= 128 && ((al.c0 >> 16) & 4096)) {   // opt-in (knob 4096): measured on par with wgrad_ws_kernel, see the header above
         size_t smem;

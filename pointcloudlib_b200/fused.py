@@ -156,6 +156,8 @@ def wgrad(pro_l, kw_l, pro_r, kw_r, P, M, N, out, name="wgrad"):
     ar, k2 = _args(**kw_r)
     if WS_DBG and pro_l != PRO_PLAIN2:
         al.c0 = WS_DBG << 16
+        if PROF_BUF is not None and name == "sa_dw2":
+            al.gmin = ptr(PROF_BUF)
     _lib.call("pcl_wgrad", ctypes.byref(al), pro_l, ctypes.byref(ar), pro_r, P, M, N, ptr(out),
               out.stride(0), int(MODE), stream(out), key=(name, P, M, N))
 

@@ -46,6 +46,8 @@ for ci, (cen, pts, feat, r, ns, chans) in enumerate(cases):
         grads[flag] = [p.grad.clone() for p in seq.parameters()]
         if flag and len(sys.argv) > 3:
             print('   all kernels (us):', dict(sorted(t.items(), key=lambda kv: -kv[1])[:14]), flush=True)
-        if flag and knob & 16384:
+        if flag and knob & 16384 and knob & 8192:
+            print('   wgrad_own thread 0 of CTA 0, cycles {copy wait, L, R, barrier, MMA wait, chunks}:', fused.PROF_BUF.view(torch.int64).tolist()[:6])
+        elif flag and knob & 16384:
             print('   epilogue warp 8 of CTA 0, cycles {entry wait, zero fill, entry loop, accfull wait, drain, tiles}:', fused.PROF_BUF.view(torch.int64).tolist()[:6])
     print("   max rel grad diff preload vs one-hot:", max(((a - b).norm() / b.norm().clamp_min(1e-20)).item() for a, b in zip(grads[1], grads[0])), flush=True)

@@ -15,7 +15,8 @@ MAP = [  # (substrings of the kernel name, key in bench.py's table); generation 
     (("rowgemm_ws_kernel", "WProG3A2", "WEpiBwdYMask"), "pcl_rowgemm|sa_b3|4|6|2097152|224|96"),
     (("rowgemm_ws2_kernel", "WProBnBwd", "WEpiStore"), "pcl_rowgemm|sa_b2|3|0|2097152|96|64"),
     (("wgrad_ws_kernel", "GBnAct, ws::GBnActOnes"), "pcl_wgrad|sa_gram|2097152|96|97"),
-    (("wgrad_ws_kernel", "GBnBwd", "GGatherBnActMask"), "pcl_wgrad|sa_dw2|2097152|96|128"),
+    (("wgrad_own_kernel", "GGatherBnActMask"), "pcl_wgrad|sa_dw2|2097152|96|128"),
+    (("wgrad_ws_kernel", "GBnBwd", "GGatherBnActMask"), "pcl_wgrad|sa_dw2_ws|2097152|96|128"),
     (("sel_outer_group_kernel",), "pcl_sel_outer|sa_sel_outer|16384|128|96"),
     (("gather_bn_backward_kernel<1>",), "pcl_gather_bn_backward_masked|sa_b1_scatter|2097152|64"),
     (("gather_stats_kernel",), "pcl_gather_stats|sa_gather_stats|2097152|64"),
@@ -39,6 +40,12 @@ for r in rows[2:]:
     for w in want:
         if w in col:
             lines.append(f"  {w}: {r[col[w]]} {units[col[w]]}")
+try:   # merge into the existing table (captures of single kernels update their rows only)
+    prev = json.load(open("profiles/ncu_traffic_r02.json"))
+except Exception:
+    prev = {}
+prev.update(out)
+out = prev
 json.dump(out, open("profiles/ncu_traffic_r02.json", "w"), indent=1)
 if len(sys.argv) > 2:
     open(sys.argv[2], "w").write("\n".join(lines) + "\n")

@@ -1063,6 +1063,238 @@ wgrad_own_kernel(const PclRowGemm al, const PclRowGemm ar, long long P, int M, i
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
+// The Gram case of wgrad_own_kernel: OUT (M, M + 1) += a^T.[a | 1] with a = act(scale*x0 + shift), both operands from the
+// SAME raw rows.  A group's buffer is [R hi | R lo | raw 0 | raw 1]: the raw chunk lands once (16-byte pieces over the
+// group's threads, double-buffered, the copies of chunk k + 1 go out at the top of chunk k), is read back by channel
+// for the tensor-memory L operand and by 16-byte piece for the [a | 1] tile (the ones column is written once).
+constexpr int NPG_OWN = (96 / 4 * WG_ROWS + 127) / 128;   // R pieces per thread and chunk (M <= 96)
+
+__global__ void __launch_bounds__(kOwnThreads, 1)
+wgrad_own_gram_kernel(const PclRowGemm a, long long P, int M, int N, float *__restrict__ out, int ldo) {
+    constexpr int G = kOwnG;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    __shared__ __align__(8) uint64_t s_mdone[G];
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(16) float4 s_tab[2][kTabQuads];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = warp >> 2, q = warp & 3, tg = tid & 127;
+    const int Npad = (N + 15) & ~15;                        // N = M + 1: [a | 1]
+    const int MB = (M + 31) / 32, NB = (Npad + 31) / 32;
+    const uint32_t l_raw = MB * WG_BLK, r_tile = NB * WG_BLK;
+    const uint32_t gbytes = 2 * r_tile + 2 * l_raw;        // [R hi | R lo | raw 0 | raw 1]
+    const uint32_t gb = sbase + (uint32_t)g * gbytes;
+    const uint32_t rowstep = (uint32_t)MB * 128u;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int i = 0; i < G; ++i) mbar_init(smem_u32(&s_mdone[i]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int e = tid; e < 2 * kTabQuads; e += kOwnThreads) {
+        const int t = e / kTabQuads, qd = e % kTabQuads;
+        s_tab[t][qd] = qd * 4 < M ? ld4((t == 0 ? a.scale : a.shift) + qd * 4) : f4zero();
+    }
+    {   // constant pieces of this group's tile: the ones column (first quad past the operand) and zeros behind it
+        const int qR = 8 * NB;
+        for (int e = tg; e < WG_ROWS * qR; e += 128) {
+            const int qd = e % qR, row = e / qR;
+            if (qd * 4 >= M) {
+                const uint32_t o = gb + mn_off(row, qd);
+                sts4(o, qd * 4 == M ? 0x3F800000u : 0u, 0u, 0u, 0u);
+                sts4(o + r_tile, 0u, 0u, 0u, 0u);
+            }
+        }
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    if (g == 0) {
+        uint32_t z[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) z[i] = 0u;
+        for (int c0 = 0; c0 < 128; c0 += 16) tc_st16(tlane + c0, z);
+        tc_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const long long n_chunks = (P + WG_ROWS - 1) / WG_ROWS;
+    const long long per = (n_chunks + gridDim.x - 1) / gridDim.x;
+    const long long c_begin = blockIdx.x * per;
+    const long long c_end = n_chunks < c_begin + per ? n_chunks : c_begin + per;
+    const int total = c_end > c_begin ? (int)(c_end - c_begin) : 0;
+    const int mine = total > g ? (total - g + G - 1) / G : 0;
+
+    const int ch = q * 32 + lane;
+    const bool act = ch < M;
+    const float cs = act ? __ldg(a.scale + ch) : 0.f, ct = act ? __ldg(a.shift + ch) : 0.f;
+    const float slope = a.slope;
+    const int lq = M / 4, n_lp = WG_ROWS * lq;
+    const int lr0 = tg / lq, lc0 = tg % lq, lrs = 128 / lq, lcs = 128 % lq;
+    auto issue = [&](int k) {   // raw rows of the k-th own chunk -> raw buffer k & 1
+        if (k < mine) {
+            const long long row0 = (c_begin + g + (long long)k * G) * WG_ROWS;
+            const long long left = P - row0;
+            const uint32_t rb = gb + 2 * r_tile + (uint32_t)(k & 1) * l_raw;
+            int r = lr0, c4 = lc0;
+            for (int e = tg; e < n_lp; e += 128, r += lrs, c4 += lcs) {
+                if (c4 >= lq) { c4 -= lq; ++r; }
+                const bool ok = r < left;
+                cp_async16_zfill(rb + (uint32_t)r * rowstep + 16u * (uint32_t)c4, a.x0 + (ok ? (row0 + r) * a.K + 4 * c4 : 0), ok);
+            }
+        }
+        cp_async_commit();
+    };
+    // this thread's R pieces: e = tg + 128 i -> (row, quad)
+    int prow[NPG_OWN], pkq[NPG_OWN], n_live = 0;
+#pragma unroll
+    for (int i = 0; i < NPG_OWN; ++i) {
+        const int e = tg + 128 * i;
+        prow[i] = e / lq;
+        pkq[i] = e % lq;
+        if (e < n_lp) n_live = i + 1;
+    }
+    // D = F32, A = TF32 from tensor memory, B = TF32 MN-major (bit 16), N >> 3, M = 128 >> 4
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(Npad >> 3) << 17) |
+                           ((uint32_t)(128 >> 4) << 24);
+    const uint32_t ahi = tmem + 128u + (uint32_t)(g * 64), alo = ahi + 32u;
+
+    issue(0);
+    for (int k = 0; k < mine; ++k) {
+        const long long row0 = (c_begin + g + (long long)k * G) * WG_ROWS;
+        const long long left = P - row0;
+        const int left32 = left < WG_ROWS ? (int)left : WG_ROWS;
+        const uint32_t rb = gb + 2 * r_tile + (uint32_t)(k & 1) * l_raw;
+        cp_async_wait<0>();
+        asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");   // chunk k has landed; everyone is done with chunk k - 1's rows
+        issue(k + 1);                             // into the other raw buffer: a whole turn of lead time
+        if (k > 0) mbar_wait(smem_u32(&s_mdone[g]), (uint32_t)((k - 1) & 1));   // tile + tensor-memory buffer free
+        tc_fence_after();
+        // ---- L: thread = channel ----
+        if (act) {
+            uint32_t la = rb + 4u * (uint32_t)ch;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                float y[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y[j]) : "r"(la));
+                    la += rowstep;
+                }
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float z = fmaf(cs, y[j], ct);
+                    const float v = 16 * hf + j < left32 ? fmaxf(z, z * slope) : 0.f;   // rows past P: nothing
+                    hi[j] = __float_as_uint(v) & 0xFFFFE000u;
+                    lo[j] = __float_as_uint(v - __uint_as_float(hi[j]));
+                }
+                tc_st16(tlane + 128u + (uint32_t)(g * 64 + 16 * hf), hi);
+                tc_st16(tlane + 128u + (uint32_t)(g * 64 + 32 + 16 * hf), lo);
+            }
+        }
+        // ---- R: [a | 1] tile, 16-byte pieces ----
+#pragma unroll
+        for (int i0 = 0; i0 < NPG_OWN; i0 += 3) {
+            float4 r0[3], t0[3], t1[3];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int i = i0 + u;
+                if (i < NPG_OWN && i < n_live) {
+                    r0[u] = lds4(rb + (uint32_t)prow[i] * rowstep + 16u * (uint32_t)pkq[i]);
+                    t0[u] = s_tab[0][pkq[i]];
+                    t1[u] = s_tab[1][pkq[i]];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int i = i0 + u;
+                if (i < NPG_OWN && i < n_live) {
+                    const WPar2 w = {t0[u], t1[u]};
+                    float4 v = bn_act_p(r0[u], w, slope);
+                    if (prow[i] >= left32) v = f4zero();
+                    const float x[4] = {v.x, v.y, v.z, v.w};
+                    uint32_t hi[4], lo[4];
+                    split_tf32_trunc<4>(x, hi, lo);
+                    const uint32_t o = gb + mn_off(prow[i], pkq[i]);
+                    sts4(o, hi[0], hi[1], hi[2], hi[3]);
+                    sts4(o + r_tile, lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+        }
+        if (left32 < WG_ROWS && tg < WG_ROWS)   // ragged last chunk: the ones column is 0 for the rows past P
+            sts4(gb + mn_off(tg, lq), tg < left32 ? 0x3F800000u : 0u, 0u, 0u, 0u);
+        fence_proxy_async();
+        tc_wait_st();
+        tc_fence_before();
+        asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
+        if (tg == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int kg = 0; kg < 4; ++kg) {
+                const uint32_t o = kg * 1024;
+                const uint64_t dRhi = umma_desc_mn(gb + o, WG_BLK, 512);
+                const uint64_t dRlo = umma_desc_mn(gb + r_tile + o, WG_BLK, 512);
+                tc_mma_tf32_ts(tmem, alo + kg * 8, dRhi, idesc, 1u);
+                tc_mma_tf32_ts(tmem, ahi + kg * 8, dRlo, idesc, 1u);
+                tc_mma_tf32_ts(tmem, ahi + kg * 8, dRhi, idesc, 1u);
+            }
+            tc_commit(smem_u32(&s_mdone[g]));
+        }
+    }
+    if (mine > 0) mbar_wait(smem_u32(&s_mdone[g]), (uint32_t)((mine - 1) & 1));
+    cp_async_wait<0>();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (total > 0) {
+        for (int c0 = g * 16; c0 < Npad; c0 += 16 * G) {
+            float v[16];
+            tc_ld16(tlane + (uint32_t)c0, v);
+            if (act) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < N) atomicAdd(out + (long long)ch * ldo + c0 + j, v[j]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+static bool wgrad_own_gram_fits(int M, int N, size_t &smem) {
+    const int Npad = (N + 15) & ~15;
+    const int MB = (M + 31) / 32, NB = (Npad + 31) / 32;
+    smem = 1024 + (size_t)kOwnG * (size_t)(2 * NB + 2 * MB) * WG_BLK;
+    return M <= 96 && M % 4 == 0 && N == M + 1 && Npad <= 128 && smem <= (size_t)(232448 - 2048);
+}
+
+static int launch_wgrad_own_gram(const PclRowGemm &a, long long P, int M, int N, float *out, int ldo, cudaStream_t st) {
+    size_t smem = 0;
+    wgrad_own_gram_fits(M, N, smem);
+    const long long n_chunks = (P + WG_ROWS - 1) / WG_ROWS;
+    const unsigned grid = (unsigned)(n_chunks < kNumSMs ? n_chunks : kNumSMs);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_own_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("pcl_wgrad(own gram): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    wgrad_own_gram_kernel<<<grid, kOwnThreads, smem, st>>>(a, P, M, N, out, ldo);
+    return check_launch("pcl_wgrad(own gram)");
+}
+
 static bool wgrad_own_fits(int M, int N, int r_width, bool mask, size_t &smem) {
     const int Npad = (N + 15) & ~15;
     const int MB = (M + 31) / 32, NB = (Npad + 31) / 32, NBlo = mask ? (r_width + 31) / 32 : NB;
@@ -1258,6 +1490,10 @@ int wgrad_ws_dispatch(const PclRowGemm &al, int pl, const PclRowGemm &ar, int pr
         if (wgrad_tl_plan(M, N, ar.K, pr == PCL_PRO_GATHER_BN_ACT_MASK, S_, DL_, smem))
             return pr == PCL_PRO_GATHER_BN_ACT_MASK ? launch_wgrad_tl<GGatherBnActMask>(al, ar, P, M, N, out, ldo, st)
                                                     : launch_wgrad_tl<GGatherBnAct>(al, ar, P, M, N, out, ldo, st);
+    }
+    if (gram_shares(al, pl, ar, pr, M) && !((al.c0 >> 16) & 2048)) {
+        size_t smem;   // chunk-owning warp groups (knob 2048: wgrad_ws_kernel)
+        if (wgrad_own_gram_fits(M, N, smem)) return launch_wgrad_own_gram(ar, P, M, N, out, ldo, st);
     }
     if (gram_shares(al, pl, ar, pr, M)) return launch_wgrad_ws<true, GBnAct, GBnActOnes>(al, ar, P, M, N, out, ldo, st);
     PCL_WS(PCL_PRO_BN_ACT, PCL_PRO_BN_ACT_ONES, GBnAct, GBnActOnes);

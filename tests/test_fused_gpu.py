@@ -54,6 +54,7 @@ def _rel(a, b):
     (2, 1024, 128, 0.4, 128, 3, (64, 96, 128)),
     (4, 512, 64, 0.4, 64, 320, (128, 128, 256)),
     (3, 300, 50, 0.3, 64, 5, (32, 64, 64)),        # ragged: P not a multiple of the 128-row tile
+    (3, 300, 25, 0.15, 16, 5, (32, 32, 64)),       # P = 1200: not a multiple of the 32-row chunk of the weight-gradient kernels
 ])
 # 4 = 3 + the opt-in fetch epilogues of rowgemm_ws.cu | tcgen05 warp-specialised | tcgen05 | mma.sync 3xTF32 | mma.sync TF32
 @pytest.mark.parametrize("mode", [4, 3, 2, 1, 0])

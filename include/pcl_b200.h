@@ -307,6 +307,11 @@ int pcl_sa_bwd_sums1(const float *W2, const float *dwm, const float *sc1, const 
  * ns = 2^j <= 128, C3*N*4 <= 2^24. */
 int pcl_routed_sort(const int32_t *selpos, const float *g3s, long long G, int C3, int ns, int N, int32_t *ent,
                     void *stream);
+/* The routed outer product of pcl_sel_outer from those ROW-ORDERED entry lists: T (C3,C2) += sum_e value_e *
+ * act(scale2*y2[row_e] + shift2), each row of y2 read once for all channels routed to it.  ent must have been made
+ * with N == C2.  C2 in {32, 64, 96, 128}, ns = 2^j <= 128, C3*C2*4 <= 200 KB. */
+int pcl_sel_outer_sorted(const int32_t *ent, const float *y2, const float *scale2, const float *shift2, float slope,
+                         long long G, int ns, int C3, int C2, float *T, void *stream);
 
 /* ---- a7 / a8: fused EdgeConv (networks/cls/dgcnn.py:29-50 + :72-83,100-111) -------------------
  * W.[x_j - x_i ; x_i] = W1.x_j + (W2-W1).x_i  =>  y[i,j] = u[src[i,j]] + vsign*v[i] on per-point

@@ -60,7 +60,8 @@ FUSED_SYMBOLS = ("pcl_rowgemm", "pcl_wgrad", "pcl_gather_stats", "pcl_bn_param",
                  "pcl_maxpool_finalize", "pcl_maxpool_backward", "pcl_sel_outer",
                  "pcl_gather_bn_backward", "pcl_gather_maxmin", "pcl_gather_bn_backward_routed",
                  "pcl_gather_bn_backward_masked", "pcl_bn_act_forward", "pcl_bn_act_backward", "pcl_bn_bwd_apply",
-                 "pcl_sa_bwd_prepare", "pcl_sa_bwd_finish", "pcl_sa_bwd_sums1", "pcl_routed_sort")
+                 "pcl_sa_bwd_prepare", "pcl_sa_bwd_finish", "pcl_sa_bwd_sums1", "pcl_routed_sort",
+                 "pcl_sel_outer_sorted")
 
 
 def declared_symbols(header: str = HEADER_PATH):

@@ -215,6 +215,80 @@ __global__ void __launch_bounds__(kSortWarps * 32) routed_sort_kernel(const int3
     }
 }
 
+// Routed outer product T (C3, C2) += sum over entries of value * a2[row, :], a2 = act(scale2*y2 + shift2), from the
+// ROW-ORDERED entry lists of pcl_routed_sort: a row of y2 is read ONCE for all the channels routed to it (the
+// per-entry gather of sel_outer_kernel reads it once per entry — 4x the rows on the ns = 32 branches, where a group
+// of 32 rows receives 128 entries).  One warp per group, lanes over channels (C2 = 32 NC); the distinct rows of a
+// 32-entry batch are found by ballot and fetched four at a time; T lives in shared memory (fp32 atomics, one row of
+// T per entry) and is added to global memory once per CTA.
+template <int NC>
+__global__ void __launch_bounds__(1024) sel_outer_sorted_kernel(const int2 *__restrict__ ent, const float *__restrict__ y2,
+                                                                const float *__restrict__ scale2,
+                                                                const float *__restrict__ shift2, float slope, long long G,
+                                                                int ns, int C3, float *__restrict__ T) {
+    extern __shared__ float s_T[];                          // (C3, C2)
+    constexpr int C2 = NC * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int e = threadIdx.x; e < C3 * C2; e += 1024) s_T[e] = 0.f;
+    float sc[NC], sh[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        sc[i] = __ldg(scale2 + lane + 32 * i);
+        sh[i] = __ldg(shift2 + lane + 32 * i);
+    }
+    __syncthreads();
+    for (long long g = (long long)blockIdx.x * 32 + warp; g < G; g += (long long)gridDim.x * 32) {
+        const int2 *e = ent + g * C3;
+        const float *ybase = y2 + g * ns * C2 + lane;
+        for (int j0 = 0; j0 < C3; j0 += 32) {
+            const int nvalid = C3 - j0 < 32 ? C3 - j0 : 32;
+            const int2 my = lane < nvalid ? __ldg(e + j0 + lane) : make_int2(0, 0);
+            const int myrow = (my.x >> 24) & (ns - 1);      // row inside the group
+            const int prev = __shfl_up_sync(0xffffffffu, myrow, 1);
+            const unsigned lead_all = __ballot_sync(0xffffffffu, lane < nvalid && (lane == 0 || myrow != prev));
+            unsigned lead = lead_all;
+            while (lead) {                                   // the distinct rows of this batch, four at a time
+                int l[4];
+                float y[4][NC];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    l[u] = -1;
+                    if (lead) {
+                        l[u] = __ffs(lead) - 1;
+                        lead &= lead - 1;
+                        const int r = __shfl_sync(0xffffffffu, myrow, l[u]);
+#pragma unroll
+                        for (int i = 0; i < NC; ++i) y[u][i] = __ldg(ybase + (long long)r * C2 + 32 * i);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (l[u] < 0) break;
+                    float a[NC];
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) {
+                        const float z = fmaf(sc[i], y[u][i], sh[i]);
+                        a[i] = z > 0.f ? z : z * slope;
+                    }
+                    const unsigned rest = l[u] == 31 ? 0u : lead_all & ~((2u << l[u]) - 1u);   // leaders behind this one
+                    const int end = rest ? __ffs(rest) - 1 : nvalid;
+                    for (int j = l[u]; j < end; ++j) {       // the entries routed to this row
+                        const int off = (__shfl_sync(0xffffffffu, my.x, j) & 0xFFFFFF) >> 2;   // float offset of T's row c3
+                        const float v = __int_as_float(__shfl_sync(0xffffffffu, my.y, j));
+#pragma unroll
+                        for (int i = 0; i < NC; ++i) atomicAdd(s_T + off + lane + 32 * i, v * a[i]);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < C3 * C2; e += 1024) {
+        const float v = s_T[e];
+        if (v != 0.f) atomicAdd(T + e, v);
+    }
+}
+
 }  // namespace pcl
 
 using namespace pcl;
@@ -265,4 +339,37 @@ extern "C" int pcl_routed_sort(const int32_t *selpos, const float *g3s, long lon
     routed_sort_kernel<<<(unsigned)((G + kSortWarps - 1) / kSortWarps), kSortWarps * 32, 0, (cudaStream_t)stream>>>(
         selpos, g3s, G, C3, ns, N, reinterpret_cast<int2 *>(ent));
     return check_launch("pcl_routed_sort");
+}
+
+extern "C" int pcl_sel_outer_sorted(const int32_t *ent, const float *y2, const float *scale2, const float *shift2, float slope,
+                                    long long G, int ns, int C3, int C2, float *T, void *stream) {
+    PCL_REQUIRE(ent && y2 && scale2 && shift2 && T, "pcl_sel_outer_sorted: null pointer");
+    PCL_REQUIRE(G >= 0 && C3 >= 1 && C2 >= 32 && C2 <= 128 && C2 % 32 == 0 && ns >= 1 && ns <= 128 && (ns & (ns - 1)) == 0 &&
+                    (size_t)C3 * C2 * 4 <= 200 * 1024,
+                "pcl_sel_outer_sorted: bad shape (C2 = 32..128 in steps of 32, ns = 2^j <= 128, C3*C2*4 <= 200 KB)");
+    if (G == 0) return PCL_OK;
+    const size_t smem = (size_t)C3 * C2 * 4;
+    const long long want = (G + 31) / 32;
+    const unsigned grid = (unsigned)(want < kNumSMs ? want : kNumSMs);
+    cudaError_t e = cudaSuccess;
+#define PCL_SOS(NC_)                                                                                          \
+    do {                                                                                                      \
+        auto kern = sel_outer_sorted_kernel<NC_>;                                                             \
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+        if (e == cudaSuccess)                                                                                 \
+            kern<<<grid, 1024, smem, (cudaStream_t)stream>>>(reinterpret_cast<const int2 *>(ent), y2, scale2, shift2, slope, \
+                                                             G, ns, C3, T);                                   \
+    } while (0)
+    switch (C2 / 32) {
+        case 1: PCL_SOS(1); break;
+        case 2: PCL_SOS(2); break;
+        case 3: PCL_SOS(3); break;
+        default: PCL_SOS(4); break;
+    }
+#undef PCL_SOS
+    if (e != cudaSuccess) {
+        set_error("pcl_sel_outer_sorted: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    return check_launch("pcl_sel_outer_sorted");
 }

@@ -75,6 +75,7 @@ def _bind():
         "pcl_sa_bwd_finish": [P, P, P, P, P, P, P, I, P, P, P, P, P, P, L, I, I, I, P, P, P, P, P],
         "pcl_sa_bwd_sums1": [P, P, P, P, P, P, L, I, I, P, P, P, P],
         "pcl_routed_sort": [P, P, L, I, I, I, P, P],
+        "pcl_sel_outer_sorted": [P, P, P, P, Fl, L, I, I, I, P, P],
     }
     for name, argtypes in sigs.items():
         fn = getattr(l, name)
@@ -87,7 +88,7 @@ SIGNATURE_NAMES = ("pcl_rowgemm", "pcl_wgrad", "pcl_gather_stats", "pcl_bn_param
                    "pcl_maxpool_finalize", "pcl_maxpool_backward", "pcl_sel_outer",
                    "pcl_gather_bn_backward", "pcl_gather_maxmin", "pcl_gather_bn_backward_routed",
                    "pcl_gather_bn_backward_masked", "pcl_bn_act_forward", "pcl_bn_act_backward", "pcl_bn_bwd_apply",
-                   "pcl_sa_bwd_prepare", "pcl_sa_bwd_finish", "pcl_sa_bwd_sums1", "pcl_routed_sort")
+                   "pcl_sa_bwd_prepare", "pcl_sa_bwd_finish", "pcl_sa_bwd_sums1", "pcl_routed_sort", "pcl_sel_outer_sorted")
 
 
 def _args(**kw):
@@ -136,6 +137,7 @@ MASK_STASH = 1   # 0: last-layer backward row GEMM on the round-1 kernel (re-rea
 # 4 entries per output channel (measured faster there, profiles/r02/sa_b3_ab_r02.txt), 2 = wherever supported,
 # 0 = always the one-hot K block (PCL_PRO_G3_A2)
 ROUTED_PRELOAD = int(__import__("os").environ.get("PCL_ROUTED_PRELOAD", "1"))
+SORTED_OUTER = int(__import__("os").environ.get("PCL_SORTED_OUTER", "1"))   # 0: per-entry gather (pcl_sel_outer) for A/B runs
 PROF_BUF = None   # profiling (knob 16384 of rowgemm_ws2.cu): a 64-byte CUDA tensor that receives phase cycle counters
 WS_DBG = 0   # profiling knobs of rowgemm_ws.cu (scratch/ws_branch_knobs.py); 0 in production
 WS_FETCH_EPI = 0   # 1: also route the BWD_Y / BWD_GATHER epilogues to rowgemm_ws.cu (slower today)
@@ -281,10 +283,27 @@ class FusedSAFn(torch.autograd.Function):
         T = torch.zeros((C3, C2), **f32)
         a2kw = dict(x0=y2, scale=sc2, shift=sh2, slope=slope, K=C2)
 
+        # the routed entries ordered by row (pcl_routed_sort): consumed by the row-ordered outer product and by the
+        # pre-load form of the last-layer backward
+        ent = None
+        want_sorted = (SORTED_OUTER > 1 or (SORTED_OUTER and C3 >= 4 * ns)) and C2 % 32 == 0 and C2 <= 128
+        want_preload = ROUTED_PRELOAD and C3 % 32 == 0 and (ROUTED_PRELOAD > 1 or (128 // max(ns, 1)) * C3 <= 4 * C2)
+        if (want_sorted or want_preload) and MODE == 3 and ns <= 128 and ns & (ns - 1) == 0 and C3 * C2 * 4 <= 1 << 24:
+            ent = torch.empty((G, C3, 2), dtype=torch.int32, device=dev)
+            _lib.call("pcl_routed_sort", ptr(selpos), ptr(g3s), G, C3, ns, C2, ptr(ent), stream(g3s),
+                      key=("sa_routed_sort", G, C3))
+
         def gram_and_routed_outer():
             wgrad(PRO_BN_ACT, a2kw, PRO_BN_ACT_ONES, a2kw, P, C2, C2 + 1, gram, name="sa_gram")
-            _lib.call("pcl_sel_outer", ptr(g3s), ptr(selpos), ptr(y2), ptr(sc2), ptr(sh2), float(slope), G,
-                      ns, C3, C2, ptr(T), stream(g3s), key=("sa_sel_outer", G, C3, C2))
+            # row-ordered form where a row receives several entries (C3 >= 4 ns: measured 104 -> 50, 232 -> 156, 63 -> 36 us;
+            # at one or two entries per row the per-entry gather is as fast or faster: 267 vs 310 us at ns = 128)
+            if (SORTED_OUTER and ent is not None and C2 % 32 == 0 and C2 <= 128 and C3 * C2 * 4 <= 200 * 1024
+                    and (SORTED_OUTER > 1 or C3 >= 4 * ns)):
+                _lib.call("pcl_sel_outer_sorted", ptr(ent), ptr(y2), ptr(sc2), ptr(sh2), float(slope), G, ns, C3, C2,
+                          ptr(T), stream(g3s), key=("sa_sel_outer", G, C3, C2))
+            else:
+                _lib.call("pcl_sel_outer", ptr(g3s), ptr(selpos), ptr(y2), ptr(sc2), ptr(sh2), float(slope), G,
+                          ns, C3, C2, ptr(T), stream(g3s), key=("sa_sel_outer", G, C3, C2))
 
         if use_mask:
             # -- the small fp64 algebra (Q, const, the packed [W3^T | -Q^T] weight) in ONE kernel (sa_algebra.cu)
@@ -299,13 +318,10 @@ class FusedSAFn(torch.autograd.Function):
             # -- da2 -> dyhat2 on the warp-specialised kernel: the routed gradient enters as a one-hot K block, the
             # ReLU mask comes from the operand tile the kernel stages itself; its epilogue reads nothing of size
             # (P, C2) and accumulates sum(dyhat2) only
-            if (ROUTED_PRELOAD and C3 % 32 == 0 and ns <= 128 and (128 // ns) * C3 <= 512
+            if (ROUTED_PRELOAD and ent is not None and C3 % 32 == 0 and (128 // ns) * C3 <= 512
                     and (ROUTED_PRELOAD > 1 or (128 // ns) * C3 <= 4 * C2)):
                 # the routed term as sorted entry lists that the kernel's epilogue warps sum into the tensor-memory
                 # accumulator before the tile's MMAs (-a2.Q, K = C2) run: no one-hot K block
-                ent = torch.empty((G, C3, 2), dtype=torch.int32, device=dev)
-                _lib.call("pcl_routed_sort", ptr(selpos), ptr(g3s), G, C3, ns, C2, ptr(ent), stream(g3s),
-                          key=("sa_routed_sort", G, C3))
                 rowgemm(PRO_BN_ACT, EPI_BWD_Y_MASK_ROUTED, "sa_b3", x0=y2, W=(Wb, C3), x1=W3f, selpos=ent,
                         C3=C3, ns=ns, scale=sc2, shift=sh2, slope=0.0, P=P, K=C2, N=C2, ldw=ld, out=dyh2,
                         stats=sums2, ebias=constf, eslope=0.0, gmin=PROF_BUF)
